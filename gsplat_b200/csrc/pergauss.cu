@@ -1,0 +1,992 @@
+// pergauss.cu -- the per-gaussian (HBM-bound) kernels: quat/scale -> covariance, EWA projection,
+// spherical harmonics, the fused projection + conic + SH->RGB pass, tile counting / emission and
+// the tile-offset encoder.  Compiled with -fmad=false (see gaussmath.cuh).
+//
+// Reference kernels replaced: csrc/QuatScaleToCovarCUDA.cu:37,211;
+// csrc/ProjectionEWA3DGSFused.cu:38-219,376-638; csrc/SphericalHarmonicsCUDA.cu:443-569,785-890,
+// 1085-1250 (assemble_proj_features); csrc/IntersectTile.cu:83-464,925-988.
+#include <cub/device/device_scan.cuh>
+
+#include "gaussmath.cuh"
+
+namespace gsb
+{
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------ quat_scale_to_covar_preci
+__device__ __forceinline__ void store_sym(float *dst, const M3 &S, bool triu)
+{
+    if(triu)
+    {
+        dst[0] = S.m[0], dst[1] = S.m[1], dst[2] = S.m[2], dst[3] = S.m[4], dst[4] = S.m[5], dst[5] = S.m[8];
+    }
+    else
+    {
+#pragma unroll
+        for(int k = 0; k < 9; ++k)
+            dst[k] = S.m[k];
+    }
+}
+__device__ __forceinline__ M3 load_sym_grad(const float *v, bool triu)
+{
+    M3 G;
+    if(triu)
+    {
+        G.m[0] = v[0];
+        G.m[1] = G.m[3] = v[1] * 0.5f;
+        G.m[2] = G.m[6] = v[2] * 0.5f;
+        G.m[4] = v[3];
+        G.m[5] = G.m[7] = v[4] * 0.5f;
+        G.m[8] = v[5];
+    }
+    else
+    {
+#pragma unroll
+        for(int k = 0; k < 9; ++k)
+            G.m[k] = v[k];
+    }
+    return G;
+}
+
+__global__ void __launch_bounds__(kThreads) quat_scale_fwd_kernel(
+    int64_t N, const float *__restrict__ quats, const float *__restrict__ scales, bool triu, float *__restrict__ covars,
+    float *__restrict__ precis
+)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= N)
+        return;
+    const float q[4] = {quats[n * 4], quats[n * 4 + 1], quats[n * 4 + 2], quats[n * 4 + 3]};
+    const float s[3] = {scales[n * 3], scales[n * 3 + 1], scales[n * 3 + 2]};
+    const int stride = triu ? 6 : 9;
+    if(covars)
+        store_sym(covars + n * stride, quat_scale_to_sym<false>(q, s), triu);
+    if(precis)
+        store_sym(precis + n * stride, quat_scale_to_sym<true>(q, s), triu);
+}
+
+__global__ void __launch_bounds__(kThreads) quat_scale_bwd_kernel(
+    int64_t N, const float *__restrict__ quats, const float *__restrict__ scales, bool triu,
+    const float *__restrict__ v_covars, const float *__restrict__ v_precis, float *__restrict__ v_quats,
+    float *__restrict__ v_scales
+)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= N)
+        return;
+    const float q[4] = {quats[n * 4], quats[n * 4 + 1], quats[n * 4 + 2], quats[n * 4 + 3]};
+    const float s[3] = {scales[n * 3], scales[n * 3 + 1], scales[n * 3 + 2]};
+    const int stride = triu ? 6 : 9;
+    float vq[4] = {0.f, 0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
+    if(v_covars)
+        quat_scale_sym_vjp<false>(q, s, load_sym_grad(v_covars + n * stride, triu), vq, vs);
+    if(v_precis)
+        quat_scale_sym_vjp<true>(q, s, load_sym_grad(v_precis + n * stride, triu), vq, vs);
+#pragma unroll
+    for(int k = 0; k < 4; ++k)
+        v_quats[n * 4 + k] = vq[k];
+#pragma unroll
+    for(int k = 0; k < 3; ++k)
+        v_scales[n * 3 + k] = vs[k];
+}
+
+// ------------------------------------------------------------------ projection
+__device__ __forceinline__ M3 load_cov6(const float *c6)
+{
+    M3 S;
+    S.m[0] = c6[0];
+    S.m[1] = S.m[3] = c6[1];
+    S.m[2] = S.m[6] = c6[2];
+    S.m[4] = c6[3];
+    S.m[5] = S.m[7] = c6[4];
+    S.m[8] = c6[5];
+    return S;
+}
+
+__global__ void __launch_bounds__(kThreads) projection_fwd_kernel(
+    int64_t B, int64_t C, int64_t N, const float *__restrict__ means, const float *__restrict__ covars,
+    const float *__restrict__ quats, const float *__restrict__ scales, const float *__restrict__ opacities,
+    const float *__restrict__ viewmats, const float *__restrict__ Ks, uint32_t W, uint32_t H, float eps2d,
+    float near_plane, float far_plane, float radius_clip, int32_t *__restrict__ radii, float *__restrict__ means2d,
+    float *__restrict__ depths, float *__restrict__ conics, float *__restrict__ compensations
+)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(idx >= B * C * N)
+        return;
+    const int64_t b = idx / (C * N), c = (idx / N) % C, n = idx % N;
+    const int64_t bn = b * N + n;
+    const Cam cam = load_cam(viewmats + (b * C + c) * 16, Ks + (b * C + c) * 9);
+    const float mean[3] = {means[bn * 3], means[bn * 3 + 1], means[bn * 3 + 2]};
+    M3 cov;
+    if(covars)
+        cov = load_cov6(covars + bn * 6);
+    else
+    {
+        const float q[4] = {quats[bn * 4], quats[bn * 4 + 1], quats[bn * 4 + 2], quats[bn * 4 + 3]};
+        const float s[3] = {scales[bn * 3], scales[bn * 3 + 1], scales[bn * 3 + 2]};
+        cov = quat_scale_to_sym<false>(q, s);
+    }
+    float op = 0.f;
+    if(opacities)
+        op = opacities[bn];
+    const Proj p = project_one(
+        mean, cov, opacities ? &op : nullptr, cam, W, H, eps2d, near_plane, far_plane, radius_clip, compensations != nullptr
+    );
+    reinterpret_cast<int2 *>(radii)[idx]    = make_int2(p.rx, p.ry);
+    reinterpret_cast<float2 *>(means2d)[idx] = make_float2(p.mx, p.my);
+    depths[idx]         = p.depth;
+    conics[idx * 3]     = p.ca;
+    conics[idx * 3 + 1] = p.cb;
+    conics[idx * 3 + 2] = p.cc;
+    if(compensations)
+        compensations[idx] = p.comp;
+}
+
+// One thread per (b, n), looping over the C cameras: the per-gaussian sums stay in registers and
+// every output row is written exactly once (deterministic, no zero-init, no atomics).
+__global__ void __launch_bounds__(kThreads) projection_bwd_kernel(
+    int64_t B, int64_t C, int64_t N, const float *__restrict__ means, const float *__restrict__ covars,
+    const float *__restrict__ quats, const float *__restrict__ scales, const float *__restrict__ viewmats,
+    const float *__restrict__ Ks, uint32_t W, uint32_t H, float eps2d, const int32_t *__restrict__ radii,
+    const float *__restrict__ conics, const float *__restrict__ compensations, const float *__restrict__ v_means2d,
+    int64_t s_m2, const float *__restrict__ v_depths, int64_t s_d, const float *__restrict__ v_conics, int64_t s_c,
+    const float *__restrict__ v_compensations, float *__restrict__ v_means, float *__restrict__ v_covars,
+    float *__restrict__ v_quats, float *__restrict__ v_scales, float *__restrict__ v_viewmats
+)
+{
+    const int64_t bn   = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active  = bn < B * N;
+    const int64_t b    = active ? bn / N : 0, n = active ? bn % N : 0;
+    const unsigned lane = threadIdx.x & 31;
+    float mean[3] = {0.f, 0.f, 0.f}, q[4] = {1.f, 0.f, 0.f, 0.f}, s[3] = {1.f, 1.f, 1.f};
+    M3 cov;
+#pragma unroll
+    for(int k = 0; k < 9; ++k)
+        cov.m[k] = 0.f;
+    if(active)
+    {
+        mean[0] = means[bn * 3], mean[1] = means[bn * 3 + 1], mean[2] = means[bn * 3 + 2];
+        if(covars)
+            cov = load_cov6(covars + bn * 6);
+        else
+        {
+#pragma unroll
+            for(int k = 0; k < 4; ++k)
+                q[k] = quats[bn * 4 + k];
+#pragma unroll
+            for(int k = 0; k < 3; ++k)
+                s[k] = scales[bn * 3 + k];
+            cov = quat_scale_to_sym<false>(q, s);
+        }
+    }
+    float v_mean[3] = {0.f, 0.f, 0.f};
+    M3 v_cov;
+#pragma unroll
+    for(int k = 0; k < 9; ++k)
+        v_cov.m[k] = 0.f;
+    for(int64_t c = 0; c < C; ++c)
+    {
+        const int64_t idx = (b * C + c) * N + n;
+        const bool vis    = active && radii[idx * 2] > 0 && radii[idx * 2 + 1] > 0;
+        float vm_part[12];
+#pragma unroll
+        for(int k = 0; k < 12; ++k)
+            vm_part[k] = 0.f;
+        if(vis)
+        {
+            const Cam cam       = load_cam(viewmats + (b * C + c) * 16, Ks + (b * C + c) * 9);
+            const float conic[3] = {conics[idx * 3], conics[idx * 3 + 1], conics[idx * 3 + 2]};
+            const float vc[3]    = {v_conics[idx * s_c], v_conics[idx * s_c + 1], v_conics[idx * s_c + 2]};
+            const bool has_comp  = v_compensations != nullptr;
+            const ProjGrad g     = project_one_vjp(
+                mean, cov, cam, W, H, eps2d, conic, v_means2d[idx * s_m2], v_means2d[idx * s_m2 + 1], v_depths[idx * s_d],
+                vc, has_comp, has_comp ? compensations[idx] : 0.f, has_comp ? v_compensations[idx] : 0.f
+            );
+#pragma unroll
+            for(int k = 0; k < 3; ++k)
+                v_mean[k] += g.v_mean[k];
+#pragma unroll
+            for(int k = 0; k < 9; ++k)
+                v_cov.m[k] += g.v_cov.m[k];
+            if(v_viewmats)
+            { // v_R = v_pc mean^T + v_covc R cov^T + v_covc^T R cov ; v_t = v_pc
+                const M3 A2 = mul_bt(mul(g.v_covc, cam.R), cov);
+                const M3 B2 = mul(mul_at(g.v_covc, cam.R), cov);
+#pragma unroll
+                for(int i = 0; i < 3; ++i)
+                {
+#pragma unroll
+                    for(int j = 0; j < 3; ++j)
+                        vm_part[i * 4 + j] = g.v_pc[i] * mean[j] + A2.m[i * 3 + j] + B2.m[i * 3 + j];
+                    vm_part[i * 4 + 3] = g.v_pc[i];
+                }
+            }
+        }
+        if(v_viewmats)
+        { // warp butterfly reduce of the 12 pose-gradient entries, one atomic per owning lane
+            Butterfly<12, 16>::run(vm_part, lane);
+            const int slot = butterfly_slot<12>(lane);
+            if(slot >= 0 && vm_part[0] != 0.f)
+                atomicAdd(v_viewmats + (b * C + c) * 16 + slot, vm_part[0]);
+        }
+    }
+    if(!active)
+        return;
+#pragma unroll
+    for(int k = 0; k < 3; ++k)
+        v_means[bn * 3 + k] = v_mean[k];
+    if(covars)
+    {
+        float *o = v_covars + bn * 6;
+        o[0] = v_cov.m[0];
+        o[1] = v_cov.m[1] + v_cov.m[3];
+        o[2] = v_cov.m[2] + v_cov.m[6];
+        o[3] = v_cov.m[4];
+        o[4] = v_cov.m[5] + v_cov.m[7];
+        o[5] = v_cov.m[8];
+    }
+    else
+    {
+        float vq[4] = {0.f, 0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
+        quat_scale_sym_vjp<false>(q, s, v_cov, vq, vs);
+#pragma unroll
+        for(int k = 0; k < 4; ++k)
+            v_quats[bn * 4 + k] = vq[k];
+#pragma unroll
+        for(int k = 0; k < 3; ++k)
+            v_scales[bn * 3 + k] = vs[k];
+    }
+}
+
+// ------------------------------------------------------------------ spherical harmonics
+template<int DEG>
+__global__ void __launch_bounds__(kThreads) sh_fwd_kernel(
+    int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, const float *__restrict__ means,
+    const float *__restrict__ viewmats, const float *__restrict__ coeffs, const uint8_t *__restrict__ masks,
+    float *__restrict__ colors
+)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(idx >= B * C * N)
+        return;
+    const int64_t b = idx / (C * N), c = (idx / N) % C, n = idx % N;
+    float *out = colors + idx * D;
+    if(masks && !masks[idx])
+    {
+        for(int64_t d = 0; d < D; ++d)
+            out[d] = 0.f;
+        return;
+    }
+    const float mean[3] = {means[(b * N + n) * 3], means[(b * N + n) * 3 + 1], means[(b * N + n) * 3 + 2]};
+    float dir[3];
+    sh_view_dir(mean, viewmats + (b * C + c) * 16, dir);
+    const float inorm = 1.f / sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    constexpr int NB  = (DEG + 1) * (DEG + 1);
+    Dual<false> Y[NB];
+    sh_basis<DEG, false>(dir[0] * inorm, dir[1] * inorm, dir[2] * inorm, Y);
+    const float *cf = coeffs + n * K * D;
+    for(int64_t d = 0; d < D; ++d)
+    {
+        float acc = 0.f;
+#pragma unroll
+        for(int k = 0; k < NB; ++k)
+            acc += Y[k].v * cf[k * D + d];
+        out[d] = acc;
+    }
+}
+
+// one thread per (gaussian, channel), looping over images; v_coeffs written once per thread,
+// v_means accumulated with atomics (pre-zeroed by the host wrapper).
+template<int DEG>
+__global__ void __launch_bounds__(kThreads) sh_bwd_kernel(
+    int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, const float *__restrict__ means,
+    const float *__restrict__ viewmats, const float *__restrict__ coeffs, const uint8_t *__restrict__ masks,
+    const float *__restrict__ v_colors, float *__restrict__ v_coeffs, float *__restrict__ v_means
+)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(idx >= N * D)
+        return;
+    const int64_t n = idx / D, d = idx % D;
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    float acc[NB];
+#pragma unroll
+    for(int k = 0; k < NB; ++k)
+        acc[k] = 0.f;
+    const float *cf = coeffs + n * K * D;
+    for(int64_t img = 0; img < B * C; ++img)
+    {
+        const int64_t b = img / C;
+        const int64_t o = img * N + n;
+        if(masks && !masks[o])
+            continue;
+        const float *mean = means + (b * N + n) * 3;
+        float dir[3];
+        sh_view_dir(mean, viewmats + img * 16, dir);
+        const float inorm = 1.f / sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+        const float u[3]  = {dir[0] * inorm, dir[1] * inorm, dir[2] * inorm};
+        Dual<true> Y[NB];
+        sh_basis<DEG, true>(u[0], u[1], u[2], Y);
+        const float vc = v_colors[o * D + d];
+        float vu[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for(int k = 0; k < NB; ++k)
+        {
+            acc[k] += Y[k].v * vc;
+            const float g = cf[k * D + d] * vc;
+            vu[0] += g * Y[k].x;
+            vu[1] += g * Y[k].y;
+            vu[2] += g * Y[k].z;
+        }
+        if(v_means != nullptr && DEG >= 1)
+        {
+            const float dot = vu[0] * u[0] + vu[1] * u[1] + vu[2] * u[2];
+#pragma unroll
+            for(int j = 0; j < 3; ++j)
+                atomicAdd(v_means + (b * N + n) * 3 + j, (vu[j] - dot * u[j]) * inorm);
+        }
+    }
+    float *vcf = v_coeffs + n * K * D;
+#pragma unroll
+    for(int k = 0; k < NB; ++k)
+        vcf[k * D + d] = acc[k];
+    for(int64_t k = NB; k < K; ++k)
+        vcf[k * D + d] = 0.f;
+}
+
+// ------------------------------------------------------------------ fused projection + conic + SH -> RGB
+// One thread per (camera, gaussian).  SH coefficients of a visible gaussian are fetched with 128-bit
+// loads (48 floats = 12 x float4 when K = 16); culled gaussians never touch them.
+template<int DEG>
+__global__ void __launch_bounds__(kThreads) project_sh_fwd_kernel(
+    int64_t C, int64_t N, int64_t K, const float *__restrict__ means, const float *__restrict__ quats,
+    const float *__restrict__ scales, const float *__restrict__ opacities, const float *__restrict__ sh,
+    const float *__restrict__ viewmats, const float *__restrict__ Ks, uint32_t W, uint32_t H, float eps2d,
+    float near_plane, float far_plane, float radius_clip, int32_t *__restrict__ radii, float *__restrict__ means2d,
+    float *__restrict__ depths, float *__restrict__ conics, float *__restrict__ compensations,
+    float *__restrict__ colors
+)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(idx >= C * N)
+        return;
+    const int64_t c = idx / N, n = idx % N;
+    const float *vm = viewmats + c * 16;
+    const Cam cam   = load_cam(vm, Ks + c * 9);
+    const float mean[3] = {means[n * 3], means[n * 3 + 1], means[n * 3 + 2]};
+    const float4 q4     = *reinterpret_cast<const float4 *>(quats + n * 4);
+    const float q[4]    = {q4.x, q4.y, q4.z, q4.w};
+    const float s[3]    = {scales[n * 3], scales[n * 3 + 1], scales[n * 3 + 2]};
+    const float op      = opacities[n];
+    const M3 cov        = quat_scale_to_sym<false>(q, s);
+    const Proj p = project_one(mean, cov, &op, cam, W, H, eps2d, near_plane, far_plane, radius_clip, compensations != nullptr);
+    reinterpret_cast<int2 *>(radii)[idx]     = make_int2(p.rx, p.ry);
+    reinterpret_cast<float2 *>(means2d)[idx] = make_float2(p.mx, p.my);
+    depths[idx]         = p.depth;
+    conics[idx * 3]     = p.ca;
+    conics[idx * 3 + 1] = p.cb;
+    conics[idx * 3 + 2] = p.cc;
+    if(compensations)
+        compensations[idx] = p.comp;
+    float rgb[3] = {0.f, 0.f, 0.f};
+    if(p.rx > 0 && p.ry > 0)
+    {
+        float dir[3];
+        sh_view_dir(mean, vm, dir);
+        const float inorm = 1.f / sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+        constexpr int NB  = (DEG + 1) * (DEG + 1);
+        Dual<false> Y[NB];
+        sh_basis<DEG, false>(dir[0] * inorm, dir[1] * inorm, dir[2] * inorm, Y);
+        const float *cf = sh + n * K * 3;
+        float cbuf[NB * 3];
+        if(((K * 3) & 3) == 0 && (NB * 3) % 4 == 0)
+        { // 16-byte aligned rows: 128-bit read-only loads
+            const float4 *cf4 = reinterpret_cast<const float4 *>(cf);
+#pragma unroll
+            for(int v = 0; v < NB * 3 / 4; ++v)
+            {
+                const float4 t = ldg_nc_f4(cf4 + v);
+                cbuf[4 * v] = t.x, cbuf[4 * v + 1] = t.y, cbuf[4 * v + 2] = t.z, cbuf[4 * v + 3] = t.w;
+            }
+        }
+        else
+        {
+#pragma unroll
+            for(int k = 0; k < NB * 3; ++k)
+                cbuf[k] = __ldg(cf + k);
+        }
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+        {
+            float acc = 0.f;
+#pragma unroll
+            for(int k = 0; k < NB; ++k)
+                acc += Y[k].v * cbuf[k * 3 + d];
+            const float shifted = acc + 0.5f;
+            rgb[d]              = shifted > 0.f ? shifted : 0.f;
+        }
+    }
+    colors[idx * 3] = rgb[0], colors[idx * 3 + 1] = rgb[1], colors[idx * 3 + 2] = rgb[2];
+}
+
+// One thread per gaussian, looping over cameras: v_means / v_quats / v_scales / v_sh written once.
+template<int DEG>
+__global__ void __launch_bounds__(kThreads) project_sh_bwd_kernel(
+    int64_t C, int64_t N, int64_t K, const float *__restrict__ means, const float *__restrict__ quats,
+    const float *__restrict__ scales, const float *__restrict__ sh, const float *__restrict__ viewmats,
+    const float *__restrict__ Ks, uint32_t W, uint32_t H, float eps2d, const int32_t *__restrict__ radii,
+    const float *__restrict__ conics, const float *__restrict__ compensations, const float *__restrict__ colors,
+    const float *__restrict__ v_means2d, int64_t s_m2, const float *__restrict__ v_depths, int64_t s_d,
+    const float *__restrict__ v_conics, int64_t s_c, const float *__restrict__ v_colors, int64_t s_col,
+    const float *__restrict__ v_compensations, float *__restrict__ v_means, float *__restrict__ v_quats,
+    float *__restrict__ v_scales, float *__restrict__ v_sh
+)
+{
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(n >= N)
+        return;
+    constexpr int NB    = (DEG + 1) * (DEG + 1);
+    const float mean[3] = {means[n * 3], means[n * 3 + 1], means[n * 3 + 2]};
+    const float4 q4     = *reinterpret_cast<const float4 *>(quats + n * 4);
+    const float q[4]    = {q4.x, q4.y, q4.z, q4.w};
+    const float s[3]    = {scales[n * 3], scales[n * 3 + 1], scales[n * 3 + 2]};
+    const M3 cov        = quat_scale_to_sym<false>(q, s);
+    float v_mean[3] = {0.f, 0.f, 0.f};
+    M3 v_cov;
+#pragma unroll
+    for(int k = 0; k < 9; ++k)
+        v_cov.m[k] = 0.f;
+    float acc[NB * 3];
+#pragma unroll
+    for(int k = 0; k < NB * 3; ++k)
+        acc[k] = 0.f;
+    const float *cf = sh + n * K * 3;
+    for(int64_t c = 0; c < C; ++c)
+    {
+        const int64_t idx = c * N + n;
+        if(!(radii[idx * 2] > 0 && radii[idx * 2 + 1] > 0))
+            continue;
+        const float *vm      = viewmats + c * 16;
+        const Cam cam        = load_cam(vm, Ks + c * 9);
+        const float conic[3] = {conics[idx * 3], conics[idx * 3 + 1], conics[idx * 3 + 2]};
+        const float vc[3]    = {v_conics[idx * s_c], v_conics[idx * s_c + 1], v_conics[idx * s_c + 2]};
+        const bool has_comp  = v_compensations != nullptr;
+        const ProjGrad g     = project_one_vjp(
+            mean, cov, cam, W, H, eps2d, conic, v_means2d[idx * s_m2], v_means2d[idx * s_m2 + 1], v_depths ? v_depths[idx * s_d] : 0.f,
+            vc, has_comp, has_comp ? compensations[idx] : 0.f, has_comp ? v_compensations[idx] : 0.f
+        );
+#pragma unroll
+        for(int k = 0; k < 3; ++k)
+            v_mean[k] += g.v_mean[k];
+#pragma unroll
+        for(int k = 0; k < 9; ++k)
+            v_cov.m[k] += g.v_cov.m[k];
+        // SH part: relu mask re-derived from the stored post-activation colour
+        float vcol[3];
+#pragma unroll
+        for(int d = 0; d < 3; ++d)
+            vcol[d] = colors[idx * 3 + d] > 0.f ? v_colors[idx * s_col + d] : 0.f;
+        float dir[3];
+        sh_view_dir(mean, vm, dir);
+        const float inorm = 1.f / sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+        const float u[3]  = {dir[0] * inorm, dir[1] * inorm, dir[2] * inorm};
+        Dual<true> Y[NB];
+        sh_basis<DEG, true>(u[0], u[1], u[2], Y);
+        float vu[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for(int k = 0; k < NB; ++k)
+        {
+            float gk = 0.f;
+#pragma unroll
+            for(int d = 0; d < 3; ++d)
+            {
+                acc[k * 3 + d] += Y[k].v * vcol[d];
+                gk += __ldg(cf + k * 3 + d) * vcol[d];
+            }
+            vu[0] += gk * Y[k].x;
+            vu[1] += gk * Y[k].y;
+            vu[2] += gk * Y[k].z;
+        }
+        if(DEG >= 1)
+        {
+            const float dot = vu[0] * u[0] + vu[1] * u[1] + vu[2] * u[2];
+#pragma unroll
+            for(int j = 0; j < 3; ++j)
+                v_mean[j] += (vu[j] - dot * u[j]) * inorm;
+        }
+    }
+#pragma unroll
+    for(int k = 0; k < 3; ++k)
+        v_means[n * 3 + k] = v_mean[k];
+    float vq[4] = {0.f, 0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
+    quat_scale_sym_vjp<false>(q, s, v_cov, vq, vs);
+    *reinterpret_cast<float4 *>(v_quats + n * 4) = make_float4(vq[0], vq[1], vq[2], vq[3]);
+#pragma unroll
+    for(int k = 0; k < 3; ++k)
+        v_scales[n * 3 + k] = vs[k];
+    float *vsh = v_sh + n * K * 3;
+    if(((K * 3) & 3) == 0 && (NB * 3) % 4 == 0)
+    {
+#pragma unroll
+        for(int v = 0; v < NB * 3 / 4; ++v)
+            reinterpret_cast<float4 *>(vsh)[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+    }
+    else
+    {
+#pragma unroll
+        for(int k = 0; k < NB * 3; ++k)
+            vsh[k] = acc[k];
+    }
+    for(int64_t k = NB * 3; k < K * 3; ++k)
+        vsh[k] = 0.f;
+}
+
+// ------------------------------------------------------------------ tile intersection
+// Enumerates the tiles of one gaussian in the reference's emit order, calling f(tile_id).
+// AccuTile / SNUGBOX (csrc/IntersectTile.cu:83-207, 288-373) or the radius AABB (:374-463).
+template<class F>
+__device__ __forceinline__ int tiles_of_gaussian(
+    float mx, float my, int rx, int ry, const float *conic, const float *opacity, uint32_t tile_size, uint32_t tw,
+    uint32_t th, F &&f
+)
+{
+    if(rx <= 0 || ry <= 0)
+        return 0;
+    int count      = 0;
+    const float ts = (float)tile_size;
+    auto clampi    = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    if(conic != nullptr && opacity != nullptr)
+    {
+        const float A = conic[0], Bc = conic[1], Cc = conic[2];
+        const float disc = Bc * Bc - A * Cc;
+        float t          = 2.f * exact_log(*opacity / kAlphaThreshold);
+        const float cap  = kGaussianExtend * kGaussianExtend;
+        t                = t < cap ? t : cap;
+        const float ntd  = -t / disc;
+        const float xe = sqrtf(ntd * Cc), ye = sqrtf(ntd * A);
+        const float bminx = mx - xe, bminy = my - ye, bmaxx = mx + xe, bmaxy = my + ye;
+        const float BxC = Bc * xe / Cc, ByA = Bc * ye / A;
+        const float argminx = my + BxC, argminy = mx + ByA, argmaxx = my - BxC, argmaxy = mx - ByA;
+        const int rminx = clampi((int)(bminx / ts), 0, (int)tw), rminy = clampi((int)(bminy / ts), 0, (int)th);
+        const int rmaxx = clampi((int)(bmaxx / ts + 1.f), 0, (int)tw), rmaxy = clampi((int)(bmaxy / ts + 1.f), 0, (int)th);
+        const int ys = rmaxy - rminy, xs = rmaxx - rminx;
+        if(ys * xs == 0)
+            return 0;
+        const bool isY = ys < xs;
+        const int ru0 = isY ? rminy : rminx, ru1 = isY ? rmaxy : rmaxx, rv0 = isY ? rminx : rminy, rv1 = isY ? rmaxx : rmaxy;
+        const float bminu = isY ? bminy : bminx, bmaxu = isY ? bmaxy : bmaxx;
+        const float bminv = isY ? bminx : bminy, bmaxv = isY ? bmaxx : bmaxy;
+        const float amin_v = isY ? argminx : argminy, amax_v = isY ? argmaxx : argmaxy;
+        const float pu = isY ? my : mx, pv = isY ? mx : my, coeff = isY ? A : Cc;
+        auto line = [&](float coord, float &lo, float &hi) {
+            const float h  = coord - pu;
+            const float sq = sqrtf(disc * h * h + t * coeff);
+            lo             = (-Bc * h - sq) / coeff + pv;
+            hi             = (-Bc * h + sq) / coeff + pv;
+        };
+        float maxlo = bmaxv, maxhi = bminv, minlo, minhi;
+        float min_line = (float)ru0 * ts;
+        if(bminu <= min_line)
+            line(min_line, minlo, minhi);
+        else
+            minlo = maxlo, minhi = maxhi;
+        for(int u = ru0; u < ru1; ++u)
+        {
+            const float max_line = min_line + ts;
+            if(max_line <= bmaxu)
+                line(max_line, maxlo, maxhi);
+            const float emin = (min_line <= amin_v && amin_v < max_line) ? bminv : (minlo < maxlo ? minlo : maxlo);
+            const float emax = (min_line <= amax_v && amax_v < max_line) ? bmaxv : (minhi > maxhi ? minhi : maxhi);
+            const int e0 = (int)(emin / ts), e1 = (int)(emax / ts + 1.f);
+            int v0 = e0 < rv1 ? e0 : rv1;
+            v0     = v0 > rv0 ? v0 : rv0;
+            int v1 = e1 > rv0 ? e1 : rv0;
+            v1     = v1 < rv1 ? v1 : rv1;
+            for(int v = v0; v < v1; ++v)
+            {
+                ++count;
+                f(isY ? (int64_t)u * tw + v : (int64_t)v * tw + u);
+            }
+            minlo = maxlo, minhi = maxhi, min_line = max_line;
+        }
+    }
+    else
+    {
+        const float trx = (float)rx / ts, try_ = (float)ry / ts, tx = mx / ts, ty = my / ts;
+        const int x0 = clampi((int)floorf(tx - trx), 0, (int)tw), y0 = clampi((int)floorf(ty - try_), 0, (int)th);
+        const int x1 = clampi((int)ceilf(tx + trx), 0, (int)tw), y1 = clampi((int)ceilf(ty + try_), 0, (int)th);
+        for(int i = y0; i < y1; ++i)
+            for(int j = x0; j < x1; ++j)
+            {
+                ++count;
+                f((int64_t)i * tw + j);
+            }
+    }
+    return count;
+}
+
+__global__ void __launch_bounds__(kThreads) isect_count_kernel(
+    int64_t total, const float *__restrict__ means2d, const int32_t *__restrict__ radii, const float *__restrict__ conics,
+    const float *__restrict__ opacities, uint32_t tile_size, uint32_t tw, uint32_t th, int32_t *__restrict__ tiles_per_gauss
+)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= total)
+        return;
+    const int2 r = reinterpret_cast<const int2 *>(radii)[i];
+    int cnt      = 0;
+    if(r.x > 0 && r.y > 0)
+    {
+        const float2 m = reinterpret_cast<const float2 *>(means2d)[i];
+        float cn[3] = {0.f, 0.f, 0.f}, op = 0.f;
+        const bool accu = conics != nullptr && opacities != nullptr;
+        if(accu)
+            cn[0] = conics[i * 3], cn[1] = conics[i * 3 + 1], cn[2] = conics[i * 3 + 2], op = opacities[i];
+        cnt = tiles_of_gaussian(m.x, m.y, r.x, r.y, accu ? cn : nullptr, accu ? &op : nullptr, tile_size, tw, th, [](int64_t) {});
+    }
+    tiles_per_gauss[i] = cnt;
+}
+
+__global__ void __launch_bounds__(kThreads) isect_emit_kernel(
+    int64_t total, int64_t N, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
+    const float *__restrict__ depths, const float *__restrict__ conics, const float *__restrict__ opacities,
+    const int64_t *__restrict__ cum_tiles, uint32_t tile_size, uint32_t tw, uint32_t th, uint32_t tile_n_bits,
+    int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids
+)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= total)
+        return;
+    const int2 r = reinterpret_cast<const int2 *>(radii)[i];
+    if(r.x <= 0 || r.y <= 0)
+        return;
+    const float2 m = reinterpret_cast<const float2 *>(means2d)[i];
+    float cn[3] = {0.f, 0.f, 0.f}, op = 0.f;
+    const bool accu = conics != nullptr && opacities != nullptr;
+    if(accu)
+        cn[0] = conics[i * 3], cn[1] = conics[i * 3 + 1], cn[2] = conics[i * 3 + 2], op = opacities[i];
+    int64_t cur         = (i == 0) ? 0 : cum_tiles[i - 1];
+    const int64_t hi    = (i / N) << (32 + tile_n_bits);
+    const int64_t dbits = (int64_t)__float_as_uint(depths[i]);
+    tiles_of_gaussian(m.x, m.y, r.x, r.y, accu ? cn : nullptr, accu ? &op : nullptr, tile_size, tw, th, [&](int64_t tile) {
+        isect_ids[cur]   = hi | (tile << 32) | dbits;
+        flatten_ids[cur] = (int32_t)i;
+        ++cur;
+    });
+}
+
+// offsets[(image, tile)] = first sorted index of that tile's run.  One thread per sorted
+// intersection; a thread that starts a new run also fills the empty tiles before it.
+__global__ void __launch_bounds__(kThreads) isect_offsets_kernel(
+    int64_t n_isects, const int64_t *__restrict__ isect_ids, int64_t total_tiles, int64_t n_tiles, uint32_t tile_n_bits,
+    int32_t *__restrict__ offsets
+)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(s >= n_isects)
+        return;
+    const int64_t mask = ((int64_t)1 << tile_n_bits) - 1;
+    const int64_t hi   = isect_ids[s] >> 32;
+    const int64_t id   = (hi >> tile_n_bits) * n_tiles + (hi & mask);
+    int64_t prev       = -1;
+    if(s > 0)
+    {
+        const int64_t hp = isect_ids[s - 1] >> 32;
+        prev             = (hp >> tile_n_bits) * n_tiles + (hp & mask);
+    }
+    for(int64_t k = prev + 1; k <= id; ++k)
+        offsets[k] = (int32_t)s;
+    if(s == n_isects - 1)
+        for(int64_t k = id + 1; k < total_tiles; ++k)
+            offsets[k] = (int32_t)n_isects;
+}
+} // namespace gsb
+
+// =====================================================================================================
+// C ABI
+using namespace gsb;
+
+extern "C" int gsb200_quat_scale_to_covar_preci_fwd(
+    int64_t N, const float *quats, const float *scales, int triu, float *covars, float *precis, void *stream
+)
+{
+    if(N < 0 || (N > 0 && (!quats || !scales)))
+        return GSB200_E_INVALID;
+    if(N == 0 || (!covars && !precis))
+        return GSB200_OK;
+    quat_scale_fwd_kernel<<<grid_for(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(N, quats, scales, triu != 0, covars, precis);
+    return check_launch();
+}
+
+extern "C" int gsb200_quat_scale_to_covar_preci_bwd(
+    int64_t N, const float *quats, const float *scales, int triu, const float *v_covars, const float *v_precis,
+    float *v_quats, float *v_scales, void *stream
+)
+{
+    if(N < 0 || (N > 0 && (!quats || !scales || !v_quats || !v_scales)))
+        return GSB200_E_INVALID;
+    if(N == 0)
+        return GSB200_OK;
+    quat_scale_bwd_kernel<<<grid_for(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        N, quats, scales, triu != 0, v_covars, v_precis, v_quats, v_scales
+    );
+    return check_launch();
+}
+
+extern "C" int gsb200_projection_fwd(
+    int64_t B, int64_t C, int64_t N, const float *means, const float *covars, const float *quats, const float *scales,
+    const float *opacities, const float *viewmats, const float *Ks, uint32_t image_width, uint32_t image_height,
+    float eps2d, float near_plane, float far_plane, float radius_clip, int camera_model, int32_t *radii, float *means2d,
+    float *depths, float *conics, float *compensations, void *stream
+)
+{
+    if(B < 0 || C < 0 || N < 0)
+        return GSB200_E_INVALID;
+    if(camera_model != 0)
+        return GSB200_E_UNSUPPORTED;
+    const int64_t total = B * C * N;
+    if(total == 0)
+        return GSB200_OK;
+    if(!means || !viewmats || !Ks || !radii || !means2d || !depths || !conics)
+        return GSB200_E_INVALID;
+    if(!covars && (!quats || !scales))
+        return GSB200_E_INVALID;
+    projection_fwd_kernel<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        B, C, N, means, covars, quats, scales, opacities, viewmats, Ks, image_width, image_height, eps2d, near_plane,
+        far_plane, radius_clip, radii, means2d, depths, conics, compensations
+    );
+    return check_launch();
+}
+
+extern "C" int gsb200_projection_bwd(
+    int64_t B, int64_t C, int64_t N, const float *means, const float *covars, const float *quats, const float *scales,
+    const float *viewmats, const float *Ks, uint32_t image_width, uint32_t image_height, float eps2d, int camera_model,
+    const int32_t *radii, const float *conics, const float *compensations, const float *v_means2d,
+    int64_t v_means2d_stride, const float *v_depths, int64_t v_depths_stride, const float *v_conics,
+    int64_t v_conics_stride, const float *v_compensations, float *v_means, float *v_covars, float *v_quats,
+    float *v_scales, float *v_viewmats, void *stream
+)
+{
+    if(B < 0 || C < 0 || N < 0)
+        return GSB200_E_INVALID;
+    if(camera_model != 0)
+        return GSB200_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if(v_viewmats && B * C > 0)
+        GSB_CUDA_TRY(cudaMemsetAsync(v_viewmats, 0, sizeof(float) * 16 * (size_t)(B * C), st));
+    if(B * N == 0)
+        return GSB200_OK;
+    if(!means || !viewmats || !Ks || !radii || !conics || !v_means2d || !v_depths || !v_conics || !v_means)
+        return GSB200_E_INVALID;
+    if(covars ? !v_covars : (!quats || !scales || !v_quats || !v_scales))
+        return GSB200_E_INVALID;
+    if(v_compensations && !compensations)
+        return GSB200_E_INVALID;
+    projection_bwd_kernel<<<grid_for(B * N, kThreads), kThreads, 0, st>>>(
+        B, C, N, means, covars, quats, scales, viewmats, Ks, image_width, image_height, eps2d, radii, conics,
+        compensations, v_means2d, v_means2d_stride, v_depths, v_depths_stride, v_conics, v_conics_stride,
+        v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats
+    );
+    return check_launch();
+}
+
+#define GSB_DEG_SWITCH(deg, CALL)  \
+    switch(deg)                    \
+    {                              \
+    case 0: { CALL(0); } break;    \
+    case 1: { CALL(1); } break;    \
+    case 2: { CALL(2); } break;    \
+    case 3: { CALL(3); } break;    \
+    case 4: { CALL(4); } break;    \
+    default: return GSB200_E_INVALID; \
+    }
+
+extern "C" int gsb200_sh_fwd(
+    int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, int degrees_to_use, const float *means,
+    const float *viewmats, const float *coeffs, const uint8_t *masks, float *colors, void *stream
+)
+{
+    if(B < 0 || C < 0 || N < 0 || K <= 0 || D <= 0 || degrees_to_use < 0 || degrees_to_use > 4
+       || (int64_t)(degrees_to_use + 1) * (degrees_to_use + 1) > K)
+        return GSB200_E_INVALID;
+    const int64_t total = B * C * N;
+    if(total == 0)
+        return GSB200_OK;
+    if(!means || !viewmats || !coeffs || !colors)
+        return GSB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(d) sh_fwd_kernel<d><<<grid_for(total, kThreads), kThreads, 0, st>>>(B, C, N, K, D, means, viewmats, coeffs, masks, colors)
+    GSB_DEG_SWITCH(degrees_to_use, CALL)
+#undef CALL
+    return check_launch();
+}
+
+extern "C" int gsb200_sh_bwd(
+    int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, int degrees_to_use, const float *means,
+    const float *viewmats, const float *coeffs, const uint8_t *masks, const float *v_colors, float *v_coeffs,
+    float *v_means, void *stream
+)
+{
+    if(B < 0 || C < 0 || N < 0 || K <= 0 || D <= 0 || degrees_to_use < 0 || degrees_to_use > 4
+       || (int64_t)(degrees_to_use + 1) * (degrees_to_use + 1) > K)
+        return GSB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if(v_means && B * N > 0)
+        GSB_CUDA_TRY(cudaMemsetAsync(v_means, 0, sizeof(float) * 3 * (size_t)(B * N), st));
+    if(N == 0)
+        return GSB200_OK;
+    if(!means || !viewmats || !coeffs || !v_colors || !v_coeffs)
+        return GSB200_E_INVALID;
+#define CALL(d) sh_bwd_kernel<d><<<grid_for(N * D, kThreads), kThreads, 0, st>>>(B, C, N, K, D, means, viewmats, coeffs, masks, v_colors, v_coeffs, v_means)
+    GSB_DEG_SWITCH(degrees_to_use, CALL)
+#undef CALL
+    return check_launch();
+}
+
+extern "C" int gsb200_project_sh_fwd(
+    int64_t C, int64_t N, int64_t K, int degrees_to_use, const float *means, const float *quats, const float *scales,
+    const float *opacities, const float *sh_coeffs, const float *viewmats, const float *Ks, uint32_t image_width,
+    uint32_t image_height, float eps2d, float near_plane, float far_plane, float radius_clip, int calc_compensations,
+    int32_t *radii, float *means2d, float *depths, float *conics, float *compensations, float *colors, void *stream
+)
+{
+    if(C < 0 || N < 0 || K <= 0 || degrees_to_use < 0 || degrees_to_use > 4
+       || (int64_t)(degrees_to_use + 1) * (degrees_to_use + 1) > K)
+        return GSB200_E_INVALID;
+    if(C * N == 0)
+        return GSB200_OK;
+    if(!means || !quats || !scales || !opacities || !sh_coeffs || !viewmats || !Ks || !radii || !means2d || !depths
+       || !conics || !colors || (calc_compensations && !compensations))
+        return GSB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    float *comp     = calc_compensations ? compensations : nullptr;
+#define CALL(d)                                                                                                   \
+    project_sh_fwd_kernel<d><<<grid_for(C * N, kThreads), kThreads, 0, st>>>(                                     \
+        C, N, K, means, quats, scales, opacities, sh_coeffs, viewmats, Ks, image_width, image_height, eps2d,      \
+        near_plane, far_plane, radius_clip, radii, means2d, depths, conics, comp, colors                          \
+    )
+    GSB_DEG_SWITCH(degrees_to_use, CALL)
+#undef CALL
+    return check_launch();
+}
+
+extern "C" int gsb200_project_sh_bwd(
+    int64_t C, int64_t N, int64_t K, int degrees_to_use, const float *means, const float *quats, const float *scales,
+    const float *sh_coeffs, const float *viewmats, const float *Ks, uint32_t image_width, uint32_t image_height,
+    float eps2d, const int32_t *radii, const float *conics, const float *compensations, const float *colors,
+    const float *v_means2d, int64_t v_means2d_stride, const float *v_depths, int64_t v_depths_stride,
+    const float *v_conics, int64_t v_conics_stride, const float *v_colors, int64_t v_colors_stride,
+    const float *v_compensations, float *v_means, float *v_quats, float *v_scales, float *v_sh_coeffs, void *stream
+)
+{
+    if(C < 0 || N < 0 || K <= 0 || degrees_to_use < 0 || degrees_to_use > 4
+       || (int64_t)(degrees_to_use + 1) * (degrees_to_use + 1) > K)
+        return GSB200_E_INVALID;
+    if(N == 0)
+        return GSB200_OK;
+    if(!means || !quats || !scales || !sh_coeffs || !viewmats || !Ks || !radii || !conics || !colors || !v_means2d
+       || !v_conics || !v_colors || !v_means || !v_quats || !v_scales || !v_sh_coeffs)
+        return GSB200_E_INVALID;
+    if(v_compensations && !compensations)
+        return GSB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(d)                                                                                                    \
+    project_sh_bwd_kernel<d><<<grid_for(N, kThreads), kThreads, 0, st>>>(                                          \
+        C, N, K, means, quats, scales, sh_coeffs, viewmats, Ks, image_width, image_height, eps2d, radii, conics,   \
+        compensations, colors, v_means2d, v_means2d_stride, v_depths, v_depths_stride, v_conics, v_conics_stride,  \
+        v_colors, v_colors_stride, v_compensations, v_means, v_quats, v_scales, v_sh_coeffs                        \
+    )
+    GSB_DEG_SWITCH(degrees_to_use, CALL)
+#undef CALL
+    return check_launch();
+}
+
+// ---- isect
+extern "C" size_t gsb200_isect_scan_workspace_bytes(int64_t n_elements)
+{
+    size_t bytes = 0;
+    if(n_elements <= 0)
+        return 0;
+    cub::DeviceScan::InclusiveSum((void *)nullptr, bytes, (const int32_t *)nullptr, (int64_t *)nullptr, n_elements);
+    return bytes + 256;
+}
+
+extern "C" int gsb200_isect_count(
+    int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *conics, const float *opacities,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int32_t *tiles_per_gauss, int64_t *cum_tiles,
+    void *workspace, size_t workspace_bytes, void *stream
+)
+{
+    if(I < 0 || N < 0 || tile_size == 0)
+        return GSB200_E_INVALID;
+    const int64_t total = I * N;
+    if(total == 0)
+        return GSB200_OK;
+    if(!means2d || !radii || !tiles_per_gauss || !cum_tiles || !workspace)
+        return GSB200_E_INVALID;
+    if(bits_for_count(I) + bits_for_count((int64_t)tile_width * tile_height) > 32)
+        return GSB200_E_KEYBITS;
+    cudaStream_t st = (cudaStream_t)stream;
+    isect_count_kernel<<<grid_for(total, kThreads), kThreads, 0, st>>>(
+        total, means2d, radii, conics, opacities, tile_size, tile_width, tile_height, tiles_per_gauss
+    );
+    if(int rc = check_launch())
+        return rc;
+    size_t need = 0;
+    cub::DeviceScan::InclusiveSum((void *)nullptr, need, tiles_per_gauss, cum_tiles, total, st);
+    if(need > workspace_bytes)
+        return GSB200_E_WORKSPACE;
+    GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(workspace, need, tiles_per_gauss, cum_tiles, total, st));
+    return GSB200_OK;
+}
+
+extern "C" int gsb200_isect_emit(
+    int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *depths, const float *conics,
+    const float *opacities, const int64_t *cum_tiles, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+    int64_t *isect_ids, int32_t *flatten_ids, void *stream
+)
+{
+    if(I < 0 || N < 0 || tile_size == 0)
+        return GSB200_E_INVALID;
+    const int64_t total = I * N;
+    if(total == 0)
+        return GSB200_OK;
+    if(!means2d || !radii || !depths || !cum_tiles || !isect_ids || !flatten_ids)
+        return GSB200_E_INVALID;
+    const uint32_t tile_bits = bits_for_count((int64_t)tile_width * tile_height);
+    if(bits_for_count(I) + tile_bits > 32)
+        return GSB200_E_KEYBITS;
+    isect_emit_kernel<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        total, N, means2d, radii, depths, conics, opacities, cum_tiles, tile_size, tile_width, tile_height, tile_bits,
+        isect_ids, flatten_ids
+    );
+    return check_launch();
+}
+
+extern "C" int gsb200_isect_offsets(
+    int64_t n_isects, const int64_t *isect_ids, int64_t I, uint32_t tile_width, uint32_t tile_height, int32_t *offsets,
+    void *stream
+)
+{
+    if(n_isects < 0 || I < 0)
+        return GSB200_E_INVALID;
+    const int64_t n_tiles = (int64_t)tile_width * tile_height;
+    const int64_t total   = I * n_tiles;
+    if(total == 0)
+        return GSB200_OK;
+    if(!offsets)
+        return GSB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if(n_isects == 0)
+    {
+        GSB_CUDA_TRY(cudaMemsetAsync(offsets, 0, sizeof(int32_t) * (size_t)total, st));
+        return GSB200_OK;
+    }
+    if(!isect_ids)
+        return GSB200_E_INVALID;
+    isect_offsets_kernel<<<grid_for(n_isects, kThreads), kThreads, 0, st>>>(
+        n_isects, isect_ids, total, n_tiles, bits_for_count(n_tiles), offsets
+    );
+    return check_launch();
+}

@@ -1,0 +1,741 @@
+// raster.cu -- rasterize_to_pixels forward / backward for sm_100a.
+//
+// Replaces (behaviour, not code) the reference kernels
+//   csrc/RasterizeToPixels3DGSSerialBatchFwd.cu:41-297   (forward)
+//   csrc/RasterizeToPixels3DGSSerialBatchBwd.cu:41-320   (backward)
+//   csrc/RasterizeToPixels3DGSDevice.cuh:37-173          (per-pair math)
+//
+// B200 design (see DESIGN.md section "rasterize"):
+//  * a pack pass gathers the depth-sorted per-intersection records ONCE per view into three
+//    contiguous float4 streams (cull: mean + conservative half extents of the alpha>=1/255 ellipse,
+//    geom: conic + opacity, color), so that every tile's list is a contiguous byte range;
+//  * each CTA (one 16x16 tile, 8 warps, a warp owns an 8x4 pixel block) streams its range through a
+//    2-stage shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx);
+//  * inside a batch every lane tests ONE gaussian's extent box against the warp's pixel block and the
+//    warp ballots: only gaussians that can reach alpha >= 1/255 inside the block are evaluated
+//    (exact: the skipped pairs are `continue`d by the reference too); finished warps drop out by ballot;
+//  * the backward walks the same ring back to front, reduces the 9(+2) per-gaussian partial sums of a
+//    warp with a butterfly transpose (12 shuffles instead of 45) and lets the lanes that end up owning
+//    a sum issue one red.global.add each.
+#include "common.cuh"
+
+namespace gsb
+{
+constexpr int kBatch  = 128; // gaussians per ring stage
+constexpr int kStages = 2;
+constexpr int kWarps  = 8;
+
+template<int CDIM>
+struct RecLayout
+{
+    static constexpr int kColorVec4 = (CDIM + 3) / 4; // float4 per record for colours
+    static constexpr int kStageBytes = kBatch * (16 + 16 + 16 * kColorVec4);
+};
+
+struct RecordStreams
+{
+    float4 *cull;  // [S] {mx, my, ex, ey}
+    float4 *geom;  // [S] {a, b, c, opacity}
+    float4 *color; // [S * kColorVec4]
+};
+
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+static inline RecordStreams carve_records(void *base, int64_t S, int cvec4)
+{
+    RecordStreams r;
+    char *p = (char *)base;
+    r.cull  = (float4 *)p;
+    p += align256((size_t)S * 16);
+    r.geom = (float4 *)p;
+    p += align256((size_t)S * 16);
+    r.color = (float4 *)p;
+    (void)cvec4;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack: gather sorted records.  One thread per intersection.
+template<int CDIM>
+__global__ void __launch_bounds__(256) pack_records_kernel(
+    const int64_t S, const int32_t *__restrict__ flatten_ids, const float *__restrict__ means2d,
+    const float *__restrict__ conics, const float *__restrict__ colors, const float *__restrict__ opacities,
+    float4 *__restrict__ cull, float4 *__restrict__ geom, float4 *__restrict__ color
+)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(s >= S)
+        return;
+    const int64_t g = flatten_ids[s];
+    const float2 m  = *reinterpret_cast<const float2 *>(means2d + g * 2);
+    const float a = conics[g * 3], b = conics[g * 3 + 1], c = conics[g * 3 + 2];
+    const float op = opacities[g];
+    // conservative half extents of {alpha >= 1/255}: |dx| <= sqrt(t c / det), t = 2 ln(255 op)
+    float ex, ey;
+    const float det = a * c - b * b;
+    if(!(op >= kAlphaThreshold))
+    {
+        ex = ey = -1e30f; // can never reach the alpha threshold (NaN opacity lands here too)
+    }
+    else if(!(det > 0.f) || !(a > 0.f) || !(c > 0.f) || !isfinite(det))
+    {
+        ex = ey = 1e30f; // not a proper ellipse: never cull, let the exact test decide
+    }
+    else
+    {
+        const float t = 2.f * logf(op * 255.f) * 1.0001f + 1e-4f;
+        ex            = sqrtf(t * c / det) * 1.0001f + 0.01f;
+        ey            = sqrtf(t * a / det) * 1.0001f + 0.01f;
+        if(!isfinite(ex) || !isfinite(ey))
+            ex = ey = 1e30f;
+    }
+    cull[s] = make_float4(m.x, m.y, ex, ey);
+    geom[s] = make_float4(a, b, c, op);
+    constexpr int CV = RecLayout<CDIM>::kColorVec4;
+    float cbuf[CV * 4];
+#pragma unroll
+    for(int k = 0; k < CV * 4; ++k)
+        cbuf[k] = k < CDIM ? colors[g * CDIM + k] : 0.f;
+#pragma unroll
+    for(int v = 0; v < CV; ++v)
+        color[s * CV + v] = make_float4(cbuf[4 * v], cbuf[4 * v + 1], cbuf[4 * v + 2], cbuf[4 * v + 3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct TileGeom
+{
+    int image_id, tile_id, tile_x, tile_y;
+};
+
+__device__ __forceinline__ TileGeom decode_tile(uint32_t block, uint32_t tw, uint32_t th)
+{
+    TileGeom t;
+    const uint32_t per = tw * th;
+    t.image_id         = block / per;
+    t.tile_id          = block % per;
+    t.tile_x           = t.tile_id % tw;
+    t.tile_y           = t.tile_id / tw;
+    return t;
+}
+
+// shared-memory ring: per stage [cull | geom | color] + one full-barrier per stage
+template<int CDIM>
+struct Ring
+{
+    static constexpr int CV = RecLayout<CDIM>::kColorVec4;
+    unsigned char *base;
+
+    __device__ __forceinline__ void carve(unsigned char *smem) { base = smem; }
+    __device__ __forceinline__ float4 *cull(int s) const
+    {
+        return reinterpret_cast<float4 *>(base + (size_t)s * RecLayout<CDIM>::kStageBytes);
+    }
+    __device__ __forceinline__ float4 *geom(int s) const { return cull(s) + kBatch; }
+    __device__ __forceinline__ float4 *color(int s) const { return cull(s) + 2 * kBatch; }
+    __device__ __forceinline__ uint64_t *full(int s) const
+    {
+        return reinterpret_cast<uint64_t *>(base + (size_t)kStages * RecLayout<CDIM>::kStageBytes) + s;
+    }
+    // one thread: arm the barrier and launch the three bulk copies of records [first, first+count)
+    __device__ __forceinline__ void issue(
+        int stage, const float4 *gcull, const float4 *ggeom, const float4 *gcolor, int64_t first, int count
+    ) const
+    {
+        const uint32_t n16 = (uint32_t)count * 16u;
+        mbar_arrive_expect_tx(full(stage), n16 * (2u + CV));
+        bulk_g2s(cull(stage), gcull + first, n16, full(stage));
+        bulk_g2s(geom(stage), ggeom + first, n16, full(stage));
+        bulk_g2s(color(stage), gcolor + first * CV, n16 * CV, full(stage));
+    }
+};
+
+template<int CDIM>
+constexpr size_t ring_smem_bytes()
+{
+    return (size_t)kStages * RecLayout<CDIM>::kStageBytes + kStages * sizeof(uint64_t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+template<int CDIM>
+__global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
+    const uint32_t I, const int64_t n_isects, const float4 *__restrict__ gcull, const float4 *__restrict__ ggeom,
+    const float4 *__restrict__ gcolor, const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
+    const uint32_t W, const uint32_t H, const uint32_t tw, const uint32_t th, const int32_t *__restrict__ offsets,
+    float *__restrict__ render_colors, float *__restrict__ render_alphas, int32_t *__restrict__ last_ids
+)
+{
+    constexpr int CV = RecLayout<CDIM>::kColorVec4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Ring<CDIM> ring;
+    ring.carve(smem_raw);
+
+    const TileGeom tg   = decode_tile(blockIdx.x, tw, th);
+    const unsigned tid  = threadIdx.x;
+    const unsigned warp = tid >> 5, lane = tid & 31;
+    // warp -> 8x4 pixel block inside the 16x16 tile
+    const int bx0 = tg.tile_x * kTile + (warp & 1) * 8;
+    const int by0 = tg.tile_y * kTile + (warp >> 1) * 4;
+    const int px_i = bx0 + (lane & 7), py_i = by0 + (lane >> 3);
+    const float px = (float)px_i + 0.5f, py = (float)py_i + 0.5f;
+    const bool inside = (px_i < (int)W) && (py_i < (int)H);
+    const int64_t pix = ((int64_t)tg.image_id * H + py_i) * W + px_i;
+    const float *bg   = backgrounds ? backgrounds + (size_t)tg.image_id * CDIM : nullptr;
+
+    const int64_t tile_lin = (int64_t)tg.image_id * tw * th + tg.tile_id;
+    if(masks != nullptr && !masks[tile_lin])
+    { // masked-off tile: background, zero alpha (reference Fwd.cu:142-160)
+        if(inside)
+        {
+#pragma unroll
+            for(int k = 0; k < CDIM; ++k)
+                render_colors[pix * CDIM + k] = bg ? bg[k] : 0.f;
+            render_alphas[pix] = 0.f;
+            last_ids[pix]      = 0;
+        }
+        return;
+    }
+
+    const int32_t range_start = offsets[tile_lin];
+    const int32_t range_end   = (tile_lin == (int64_t)I * tw * th - 1) ? (int32_t)n_isects : offsets[tile_lin + 1];
+    const int num_batches     = (range_end - range_start + kBatch - 1) / kBatch;
+
+    if(tid == 0)
+    {
+#pragma unroll
+        for(int s = 0; s < kStages; ++s)
+            mbar_init(ring.full(s), 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if(tid == 0)
+    {
+#pragma unroll
+        for(int s = 0; s < kStages; ++s)
+            if(s < num_batches)
+            {
+                const int64_t first = (int64_t)range_start + (int64_t)s * kBatch;
+                const int count     = min(kBatch, (int)(range_end - first));
+                ring.issue(s, gcull, ggeom, gcolor, first, count);
+            }
+    }
+
+    // pixel-block centre extents for the cull test: centres span [bx0+0.5, bx0+7.5] x [by0+0.5, by0+3.5]
+    const float cx = (float)bx0 + 4.0f, cy = (float)by0 + 2.0f;
+    constexpr float hx = 3.5f, hy = 1.5f;
+
+    float T = 1.f;
+    float pix_out[CDIM];
+#pragma unroll
+    for(int k = 0; k < CDIM; ++k)
+        pix_out[k] = 0.f;
+    int32_t cur_idx = 0;
+    bool done       = !inside;
+    int last_b      = num_batches; // batch at which the tile-level early exit happened
+
+    for(int b = 0; b < num_batches; ++b)
+    {
+        const int stage       = b % kStages;
+        const uint32_t parity = (uint32_t)(b / kStages) & 1u;
+        const int64_t first   = (int64_t)range_start + (int64_t)b * kBatch;
+        const int count       = min(kBatch, (int)(range_end - first));
+        const bool warp_done  = __all_sync(0xffffffffu, done);
+        if(!warp_done)
+        {
+            mbar_wait(ring.full(stage), parity);
+            const float4 *scull = ring.cull(stage);
+            const float4 *sgeom = ring.geom(stage);
+            const float4 *scol  = ring.color(stage);
+            bool stop           = false;
+            for(int c0 = 0; c0 < count && !stop; c0 += 32)
+            {
+                // each lane tests one gaussian's extent box against this warp's pixel block
+                const int mine = c0 + (int)lane;
+                bool hit       = false;
+                if(mine < count)
+                {
+                    const float4 q = scull[mine];
+                    hit            = (fabsf(q.x - cx) <= q.z + hx) && (fabsf(q.y - cy) <= q.w + hy);
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, hit);
+                while(mask)
+                {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int t    = c0 + j;
+                    const float4 q = scull[t];
+                    const float4 g = sgeom[t];
+                    const float dx = q.x - px, dy = q.y - py;
+                    const float sigma = 0.5f * (g.x * dx * dx + g.z * dy * dy) + g.y * dx * dy;
+                    const float vis   = __expf(-sigma);
+                    const float alpha = fminf(kMaxAlpha, g.w * vis);
+                    bool valid        = !done && !(sigma < 0.f || alpha < kAlphaThreshold);
+                    float next_T      = 0.f;
+                    if(valid)
+                    {
+                        next_T = T * (1.0f - alpha);
+                        if(next_T <= kTransmittanceThreshold)
+                        { // this pixel is done: exclusive of the current gaussian
+                            done  = true;
+                            valid = false;
+                        }
+                    }
+                    if(__any_sync(0xffffffffu, valid))
+                    {
+                        float col[CV * 4];
+#pragma unroll
+                        for(int v = 0; v < CV; ++v)
+                        {
+                            const float4 cc = scol[t * CV + v];
+                            col[4 * v] = cc.x, col[4 * v + 1] = cc.y, col[4 * v + 2] = cc.z, col[4 * v + 3] = cc.w;
+                        }
+                        if(valid)
+                        {
+                            const float w = alpha * T;
+#pragma unroll
+                            for(int k = 0; k < CDIM; ++k)
+                                pix_out[k] += col[k] * w;
+                            cur_idx = (int32_t)(first + t);
+                            T       = next_T;
+                        }
+                    }
+                    if(__all_sync(0xffffffffu, done))
+                    { // every pixel of this warp is saturated: drop out of the list
+                        stop = true;
+                        break;
+                    }
+                }
+            }
+        }
+        // everyone finished reading this stage; tile-level early exit
+        const int n_done = __syncthreads_count(done);
+        if(tid == 0)
+            mbar_wait(ring.full(stage), parity); // batch b has landed even if no warp needed it
+        if(n_done == kWarps * 32)
+        {
+            last_b = b;
+            break;
+        }
+        if(tid == 0 && b + kStages < num_batches)
+        {
+            const int64_t nfirst = (int64_t)range_start + (int64_t)(b + kStages) * kBatch;
+            const int ncount     = min(kBatch, (int)(range_end - nfirst));
+            ring.issue(stage, gcull, ggeom, gcolor, nfirst, ncount);
+        }
+    }
+    if(tid == 0)
+    { // never retire the CTA with bulk copies still in flight into its shared memory
+        for(int b = last_b + 1; b < num_batches && b < last_b + kStages; ++b)
+            mbar_wait(ring.full(b % kStages), (uint32_t)(b / kStages) & 1u);
+    }
+
+    if(inside)
+    {
+        render_alphas[pix] = 1.0f - T;
+#pragma unroll
+        for(int k = 0; k < CDIM; ++k)
+            render_colors[pix * CDIM + k] = bg ? (pix_out[k] + T * bg[k]) : pix_out[k];
+        last_ids[pix] = cur_idx;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+struct GradDst
+{
+    float *means2d, *conics, *colors, *opacities, *abs;
+    int64_t s_means2d, s_conics, s_colors, s_opacities, s_abs;
+};
+
+template<int CDIM, bool ABS>
+__global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
+    const uint32_t I, const int64_t n_isects, const float4 *__restrict__ gcull, const float4 *__restrict__ ggeom,
+    const float4 *__restrict__ gcolor, const int32_t *__restrict__ flatten_ids, const float *__restrict__ backgrounds,
+    const uint8_t *__restrict__ masks, const uint32_t W, const uint32_t H, const uint32_t tw, const uint32_t th,
+    const int32_t *__restrict__ offsets, const float *__restrict__ render_alphas, const int32_t *__restrict__ last_ids,
+    const float *__restrict__ v_render_colors, const float *__restrict__ v_render_alphas, const GradDst dst
+)
+{
+    constexpr int CV = RecLayout<CDIM>::kColorVec4;
+    // slots: 0,1 = v_xy ; 2,3,4 = v_conic ; 5 = v_opacity ; 6..6+CDIM = v_rgb ; then 2 abs
+    constexpr int M = 6 + CDIM + (ABS ? 2 : 0);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Ring<CDIM> ring;
+    ring.carve(smem_raw);
+    __shared__ int32_t s_ids[kStages][kBatch];
+    __shared__ int32_t s_tile_bin;
+
+    const TileGeom tg      = decode_tile(blockIdx.x, tw, th);
+    const unsigned tid     = threadIdx.x;
+    const unsigned warp    = tid >> 5, lane = tid & 31;
+    const int64_t tile_lin = (int64_t)tg.image_id * tw * th + tg.tile_id;
+    if(masks != nullptr && !masks[tile_lin])
+        return;
+    const int32_t range_start = offsets[tile_lin];
+    const int32_t range_end0  = (tile_lin == (int64_t)I * tw * th - 1) ? (int32_t)n_isects : offsets[tile_lin + 1];
+    if(range_end0 <= range_start)
+        return;
+
+    const int bx0 = tg.tile_x * kTile + (warp & 1) * 8;
+    const int by0 = tg.tile_y * kTile + (warp >> 1) * 4;
+    const int px_i = bx0 + (lane & 7), py_i = by0 + (lane >> 3);
+    const float px = (float)px_i + 0.5f, py = (float)py_i + 0.5f;
+    const bool inside = (px_i < (int)W) && (py_i < (int)H);
+    const int64_t pix = inside ? ((int64_t)tg.image_id * H + py_i) * W + px_i : 0;
+    const float *bg   = backgrounds ? backgrounds + (size_t)tg.image_id * CDIM : nullptr;
+
+    const float T_final = inside ? 1.0f - render_alphas[pix] : 1.f;
+    float T             = T_final;
+    float buffer[CDIM], v_render_c[CDIM];
+    float bg_dot = 0.f;
+#pragma unroll
+    for(int k = 0; k < CDIM; ++k)
+    {
+        buffer[k]     = 0.f;
+        v_render_c[k] = inside ? v_render_colors[pix * CDIM + k] : 0.f;
+        if(bg)
+            bg_dot += bg[k] * v_render_c[k];
+    }
+    const float v_render_a       = inside ? v_render_alphas[pix] : 0.f;
+    const int32_t bin_final      = inside ? last_ids[pix] : -1;
+    const int32_t warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
+
+    // nothing behind the tile's deepest contributor matters: shorten the list (block max of last_ids)
+    if(tid == 0)
+    {
+        s_tile_bin = -1;
+#pragma unroll
+        for(int s = 0; s < kStages; ++s)
+            mbar_init(ring.full(s), 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if(lane == 0)
+        atomicMax(&s_tile_bin, warp_bin_final);
+    __syncthreads();
+    const int32_t range_end = min(range_end0, s_tile_bin + 1);
+    if(range_end <= range_start)
+        return;
+
+    // which output(s) does this lane own after the butterfly reduction?  (two groups when M > 32)
+    constexpr int MA = M > 32 ? 32 : M;
+    constexpr int MB = M - MA;
+    auto slot_dst = [&](int slot, float *&p, int64_t &stride) {
+        p = nullptr, stride = 0;
+        if(slot < 0)
+            return;
+        if(slot < 2)
+            p = dst.means2d + slot, stride = dst.s_means2d;
+        else if(slot < 5)
+            p = dst.conics + (slot - 2), stride = dst.s_conics;
+        else if(slot == 5)
+            p = dst.opacities, stride = dst.s_opacities;
+        else if(slot < 6 + CDIM)
+            p = dst.colors + (slot - 6), stride = dst.s_colors;
+        else if(ABS)
+            p = dst.abs + (slot - 6 - CDIM), stride = dst.s_abs;
+    };
+    float *my_dst, *my_dst_b = nullptr;
+    int64_t my_stride, my_stride_b = 0;
+    slot_dst(butterfly_slot<MA>(lane), my_dst, my_stride);
+    if constexpr(MB > 0)
+    {
+        const int sb = butterfly_slot<MB>(lane);
+        slot_dst(sb >= 0 ? sb + MA : -1, my_dst_b, my_stride_b);
+    }
+
+    const int num_batches = (range_end - range_start + kBatch - 1) / kBatch;
+    // batch b covers sorted indices [first, first + count), walking back to front
+    auto batch_first = [&](int b) -> int64_t {
+        const int64_t bf = (int64_t)range_end - (int64_t)(b + 1) * kBatch;
+        return bf > range_start ? bf : (int64_t)range_start;
+    };
+    auto batch_count = [&](int b) -> int {
+        return (int)((int64_t)range_end - (int64_t)b * kBatch - batch_first(b));
+    };
+
+    if(tid == 0)
+    {
+#pragma unroll
+        for(int s = 0; s < kStages; ++s)
+            if(s < num_batches)
+                ring.issue(s, gcull, ggeom, gcolor, batch_first(s), batch_count(s));
+    }
+    const float cx = (float)bx0 + 4.0f, cy = (float)by0 + 2.0f;
+    constexpr float hx = 3.5f, hy = 1.5f;
+
+    for(int b = 0; b < num_batches; ++b)
+    {
+        const int stage       = b % kStages;
+        const uint32_t parity = (uint32_t)(b / kStages) & 1u;
+        const int64_t first   = batch_first(b);
+        const int count       = batch_count(b);
+        // gaussian ids of this batch (coalesced; needed for the scatter)
+        if((int)tid < count)
+            s_ids[stage][tid] = flatten_ids[first + tid];
+        __syncthreads();
+        // the whole batch lies behind this warp's deepest contributor -> nothing to do for the warp
+        if(first <= (int64_t)warp_bin_final)
+        {
+            mbar_wait(ring.full(stage), parity);
+            const float4 *scull = ring.cull(stage);
+            const float4 *sgeom = ring.geom(stage);
+            const float4 *scol  = ring.color(stage);
+            for(int c1 = count; c1 > 0; c1 -= 32)
+            {
+                const int c0   = c1 - 32; // chunk covers local [c0, c1); c0 may be negative
+                const int mine = c0 + (int)lane;
+                bool hit       = false;
+                if(mine >= 0 && first + mine <= (int64_t)warp_bin_final)
+                {
+                    const float4 q = scull[mine];
+                    hit            = (fabsf(q.x - cx) <= q.z + hx) && (fabsf(q.y - cy) <= q.w + hy);
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, hit);
+                while(mask)
+                {
+                    const int j = 31 - __clz(mask); // back to front
+                    mask &= ~(1u << j);
+                    const int t    = c0 + j;
+                    const float4 q = scull[t];
+                    const float4 g = sgeom[t];
+                    const float dx = q.x - px, dy = q.y - py;
+                    const float sigma = 0.5f * (g.x * dx * dx + g.z * dy * dy) + g.y * dx * dy;
+                    const float vis   = __expf(-sigma);
+                    const float alpha = fminf(kMaxAlpha, g.w * vis);
+                    const bool valid
+                        = inside && (first + t <= (int64_t)bin_final) && !(sigma < 0.f || alpha < kAlphaThreshold);
+                    if(!__any_sync(0xffffffffu, valid))
+                        continue;
+                    float col[CV * 4];
+#pragma unroll
+                    for(int v = 0; v < CV; ++v)
+                    {
+                        const float4 cc = scol[t * CV + v];
+                        col[4 * v] = cc.x, col[4 * v + 1] = cc.y, col[4 * v + 2] = cc.z, col[4 * v + 3] = cc.w;
+                    }
+                    float part[M];
+#pragma unroll
+                    for(int k = 0; k < M; ++k)
+                        part[k] = 0.f;
+                    if(valid)
+                    {
+                        const float ra = 1.0f / fmaxf(kMinOneMinusAlpha, 1.0f - alpha);
+                        T *= ra;
+                        const float fac = alpha * T;
+                        float v_alpha   = 0.f;
+#pragma unroll
+                        for(int k = 0; k < CDIM; ++k)
+                        {
+                            part[6 + k] = fac * v_render_c[k];
+                            v_alpha += (col[k] * T - buffer[k] * ra) * v_render_c[k];
+                        }
+                        v_alpha += T_final * ra * v_render_a;
+                        if(bg)
+                            v_alpha += -T_final * ra * bg_dot;
+                        if(g.w * vis <= kMaxAlpha)
+                        {
+                            const float v_sigma = -g.w * vis * v_alpha;
+                            part[0]             = v_sigma * (g.x * dx + g.y * dy);
+                            part[1]             = v_sigma * (g.y * dx + g.z * dy);
+                            part[2]             = 0.5f * v_sigma * dx * dx;
+                            part[3]             = v_sigma * dx * dy;
+                            part[4]             = 0.5f * v_sigma * dy * dy;
+                            part[5]             = vis * v_alpha;
+                            if constexpr(ABS)
+                            {
+                                part[6 + CDIM]     = fabsf(part[0]);
+                                part[6 + CDIM + 1] = fabsf(part[1]);
+                            }
+                        }
+#pragma unroll
+                        for(int k = 0; k < CDIM; ++k)
+                            buffer[k] += col[k] * fac;
+                    }
+                    Butterfly<MA, 16>::run(part, lane);
+                    const int64_t gid = s_ids[stage][t];
+                    if(my_dst != nullptr)
+                        atomicAdd(my_dst + gid * my_stride, part[0]);
+                    if constexpr(MB > 0)
+                    {
+                        Butterfly<MB, 16>::run(part + MA, lane);
+                        if(my_dst_b != nullptr)
+                            atomicAdd(my_dst_b + gid * my_stride_b, part[MA]);
+                    }
+                }
+            }
+        }
+        __syncthreads(); // stage (records + ids) fully consumed
+        if(tid == 0)
+        {
+            mbar_wait(ring.full(stage), parity); // landed even if every warp skipped it
+            if(b + kStages < num_batches)
+                ring.issue(stage, gcull, ggeom, gcolor, batch_first(b + kStages), batch_count(b + kStages));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template<int CDIM>
+static int launch_fwd(
+    int64_t I, int64_t N, const float *means2d, const float *conics, const float *colors, const float *opacities,
+    const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tw, uint32_t th,
+    const int32_t *offsets, const int32_t *flatten_ids, int64_t S, void *records, float *render_colors,
+    float *render_alphas, int32_t *last_ids, cudaStream_t st
+)
+{
+    (void)N;
+    RecordStreams r = carve_records(records, S, RecLayout<CDIM>::kColorVec4);
+    if(S > 0)
+    {
+        pack_records_kernel<CDIM><<<grid_for(S, 256), 256, 0, st>>>(
+            S, flatten_ids, means2d, conics, colors, opacities, r.cull, r.geom, r.color
+        );
+        if(int rc = check_launch())
+            return rc;
+    }
+    const size_t smem = ring_smem_bytes<CDIM>();
+    GSB_CUDA_TRY(cudaFuncSetAttribute(raster_fwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned n_tiles = (unsigned)(I * tw * th);
+    raster_fwd_kernel<CDIM><<<n_tiles, kWarps * 32, smem, st>>>(
+        (uint32_t)I, S, r.cull, r.geom, r.color, backgrounds, masks, W, H, tw, th, offsets, render_colors,
+        render_alphas, last_ids
+    );
+    return check_launch();
+}
+
+template<int CDIM>
+static int launch_bwd(
+    int64_t I, const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tw, uint32_t th,
+    const int32_t *offsets, const int32_t *flatten_ids, int64_t S, const void *records, const float *render_alphas,
+    const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas, const GradDst &dst,
+    cudaStream_t st
+)
+{
+    if(S == 0)
+        return GSB200_OK; // reference: no launch when there are no intersections (Bwd.cu:350-354)
+    RecordStreams r    = carve_records(const_cast<void *>(records), S, RecLayout<CDIM>::kColorVec4);
+    const size_t smem  = ring_smem_bytes<CDIM>();
+    const unsigned n_tiles = (unsigned)(I * tw * th);
+    if(dst.abs != nullptr)
+    {
+        GSB_CUDA_TRY(cudaFuncSetAttribute(
+            raster_bwd_kernel<CDIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem
+        ));
+        raster_bwd_kernel<CDIM, true><<<n_tiles, kWarps * 32, smem, st>>>(
+            (uint32_t)I, S, r.cull, r.geom, r.color, flatten_ids, backgrounds, masks, W, H, tw, th, offsets,
+            render_alphas, last_ids, v_render_colors, v_render_alphas, dst
+        );
+    }
+    else
+    {
+        GSB_CUDA_TRY(cudaFuncSetAttribute(
+            raster_bwd_kernel<CDIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem
+        ));
+        raster_bwd_kernel<CDIM, false><<<n_tiles, kWarps * 32, smem, st>>>(
+            (uint32_t)I, S, r.cull, r.geom, r.color, flatten_ids, backgrounds, masks, W, H, tw, th, offsets,
+            render_alphas, last_ids, v_render_colors, v_render_alphas, dst
+        );
+    }
+    return check_launch();
+}
+} // namespace gsb
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+#define GSB_FOR_CHANNELS(X) X(1) X(2) X(3) X(4) X(5) X(8) X(16) X(32)
+
+extern "C" int gsb200_raster_supports_channels(int D)
+{
+    switch(D)
+    {
+#define X(n) case n:
+        GSB_FOR_CHANNELS(X)
+#undef X
+        return 1;
+    default:
+        return 0;
+    }
+}
+
+extern "C" size_t gsb200_raster_records_bytes(int64_t n_isects, int D)
+{
+    if(n_isects < 0 || D <= 0)
+        return 0;
+    const size_t cv = (size_t)((D + 3) / 4);
+    return 2 * gsb::align256((size_t)n_isects * 16) + gsb::align256((size_t)n_isects * 16 * cv) + 256;
+}
+
+extern "C" int gsb200_raster_fwd(
+    int64_t I, int64_t N, int D, const float *means2d, const float *conics, const float *colors,
+    const float *opacities, const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+    uint32_t image_height, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, const int32_t *offsets,
+    const int32_t *flatten_ids, int64_t n_isects, void *records, float *render_colors, float *render_alphas,
+    int32_t *last_ids, void *stream
+)
+{
+    if(I < 0 || N < 0 || n_isects < 0 || !offsets || !render_colors || !render_alphas || !last_ids)
+        return GSB200_E_INVALID;
+    if(n_isects > 0 && (!means2d || !conics || !colors || !opacities || !flatten_ids || !records))
+        return GSB200_E_INVALID;
+    if(tile_size != (uint32_t)gsb::kTile)
+        return GSB200_E_UNSUPPORTED;
+    if(I == 0 || image_width == 0 || image_height == 0)
+        return GSB200_OK;
+    if((uint64_t)tile_width * gsb::kTile < image_width || (uint64_t)tile_height * gsb::kTile < image_height)
+        return GSB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch(D)
+    {
+#define X(n)                                                                                                         \
+    case n:                                                                                                          \
+        return gsb::launch_fwd<n>(                                                                                   \
+            I, N, means2d, conics, colors, opacities, backgrounds, masks, image_width, image_height, tile_width,     \
+            tile_height, offsets, flatten_ids, n_isects, records, render_colors, render_alphas, last_ids, st        \
+        );
+        GSB_FOR_CHANNELS(X)
+#undef X
+    default:
+        return GSB200_E_UNSUPPORTED;
+    }
+}
+
+extern "C" int gsb200_raster_bwd(
+    int64_t I, int64_t N, int D, const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+    uint32_t image_height, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, const int32_t *offsets,
+    const int32_t *flatten_ids, int64_t n_isects, const void *records, const float *render_alphas,
+    const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas, float *v_means2d,
+    int64_t v_means2d_stride, float *v_conics, int64_t v_conics_stride, float *v_colors, int64_t v_colors_stride,
+    float *v_opacities, int64_t v_opacities_stride, float *v_means2d_abs, int64_t v_means2d_abs_stride, void *stream
+)
+{
+    if(I < 0 || N < 0 || n_isects < 0)
+        return GSB200_E_INVALID;
+    if(tile_size != (uint32_t)gsb::kTile)
+        return GSB200_E_UNSUPPORTED;
+    if(n_isects == 0 || I == 0)
+        return GSB200_OK;
+    if(!offsets || !flatten_ids || !records || !render_alphas || !last_ids || !v_render_colors || !v_render_alphas
+       || !v_means2d || !v_conics || !v_colors || !v_opacities)
+        return GSB200_E_INVALID;
+    gsb::GradDst dst;
+    dst.means2d = v_means2d, dst.s_means2d = v_means2d_stride;
+    dst.conics = v_conics, dst.s_conics = v_conics_stride;
+    dst.colors = v_colors, dst.s_colors = v_colors_stride;
+    dst.opacities = v_opacities, dst.s_opacities = v_opacities_stride;
+    dst.abs = v_means2d_abs, dst.s_abs = v_means2d_abs_stride;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch(D)
+    {
+#define X(n)                                                                                                       \
+    case n:                                                                                                        \
+        return gsb::launch_bwd<n>(                                                                                 \
+            I, backgrounds, masks, image_width, image_height, tile_width, tile_height, offsets, flatten_ids,       \
+            n_isects, records, render_alphas, last_ids, v_render_colors, v_render_alphas, dst, st                  \
+        );
+        GSB_FOR_CHANNELS(X)
+#undef X
+    default:
+        return GSB200_E_UNSUPPORTED;
+    }
+}

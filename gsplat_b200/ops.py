@@ -1,0 +1,652 @@
+"""Operator surface: the Python functions the reference exposes in gsplat/cuda/_wrapper.py, with the
+same names, argument meaning and error behaviour, implemented as torch.autograd.Function wrappers
+around the C ABI of libgsplat_b200.so (include/gsplat_b200.h).
+
+Reference wrappers mirrored here (file:line in /root/reference/gsplat/cuda/_wrapper.py):
+  quat_scale_to_covar_preci :657   fully_fused_projection :819   spherical_harmonics :436
+  isect_tiles :1196                isect_offset_encode :1328     rasterize_to_pixels :1497
+and their autograd registrations (:559-716, :966-1191, :2010-2117).
+
+PyTorch is plumbing here (device memory, streams, autograd graph); every number is produced by the
+hand-written sm_100a kernels.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+from ._cabi import check, f32c, lib, ptr, require_cuda, stream
+
+# --------------------------------------------------------------------------------------------
+# helpers
+
+
+def _prod(shape) -> int:
+    return int(math.prod(shape)) if len(shape) else 1
+
+
+def _rows(t: Optional[Tensor], width: int, name: str) -> Tuple[Optional[Tensor], int]:
+    """Return (tensor, row_stride_in_floats) for a gradient the kernels address as ptr[row * stride + k],
+    row being the C-order flattened index over the leading dims.  ``width`` > 1: t is [..., width] with a
+    unit inner stride; ``width`` == 1: t is [...] (no trailing dim).  Accepts any layout whose rows sit at
+    one uniform stride (e.g. views into a packed per-gaussian record); copies otherwise."""
+    if t is None:
+        return None, 0
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected a float32 gradient, got {t.dtype}")
+    has_inner = width > 1
+    lead_shape = t.shape[:-1] if has_inner else t.shape
+    lead_strides = t.stride()[:-1] if has_inner else t.stride()
+    ok = (not has_inner) or (t.shape[-1] == width and t.stride(-1) == 1)
+    if ok:
+        row, expect = None, None
+        for size, st in zip(reversed(lead_shape), reversed(lead_strides)):
+            if size == 1:
+                continue
+            if expect is None:
+                row, expect = st, st * size
+            elif st != expect:
+                ok = False
+                break
+            else:
+                expect *= size
+        if row is None:
+            row = width
+        if ok and row >= width:
+            return t, int(row)
+    return t.contiguous(), width
+
+
+class _Ctx:
+    """device guard + stream fetch for one operator call"""
+
+    def __init__(self, dev: torch.device):
+        self.dev = dev
+
+    def __enter__(self):
+        self._g = torch.cuda.device(self.dev)
+        self._g.__enter__()
+        return stream()
+
+    def __exit__(self, *a):
+        return self._g.__exit__(*a)
+
+
+def _camera_model_id(camera_model: str) -> int:
+    table = {"pinhole": 0, "ortho": 1, "fisheye": 2, "ftheta": 3, "lidar": 4}
+    if camera_model not in table:
+        raise ValueError(f"unknown camera_model {camera_model!r}")
+    if camera_model != "pinhole":
+        raise NotImplementedError(
+            f"camera_model={camera_model!r}: only the pinhole EWA projection is built in gsplat_b200 "
+            "(reference: csrc/ProjectionEWA3DGSFused.cu:135-147)"
+        )
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# quat_scale_to_covar_preci
+
+
+class _QuatScaleToCovarPreci(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, quats, scales, compute_covar: bool, compute_preci: bool, triu: bool):
+        dev = require_cuda(quats, scales)
+        q, s = f32c(quats, "quats"), f32c(scales, "scales")
+        lead = q.shape[:-1]
+        N = _prod(lead)
+        shp = tuple(lead) + ((6,) if triu else (3, 3))
+        covars = torch.empty(shp, device=dev, dtype=torch.float32) if compute_covar else None
+        precis = torch.empty(shp, device=dev, dtype=torch.float32) if compute_preci else None
+        with _Ctx(dev) as st:
+            check(
+                lib().gsb200_quat_scale_to_covar_preci_fwd(N, ptr(q), ptr(s), int(triu), ptr(covars), ptr(precis), st),
+                "quat_scale_to_covar_preci",
+            )
+        ctx.save_for_backward(q, s)
+        ctx.triu = triu
+        return covars, precis
+
+    @staticmethod
+    def backward(ctx, v_covars, v_precis):
+        q, s = ctx.saved_tensors
+        N = _prod(q.shape[:-1])
+        vc = None if v_covars is None else v_covars.contiguous()
+        vp = None if v_precis is None else v_precis.contiguous()
+        v_q, v_s = torch.empty_like(q), torch.empty_like(s)
+        with _Ctx(q.device) as st:
+            check(
+                lib().gsb200_quat_scale_to_covar_preci_bwd(
+                    N, ptr(q), ptr(s), int(ctx.triu), ptr(vc), ptr(vp), ptr(v_q), ptr(v_s), st
+                ),
+                "quat_scale_to_covar_preci_bwd",
+            )
+        return v_q, v_s, None, None, None
+
+
+def quat_scale_to_covar_preci(
+    quats: Tensor, scales: Tensor, compute_covar: bool = True, compute_preci: bool = True, triu: bool = False
+) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """Quaternions (wxyz, need not be normalised) and scales -> covariance / precision matrices.
+    Shapes: quats [..., 4], scales [..., 3] -> [..., 3, 3] or [..., 6] when ``triu``."""
+    if quats.shape[-1] != 4 or scales.shape[-1] != 3 or quats.shape[:-1] != scales.shape[:-1]:
+        raise ValueError(f"bad shapes quats {tuple(quats.shape)} scales {tuple(scales.shape)}")
+    return _QuatScaleToCovarPreci.apply(quats, scales, compute_covar, compute_preci, triu)
+
+
+# --------------------------------------------------------------------------------------------
+# fully_fused_projection (dense)
+
+
+class _FullyFusedProjection(torch.autograd.Function):
+    @staticmethod
+    def forward(
+        ctx, means, covars, quats, scales, opacities, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+        radius_clip, calc_compensations, camera_model_id,
+    ):
+        dev = require_cuda(means, viewmats, Ks)
+        means, covars, quats, scales = f32c(means, "means"), f32c(covars, "covars"), f32c(quats, "quats"), f32c(scales, "scales")
+        opacities, viewmats, Ks = f32c(opacities, "opacities"), f32c(viewmats, "viewmats"), f32c(Ks, "Ks")
+        batch = tuple(means.shape[:-2])
+        B, N, C = _prod(batch), means.shape[-2], viewmats.shape[-3]
+        o = dict(device=dev, dtype=torch.float32)
+        radii = torch.empty(batch + (C, N, 2), device=dev, dtype=torch.int32)
+        means2d = torch.empty(batch + (C, N, 2), **o)
+        depths = torch.empty(batch + (C, N), **o)
+        conics = torch.empty(batch + (C, N, 3), **o)
+        comps = torch.empty(batch + (C, N), **o) if calc_compensations else None
+        with _Ctx(dev) as st:
+            check(
+                lib().gsb200_projection_fwd(
+                    B, C, N, ptr(means), ptr(covars), ptr(quats), ptr(scales), ptr(opacities), ptr(viewmats), ptr(Ks),
+                    width, height, eps2d, near_plane, far_plane, radius_clip, camera_model_id, ptr(radii), ptr(means2d),
+                    ptr(depths), ptr(conics), ptr(comps), st,
+                ),
+                "projection_ewa_3dgs_fused",
+            )
+        ctx.save_for_backward(means, covars, quats, scales, viewmats, Ks, radii, conics, comps)
+        ctx.meta = (width, height, eps2d, camera_model_id)
+        ctx.mark_non_differentiable(radii)
+        return radii, means2d, depths, conics, comps
+
+    @staticmethod
+    def backward(ctx, v_radii, v_means2d, v_depths, v_conics, v_comps):
+        means, covars, quats, scales, viewmats, Ks, radii, conics, comps = ctx.saved_tensors
+        width, height, eps2d, cam_id = ctx.meta
+        batch = tuple(means.shape[:-2])
+        B, N, C = _prod(batch), means.shape[-2], viewmats.shape[-3]
+        dev = means.device
+        z = lambda shape: torch.zeros(shape, device=dev, dtype=torch.float32)  # noqa: E731
+        if v_means2d is None:
+            v_means2d = z(batch + (C, N, 2))
+        if v_depths is None:
+            v_depths = z(batch + (C, N))
+        if v_conics is None:
+            v_conics = z(batch + (C, N, 3))
+        v_means2d, s_m2 = _rows(v_means2d, 2, "v_means2d")
+        v_depths, s_d = _rows(v_depths, 1, "v_depths")
+        v_conics, s_c = _rows(v_conics, 3, "v_conics")
+        v_comps = None if (v_comps is None or comps is None) else v_comps.contiguous()
+        need_vm = ctx.needs_input_grad[5]
+        v_means = torch.empty_like(means)
+        v_covars = torch.empty_like(covars) if covars is not None else None
+        v_quats = torch.empty_like(quats) if covars is None else None
+        v_scales = torch.empty_like(scales) if covars is None else None
+        v_viewmats = torch.empty_like(viewmats) if need_vm else None
+        with _Ctx(dev) as st:
+            check(
+                lib().gsb200_projection_bwd(
+                    B, C, N, ptr(means), ptr(covars), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), width, height,
+                    eps2d, cam_id, ptr(radii), ptr(conics), ptr(comps), ptr(v_means2d), s_m2, ptr(v_depths), s_d,
+                    ptr(v_conics), s_c, ptr(v_comps), ptr(v_means), ptr(v_covars), ptr(v_quats), ptr(v_scales),
+                    ptr(v_viewmats), st,
+                ),
+                "projection_ewa_3dgs_fused_bwd",
+            )
+        return (v_means, v_covars, v_quats, v_scales, None, v_viewmats) + (None,) * 9
+
+
+def fully_fused_projection(
+    means: Tensor,  # [..., N, 3]
+    covars: Optional[Tensor],  # [..., N, 6] or None
+    quats: Optional[Tensor],  # [..., N, 4] or None
+    scales: Optional[Tensor],  # [..., N, 3] or None
+    viewmats: Tensor,  # [..., C, 4, 4]
+    Ks: Tensor,  # [..., C, 3, 3]
+    width: int,
+    height: int,
+    eps2d: float = 0.3,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    packed: bool = False,
+    sparse_grad: bool = False,
+    calc_compensations: bool = False,
+    camera_model: str = "pinhole",
+    opacities: Optional[Tensor] = None,  # [..., N] or None
+):
+    """Projects Gaussians to 2D (EWA).  Returns (radii int32 [..., C, N, 2], means2d [..., C, N, 2],
+    depths [..., C, N], conics [..., C, N, 3], compensations [..., C, N] | None).  ``radii == 0`` marks
+    culled entries; their float outputs are zero."""
+    if packed:
+        raise NotImplementedError("fully_fused_projection(packed=True) is a 'next' row (SURVEY.md section 8f.1)")
+    if sparse_grad:
+        raise AssertionError("sparse_grad is only supported when packed is True")
+    if covars is None and (quats is None or scales is None):
+        raise ValueError("either covars or (quats, scales) must be given")
+    if covars is not None:
+        quats = scales = None
+    cam = _camera_model_id(camera_model)
+    return _FullyFusedProjection.apply(
+        means, covars, quats, scales, opacities, viewmats, Ks, int(width), int(height), float(eps2d), float(near_plane),
+        float(far_plane), float(radius_clip), bool(calc_compensations), cam,
+    )
+
+
+# --------------------------------------------------------------------------------------------
+# spherical_harmonics (dense)
+
+
+class _SphericalHarmonics(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, degrees_to_use, means, viewmats, coeffs, masks):
+        dev = require_cuda(means, viewmats, coeffs)
+        means, viewmats, coeffs = f32c(means, "means"), f32c(viewmats, "viewmats"), f32c(coeffs, "coeffs")
+        batch = tuple(means.shape[:-2])
+        B, N, C = _prod(batch), means.shape[-2], viewmats.shape[-3]
+        K, D = coeffs.shape[-2:]
+        m8 = None
+        if masks is not None:
+            m8 = masks.contiguous().view(torch.uint8) if masks.dtype == torch.bool else masks.to(torch.uint8).contiguous()
+        colors = torch.empty(batch + (C, N, D), device=dev, dtype=torch.float32)
+        with _Ctx(dev) as st:
+            check(
+                lib().gsb200_sh_fwd(B, C, N, K, D, degrees_to_use, ptr(means), ptr(viewmats), ptr(coeffs), ptr(m8), ptr(colors), st),
+                "spherical_harmonics",
+            )
+        ctx.save_for_backward(means, viewmats, coeffs, m8)
+        ctx.deg = degrees_to_use
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        means, viewmats, coeffs, m8 = ctx.saved_tensors
+        if ctx.needs_input_grad[2]:
+            raise NotImplementedError(
+                "spherical_harmonics: gradient w.r.t. viewmats (pose optimisation through the SH view "
+                "direction) is not built; reference: csrc/SphericalHarmonicsViewDirectionCUDA.cu"
+            )
+        batch = tuple(means.shape[:-2])
+        B, N, C = _prod(batch), means.shape[-2], viewmats.shape[-3]
+        K, D = coeffs.shape[-2:]
+        v_colors = v_colors.contiguous()
+        v_coeffs = torch.empty_like(coeffs)
+        v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
+        with _Ctx(means.device) as st:
+            check(
+                lib().gsb200_sh_bwd(
+                    B, C, N, K, D, ctx.deg, ptr(means), ptr(viewmats), ptr(coeffs), ptr(m8), ptr(v_colors), ptr(v_coeffs),
+                    ptr(v_means), st,
+                ),
+                "spherical_harmonics_bwd",
+            )
+        return None, v_means, None, v_coeffs, None
+
+
+def spherical_harmonics(
+    degrees_to_use: int,
+    means: Tensor,  # [..., N, 3]
+    viewmats: Tensor,  # [..., C, 4, 4]
+    coeffs: Tensor,  # [N, K, D]
+    masks: Optional[Tensor] = None,  # [..., C, N]
+    batch_ids: Optional[Tensor] = None,
+    camera_ids: Optional[Tensor] = None,
+    gaussian_ids: Optional[Tensor] = None,
+    viewmats_rs: Optional[Tensor] = None,
+) -> Tensor:
+    """Evaluates SH colours for view directions ``mean - camera_position`` (camera position recovered as
+    ``-R^T t``).  Returns [..., C, N, D]; masked-off rows are 0."""
+    if batch_ids is not None or camera_ids is not None or gaussian_ids is not None:
+        raise NotImplementedError("packed spherical_harmonics is a 'next' row (SURVEY.md section 8f.1)")
+    if viewmats_rs is not None:
+        raise NotImplementedError("rolling-shutter view matrices are out of scope")
+    if coeffs.dim() != 3 or coeffs.shape[0] != means.shape[-2]:
+        raise ValueError(f"coeffs must be [N, K, D]; got {tuple(coeffs.shape)} for N={means.shape[-2]}")
+    if not (0 <= degrees_to_use <= 4) or (degrees_to_use + 1) ** 2 > coeffs.shape[-2]:
+        raise ValueError(f"degrees_to_use={degrees_to_use} needs K >= {(degrees_to_use + 1) ** 2}, got {coeffs.shape[-2]}")
+    return _SphericalHarmonics.apply(int(degrees_to_use), means, viewmats, coeffs, masks)
+
+
+# --------------------------------------------------------------------------------------------
+# fused projection + conic + SH -> RGB (the rasterization() default path)
+
+
+class _ProjectSH(torch.autograd.Function):
+    @staticmethod
+    def forward(
+        ctx, means, quats, scales, opacities, sh_coeffs, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+        radius_clip, sh_degree, calc_compensations,
+    ):
+        dev = require_cuda(means, quats, scales, opacities, sh_coeffs, viewmats, Ks)
+        means, quats, scales = f32c(means, "means"), f32c(quats, "quats"), f32c(scales, "scales")
+        opacities, sh_coeffs = f32c(opacities, "opacities"), f32c(sh_coeffs, "colors")
+        viewmats, Ks = f32c(viewmats, "viewmats"), f32c(Ks, "Ks")
+        N, C, K = means.shape[0], viewmats.shape[0], sh_coeffs.shape[1]
+        o = dict(device=dev, dtype=torch.float32)
+        radii = torch.empty((C, N, 2), device=dev, dtype=torch.int32)
+        means2d, depths, conics = torch.empty((C, N, 2), **o), torch.empty((C, N), **o), torch.empty((C, N, 3), **o)
+        colors = torch.empty((C, N, 3), **o)
+        comps = torch.empty((C, N), **o) if calc_compensations else None
+        with _Ctx(dev) as st:
+            check(
+                lib().gsb200_project_sh_fwd(
+                    C, N, K, sh_degree, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(sh_coeffs),
+                    ptr(viewmats), ptr(Ks), width, height, eps2d, near_plane, far_plane, radius_clip,
+                    int(calc_compensations), ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(colors), st,
+                ),
+                "project_sh_fwd",
+            )
+        ctx.save_for_backward(means, quats, scales, sh_coeffs, viewmats, Ks, radii, conics, comps, colors)
+        ctx.meta = (width, height, eps2d, sh_degree)
+        ctx.mark_non_differentiable(radii)
+        return radii, means2d, depths, conics, colors, comps
+
+    @staticmethod
+    def backward(ctx, v_radii, v_means2d, v_depths, v_conics, v_colors, v_comps):
+        means, quats, scales, sh_coeffs, viewmats, Ks, radii, conics, comps, colors = ctx.saved_tensors
+        width, height, eps2d, sh_degree = ctx.meta
+        if ctx.needs_input_grad[5]:
+            raise NotImplementedError("fused project+SH path does not produce viewmats gradients")
+        N, C, K = means.shape[0], viewmats.shape[0], sh_coeffs.shape[1]
+        dev = means.device
+        z = lambda shape: torch.zeros(shape, device=dev, dtype=torch.float32)  # noqa: E731
+        if v_means2d is None:
+            v_means2d = z((C, N, 2))
+        if v_conics is None:
+            v_conics = z((C, N, 3))
+        if v_colors is None:
+            v_colors = z((C, N, 3))
+        v_means2d, s_m2 = _rows(v_means2d, 2, "v_means2d")
+        v_depths, s_d = _rows(v_depths, 1, "v_depths")
+        v_conics, s_c = _rows(v_conics, 3, "v_conics")
+        v_colors, s_col = _rows(v_colors, 3, "v_colors")
+        v_comps = None if (v_comps is None or comps is None) else v_comps.contiguous()
+        v_means, v_quats, v_scales = torch.empty_like(means), torch.empty_like(quats), torch.empty_like(scales)
+        v_sh = torch.empty_like(sh_coeffs)
+        with _Ctx(dev) as st:
+            check(
+                lib().gsb200_project_sh_bwd(
+                    C, N, K, sh_degree, ptr(means), ptr(quats), ptr(scales), ptr(sh_coeffs), ptr(viewmats), ptr(Ks),
+                    width, height, eps2d, ptr(radii), ptr(conics), ptr(comps), ptr(colors), ptr(v_means2d), s_m2,
+                    ptr(v_depths), s_d, ptr(v_conics), s_c, ptr(v_colors), s_col, ptr(v_comps), ptr(v_means),
+                    ptr(v_quats), ptr(v_scales), ptr(v_sh), st,
+                ),
+                "project_sh_bwd",
+            )
+        # opacities only steer culling / radius (non-differentiable there)
+        return (v_means, v_quats, v_scales, None, v_sh, None, None) + (None,) * 8
+
+
+def fused_project_sh(
+    means, quats, scales, opacities, sh_coeffs, viewmats, Ks, width, height, sh_degree, eps2d=0.3, near_plane=0.01,
+    far_plane=1e10, radius_clip=0.0, calc_compensations=False,
+):
+    """One pass over the gaussians: world->camera, covariance->conic, SH->RGB (+0.5, clamped at 0).
+    means [N,3] quats [N,4] scales [N,3] opacities [N] sh_coeffs [N,K,3] viewmats [C,4,4] Ks [C,3,3].
+    Returns (radii, means2d, depths, conics, colors [C,N,3], compensations|None)."""
+    if sh_coeffs.dim() != 3 or sh_coeffs.shape[-1] != 3:
+        raise ValueError("fused_project_sh needs SH coefficients [N, K, 3]")
+    if not (0 <= sh_degree <= 4) or (sh_degree + 1) ** 2 > sh_coeffs.shape[1]:
+        raise ValueError(f"sh_degree={sh_degree} needs K >= {(sh_degree + 1) ** 2}")
+    return _ProjectSH.apply(
+        means, quats, scales, opacities, sh_coeffs, viewmats, Ks, int(width), int(height), float(eps2d),
+        float(near_plane), float(far_plane), float(radius_clip), int(sh_degree), bool(calc_compensations),
+    )
+
+
+# --------------------------------------------------------------------------------------------
+# isect_tiles / isect_offset_encode
+
+_scratch = {}
+
+
+def _scratch_buffer(dev: torch.device, tag: str, nbytes: int) -> Tensor:
+    """Grow-only per-device scratch (CUB temp storage).  Stream-ordered use only."""
+    key = (dev, tag, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), device=dev, dtype=torch.uint8)
+        _scratch[key] = buf
+    return buf
+
+
+@torch.no_grad()
+def isect_tiles(
+    means2d: Tensor,  # [..., N, 2]
+    radii: Tensor,  # [..., N, 2]
+    depths: Tensor,  # [..., N]
+    tile_size: int,
+    tile_width: int,
+    tile_height: int,
+    sort: bool = True,
+    segmented: bool = False,
+    packed: bool = False,
+    n_images: Optional[int] = None,
+    image_ids: Optional[Tensor] = None,
+    gaussian_ids: Optional[Tensor] = None,
+    conics: Optional[Tensor] = None,
+    opacities: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor, Tensor]:
+    """Maps projected Gaussians to the tiles they touch.  With ``conics`` and ``opacities`` the
+    conservative ellipse test (AccuTile / SNUGBOX) is used, otherwise the radius AABB.
+    Returns (tiles_per_gauss int32 [..., N], isect_ids int64 [n_isects], flatten_ids int32 [n_isects])."""
+    if packed:
+        raise NotImplementedError("isect_tiles(packed=True) is a 'next' row (SURVEY.md section 8f.1)")
+    dev = require_cuda(means2d, radii, depths)
+    means2d, depths = f32c(means2d, "means2d"), f32c(depths, "depths")
+    conics, opacities = f32c(conics, "conics"), f32c(opacities, "opacities")
+    if radii.dtype != torch.int32:
+        raise TypeError("radii must be int32")
+    radii = radii.contiguous()
+    image_dims = tuple(means2d.shape[:-2])
+    I, N = _prod(image_dims), means2d.shape[-2]
+    L = lib()
+    n_tiles = tile_width * tile_height
+    image_bits, tile_bits = _cabi.bits_for_count(I), _cabi.bits_for_count(n_tiles)
+    if image_bits + tile_bits > 32:
+        raise RuntimeError(
+            f"intersect_tile: (image, tile) id packing needs {image_bits + tile_bits} bits but only 32 are "
+            f"available (I={I}, n_tiles={n_tiles})."
+        )
+    total = I * N
+    tiles_per_gauss = torch.empty(image_dims + (N,), device=dev, dtype=torch.int32)
+    if total == 0:
+        return (tiles_per_gauss, torch.empty(0, device=dev, dtype=torch.int64), torch.empty(0, device=dev, dtype=torch.int32))
+    accu = conics is not None and opacities is not None
+    cum = torch.empty(total, device=dev, dtype=torch.int64)
+    with _Ctx(dev) as st:
+        ws = _scratch_buffer(dev, "scan", L.gsb200_isect_scan_workspace_bytes(total))
+        check(
+            L.gsb200_isect_count(
+                I, N, ptr(means2d), ptr(radii), ptr(conics) if accu else None, ptr(opacities) if accu else None,
+                tile_size, tile_width, tile_height, ptr(tiles_per_gauss), ptr(cum), ptr(ws), ws.numel(), st,
+            ),
+            "intersect_tile (count)",
+        )
+        n_isects = int(cum[-1].item())  # the one host sync of the forward (reference: csrc/Intersect.cpp:259)
+        isect_ids = torch.empty(n_isects, device=dev, dtype=torch.int64)
+        flatten_ids = torch.empty(n_isects, device=dev, dtype=torch.int32)
+        if n_isects == 0:
+            return tiles_per_gauss, isect_ids, flatten_ids
+        check(
+            L.gsb200_isect_emit(
+                I, N, ptr(means2d), ptr(radii), ptr(depths), ptr(conics) if accu else None,
+                ptr(opacities) if accu else None, ptr(cum), tile_size, tile_width, tile_height, ptr(isect_ids),
+                ptr(flatten_ids), st,
+            ),
+            "intersect_tile (emit)",
+        )
+        if sort:
+            end_bit = 32 + tile_bits + image_bits
+            keys_out, vals_out = torch.empty_like(isect_ids), torch.empty_like(flatten_ids)
+            ws = _scratch_buffer(dev, "sort", L.gsb200_sort_workspace_bytes(n_isects, end_bit))
+            check(
+                L.gsb200_sort_pairs(
+                    n_isects, end_bit, ptr(isect_ids), ptr(flatten_ids), ptr(keys_out), ptr(vals_out), ptr(ws), ws.numel(), st
+                ),
+                "intersect_tile (sort)",
+            )
+            isect_ids, flatten_ids = keys_out, vals_out
+    return tiles_per_gauss, isect_ids, flatten_ids
+
+
+@torch.no_grad()
+def isect_offset_encode(isect_ids: Tensor, n_images: int, tile_width: int, tile_height: int) -> Tensor:
+    """Sorted intersection ids -> per-(image, tile) start offsets, int32 [n_images, tile_height, tile_width]."""
+    dev = require_cuda(isect_ids)
+    if isect_ids.dtype != torch.int64:
+        raise TypeError("isect_ids must be int64")
+    isect_ids = isect_ids.contiguous()
+    offsets = torch.empty((n_images, tile_height, tile_width), device=dev, dtype=torch.int32)
+    with _Ctx(dev) as st:
+        check(
+            lib().gsb200_isect_offsets(isect_ids.shape[0], ptr(isect_ids), n_images, tile_width, tile_height, ptr(offsets), st),
+            "intersect_offset",
+        )
+    return offsets
+
+
+# --------------------------------------------------------------------------------------------
+# rasterize_to_pixels
+
+_SUPPORTED_CHANNELS = (1, 2, 3, 4, 5, 8, 16, 32)
+
+
+def _grad_record_width(D: int, absgrad: bool) -> int:
+    return ((6 + D + (2 if absgrad else 0)) + 3) // 4 * 4
+
+
+class _RasterizeToPixels(torch.autograd.Function):
+    @staticmethod
+    def forward(
+        ctx, means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size, isect_offsets,
+        flatten_ids, absgrad_holder,
+    ):
+        dev = require_cuda(means2d, conics, colors, opacities)
+        means2d, conics, colors, opacities = f32c(means2d, "means2d"), f32c(conics, "conics"), f32c(colors, "colors"), f32c(opacities, "opacities")
+        backgrounds = f32c(backgrounds, "backgrounds")
+        # image dims come from the offsets; the gaussian rows may be dense [..., N, *] or packed [nnz, *]
+        image_dims = tuple(isect_offsets.shape[:-2])
+        row_dims = tuple(means2d.shape[:-1])
+        I, R, D = _prod(image_dims), _prod(row_dims), colors.shape[-1]
+        N = R // I if I > 0 and R % max(I, 1) == 0 else R
+        th, tw = isect_offsets.shape[-2:]
+        m8 = None
+        if masks is not None:
+            m8 = masks.contiguous().view(torch.uint8) if masks.dtype == torch.bool else masks.to(torch.uint8).contiguous()
+        offsets = isect_offsets.contiguous()
+        fl = flatten_ids.contiguous()
+        if offsets.dtype != torch.int32 or fl.dtype != torch.int32:
+            raise TypeError("isect_offsets and flatten_ids must be int32")
+        S = fl.shape[0]
+        L = lib()
+        records = torch.empty(max(L.gsb200_raster_records_bytes(S, D), 16), device=dev, dtype=torch.uint8)
+        o = dict(device=dev, dtype=torch.float32)
+        render_colors = torch.empty(image_dims + (height, width, D), **o)
+        render_alphas = torch.empty(image_dims + (height, width, 1), **o)
+        last_ids = torch.empty(image_dims + (height, width), device=dev, dtype=torch.int32)
+        with _Ctx(dev) as st:
+            check(
+                L.gsb200_raster_fwd(
+                    I, N, D, ptr(means2d), ptr(conics), ptr(colors), ptr(opacities), ptr(backgrounds), ptr(m8), width,
+                    height, tile_size, tw, th, ptr(offsets), ptr(fl), S, ptr(records), ptr(render_colors),
+                    ptr(render_alphas), ptr(last_ids), st,
+                ),
+                "rasterize_to_pixels_3dgs",
+            )
+        ctx.save_for_backward(backgrounds, m8, offsets, fl, records, render_alphas, last_ids)
+        ctx.absgrad_holder = absgrad_holder  # filled in place by backward; deliberately not a saved tensor
+        ctx.meta = (row_dims, I, N, R, D, width, height, tile_size, tw, th, S)
+        return render_colors, render_alphas
+
+    @staticmethod
+    def backward(ctx, v_render_colors, v_render_alphas):
+        backgrounds, m8, offsets, fl, records, render_alphas, last_ids = ctx.saved_tensors
+        absgrad_holder = ctx.absgrad_holder
+        row_dims, I, N, R, D, width, height, tile_size, tw, th, S = ctx.meta
+        dev = render_alphas.device
+        v_render_colors = v_render_colors.contiguous()
+        v_render_alphas = v_render_alphas.contiguous()
+        absgrad = absgrad_holder is not None
+        P = _grad_record_width(D, absgrad)
+        # one packed gradient record per gaussian: [v_xy 2 | v_conic 3 | v_opacity 1 | v_rgb D | (abs 2) | pad]
+        rec = torch.zeros((R, P), device=dev, dtype=torch.float32)
+        base = rec.data_ptr()
+        with _Ctx(dev) as st:
+            check(
+                lib().gsb200_raster_bwd(
+                    I, N, D, ptr(backgrounds), ptr(m8), width, height, tile_size, tw, th, ptr(offsets), ptr(fl), S,
+                    ptr(records), ptr(render_alphas), ptr(last_ids), ptr(v_render_colors), ptr(v_render_alphas),
+                    base, P, base + 8, P, base + 24, P, base + 20, P, (base + 4 * (6 + D)) if absgrad else None, P, st,
+                ),
+                "rasterize_to_pixels_3dgs_bwd",
+            )
+        rec = rec.view(row_dims + (P,))
+        v_means2d, v_conics, v_opacities, v_colors = rec[..., 0:2], rec[..., 2:5], rec[..., 5], rec[..., 6 : 6 + D]
+        if absgrad:
+            absgrad_holder.copy_(rec[..., 6 + D : 8 + D])
+        v_backgrounds = None
+        if backgrounds is not None and ctx.needs_input_grad[4]:
+            v_backgrounds = (v_render_colors * (1.0 - render_alphas)).sum(dim=(-3, -2))
+        return (v_means2d, v_conics, v_colors, v_opacities, v_backgrounds) + (None,) * 7
+
+
+def rasterize_to_pixels(
+    means2d: Tensor,  # [..., N, 2]
+    conics: Tensor,  # [..., N, 3]
+    colors: Tensor,  # [..., N, channels]
+    opacities: Tensor,  # [..., N]
+    image_width: int,
+    image_height: int,
+    tile_size: int,
+    isect_offsets: Tensor,  # [..., tile_height, tile_width]
+    flatten_ids: Tensor,  # [n_isects]
+    backgrounds: Optional[Tensor] = None,  # [..., channels]
+    masks: Optional[Tensor] = None,  # [..., tile_height, tile_width]
+    packed: bool = False,
+    absgrad: bool = False,
+) -> Tuple[Tensor, Tensor]:
+    """Front-to-back alpha compositing of depth-sorted Gaussians per 16x16 tile.
+    Returns (render_colors [..., H, W, channels], render_alphas [..., H, W, 1]).  With ``absgrad`` the
+    backward fills ``means2d.absgrad``."""
+    if packed != (means2d.dim() == 2):
+        raise ValueError(f"packed={packed} but means2d has shape {tuple(means2d.shape)}")
+    if tile_size != 16:
+        raise ValueError(f"Unsupported tile_size {tile_size}; gsplat_b200 is built for tile_size 16")
+    D = colors.shape[-1]
+    if D > 32:
+        raise ValueError(
+            f"Unsupported number of color channels: {D}. gsplat_b200 rasterizes up to 32 channels per pass "
+            "(rasterization() chunks wider features with channel_chunk=32)."
+        )
+    pad = 0
+    if D not in _SUPPORTED_CHANNELS:
+        target = next(c for c in _SUPPORTED_CHANNELS if c >= D)
+        pad = target - D
+        colors = torch.nn.functional.pad(colors, (0, pad))
+        if backgrounds is not None:
+            backgrounds = torch.nn.functional.pad(backgrounds, (0, pad))
+    holder = torch.zeros_like(means2d) if absgrad else None
+    render_colors, render_alphas = _RasterizeToPixels.apply(
+        means2d, conics, colors, opacities, backgrounds, masks, int(image_width), int(image_height), int(tile_size),
+        isect_offsets, flatten_ids, holder,
+    )
+    if absgrad:
+        means2d.absgrad = holder
+    if pad:
+        render_colors = render_colors[..., :D]
+    return render_colors, render_alphas

@@ -1,0 +1,290 @@
+"""rasterization(): the public entry point, signature-compatible with the reference
+(/root/reference/gsplat/rendering.py:234-690).  Orchestration (projection -> SH -> tile intersection ->
+offsets -> compositing, channel chunking, depth channels, meta dict) stays in Python and follows the
+reference's own Python restatement ``_rasterization`` (rendering.py:722-1106) and the C++ orchestrator it
+mirrors (csrc/Rendering.cpp:745-1481); every kernel is ours (gsplat_b200.ops).
+
+Scope: the 3DGS EWA path named by BASELINE.json (pinhole cameras, dense or "packed" bookkeeping,
+classic / antialiased, RGB / D / ED / RGB+D / RGB+ED, backgrounds, absgrad, SH or post-activation
+colours).  3DGUT (with_ut / with_eval3d), lidar, distortion, rolling shutter, extra signals and normals
+are out of scope and raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from .ops import (
+    fully_fused_projection,
+    fused_project_sh,
+    isect_offset_encode,
+    isect_tiles,
+    rasterize_to_pixels,
+    spherical_harmonics,
+)
+
+_COLOR_MODES = {"RGB", "RGB-d", "RGB-Ed", "RGB+D", "RGB+ED"}
+_HIT_DISTANCE_MODES = {"d", "Ed", "RGB-d", "RGB-Ed"}
+_DEPTH_MODES = {"D", "ED", "RGB+D", "RGB+ED"}
+_EXPECTED_MODES = {"Ed", "ED", "RGB-Ed", "RGB+ED"}
+_ALL_MODES = _COLOR_MODES | _HIT_DISTANCE_MODES | _DEPTH_MODES
+
+
+def _unsupported(name: str, why: str = "out of scope for the gsplat_b200 hot path (SURVEY.md section 8)"):
+    raise NotImplementedError(f"rasterization({name}): {why}")
+
+
+def rasterization(
+    means: Tensor,  # [..., N, 3]
+    quats: Optional[Tensor],  # [..., N, 4]
+    scales: Optional[Tensor],  # [..., N, 3]
+    opacities: Tensor,  # [..., N]
+    colors: Optional[Tensor],  # [..., (C,) N, D] or [N, K, 3] SH coefficients
+    viewmats: Tensor,  # [..., C, 4, 4]
+    Ks: Tensor,  # [..., C, 3, 3]
+    width: int,
+    height: int,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    eps2d: float = 0.3,
+    sh_degree: Optional[int] = None,
+    packed: bool = True,
+    tile_size: Optional[int] = None,
+    backgrounds: Optional[Tensor] = None,
+    render_mode: str = "RGB",
+    sparse_grad: bool = False,
+    absgrad: bool = False,
+    rasterize_mode: str = "classic",
+    channel_chunk: int = 32,
+    distributed: bool = False,
+    camera_model: str = "pinhole",
+    segmented: bool = False,
+    covars: Optional[Tensor] = None,
+    with_ut: bool = False,
+    with_eval3d: bool = False,
+    return_normals: bool = False,
+    global_z_order: bool = True,
+    rays: Optional[Tensor] = None,
+    radial_coeffs: Optional[Tensor] = None,
+    tangential_coeffs: Optional[Tensor] = None,
+    thin_prism_coeffs: Optional[Tensor] = None,
+    ftheta_coeffs=None,
+    lidar_coeffs=None,
+    external_distortion_coeffs=None,
+    rolling_shutter=None,
+    viewmats_rs: Optional[Tensor] = None,
+    ut_params=None,
+    extra_signals: Optional[Tensor] = None,
+    extra_signals_sh_degree: Optional[int] = None,
+    renderer_config=None,
+) -> Tuple[Tensor, Tensor, Dict]:
+    """Rasterize N 3D Gaussians to C image planes.  Returns (render_colors [..., C, H, W, X],
+    render_alphas [..., C, H, W, 1], meta) with the reference's meta keys."""
+    # ---- features outside the path
+    if with_ut or with_eval3d:
+        _unsupported("with_ut/with_eval3d", "3DGUT is a different algorithm (SURVEY.md section 2.1 #16)")
+    for name, val in (
+        ("rays", rays), ("radial_coeffs", radial_coeffs), ("tangential_coeffs", tangential_coeffs),
+        ("thin_prism_coeffs", thin_prism_coeffs), ("ftheta_coeffs", ftheta_coeffs), ("lidar_coeffs", lidar_coeffs),
+        ("external_distortion_coeffs", external_distortion_coeffs), ("viewmats_rs", viewmats_rs),
+        ("ut_params", ut_params), ("extra_signals", extra_signals), ("renderer_config", renderer_config),
+    ):
+        if val is not None:
+            _unsupported(name)
+    if return_normals:
+        _unsupported("return_normals")
+    if rolling_shutter is not None and getattr(rolling_shutter, "name", str(rolling_shutter)) not in ("GLOBAL", "RollingShutterType.GLOBAL"):
+        _unsupported("rolling_shutter")
+    if camera_model != "pinhole":
+        _unsupported(f"camera_model={camera_model!r}", "only the pinhole EWA projection is built")
+    if render_mode not in _ALL_MODES:
+        raise ValueError(f"unknown render_mode {render_mode!r}")
+    if render_mode in _HIT_DISTANCE_MODES:
+        _unsupported(f"render_mode={render_mode!r}", "hit-distance modes belong to the eval3d (3DGUT) renderer")
+    if rasterize_mode not in ("classic", "antialiased"):
+        raise ValueError(f"unknown rasterize_mode {rasterize_mode!r}")
+    if sparse_grad:
+        _unsupported("sparse_grad", "sparse COO gradients are a 'next' row (SURVEY.md section 8f.1)")
+    if distributed:
+        if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            raise ValueError("distributed=True requires an initialized default torch.distributed process group.")
+        if torch.distributed.get_world_size() > 1:
+            _unsupported(
+                "distributed=True (world_size > 1)",
+                "gaussian-sharded rendering is a 'next' row; gsplat_b200.distributed offers view-parallel DP",
+            )
+    if tile_size is None:
+        tile_size = 16
+    if tile_size != 16:
+        raise ValueError(f"Unsupported tile_size {tile_size}; gsplat_b200 is built for tile_size 16")
+
+    has_color = render_mode in _COLOR_MODES
+    has_depth = render_mode in _DEPTH_MODES
+    batch_dims = tuple(means.shape[:-2])
+    nb = len(batch_dims)
+    B = math.prod(batch_dims) if batch_dims else 1
+    N = means.shape[-2]
+    C = viewmats.shape[-3]
+    I = B * C
+
+    # ---- shape validation (reference rendering.py:526-556 / Rendering.cpp:97-512)
+    if means.shape[-1] != 3:
+        raise ValueError(f"means must be [..., N, 3], got {tuple(means.shape)}")
+    if covars is None:
+        if quats is None or scales is None:
+            raise ValueError("either covars or (quats, scales) is required")
+        if tuple(quats.shape) != batch_dims + (N, 4) or tuple(scales.shape) != batch_dims + (N, 3):
+            raise ValueError(f"quats/scales shape mismatch: {tuple(quats.shape)}, {tuple(scales.shape)}")
+    else:
+        if tuple(covars.shape) != batch_dims + (N, 3, 3):
+            raise ValueError(f"covars must be [..., N, 3, 3], got {tuple(covars.shape)}")
+        quats = scales = None
+        tri = ([0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2])
+        covars = covars[..., tri[0], tri[1]]
+    if tuple(opacities.shape) != batch_dims + (N,):
+        raise ValueError(f"opacities must be [..., N], got {tuple(opacities.shape)}")
+    if tuple(viewmats.shape) != batch_dims + (C, 4, 4) or tuple(Ks.shape) != batch_dims + (C, 3, 3):
+        raise ValueError(f"viewmats/Ks shape mismatch: {tuple(viewmats.shape)}, {tuple(Ks.shape)}")
+    if has_color:
+        if colors is None:
+            raise ValueError(f"render_mode={render_mode!r} needs colors")
+        if sh_degree is None:
+            ok = (colors.dim() == nb + 2 and tuple(colors.shape[:-1]) == batch_dims + (N,)) or (
+                colors.dim() == nb + 3 and tuple(colors.shape[:-1]) == batch_dims + (C, N)
+            )
+            if not ok:
+                raise ValueError(f"colors must be [..., N, D] or [..., C, N, D], got {tuple(colors.shape)}")
+        else:
+            if colors.dim() != 3 or colors.shape[0] != N:
+                raise ValueError(f"SH colors must be [N, K, D], got {tuple(colors.shape)}")
+            if (sh_degree + 1) ** 2 > colors.shape[-2]:
+                raise ValueError(f"sh_degree={sh_degree} needs K >= {(sh_degree + 1) ** 2}, got {colors.shape[-2]}")
+
+    antialiased = rasterize_mode == "antialiased"
+
+    # ---- projection (+ SH): fused single pass when it applies
+    fused = (
+        has_color and sh_degree is not None and covars is None and nb == 0 and colors.shape[-1] == 3
+        and not viewmats.requires_grad
+    )
+    if fused:
+        radii, means2d, depths, conics, feat, compensations = fused_project_sh(
+            means, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree, eps2d, near_plane,
+            far_plane, radius_clip, antialiased,
+        )
+    else:
+        radii, means2d, depths, conics, compensations = fully_fused_projection(
+            means, covars, quats, scales, viewmats, Ks, width, height, eps2d=eps2d, near_plane=near_plane,
+            far_plane=far_plane, radius_clip=radius_clip, packed=False, calc_compensations=antialiased,
+            camera_model=camera_model, opacities=opacities,
+        )
+        feat = None
+        if has_color:
+            if sh_degree is None:
+                feat = colors
+                if feat.dim() == nb + 2:
+                    feat = torch.broadcast_to(feat[..., None, :, :], batch_dims + (C, N, feat.shape[-1]))
+            else:
+                valid = (radii > 0).all(dim=-1)
+                feat = spherical_harmonics(sh_degree, means, viewmats, colors, masks=valid)
+                feat = torch.clamp_min(feat + 0.5, 0.0)
+
+    opac = torch.broadcast_to(opacities[..., None, :], batch_dims + (C, N))
+    if compensations is not None:
+        opac = opac * compensations
+
+    # ---- tile intersection (AccuTile) + offsets
+    tile_width = math.ceil(width / float(tile_size))
+    tile_height = math.ceil(height / float(tile_size))
+    tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(
+        means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, segmented=segmented, packed=False,
+        n_images=I, conics=conics, opacities=opac,
+    )
+    isect_offsets = isect_offset_encode(isect_ids, I, tile_width, tile_height).reshape(
+        batch_dims + (C, tile_height, tile_width)
+    )
+
+    camera_ids = gaussian_ids = batch_ids = None
+    if packed:
+        # Reference packed=True bookkeeping (rendering.py:347-353, Rendering.cpp:936-973): per-view data
+        # live in [nnz, ...] COO rows addressed by (batch_ids, camera_ids, gaussian_ids).  The projection
+        # itself still runs dense here (the two-pass compacting projection kernel is a "next" row,
+        # SURVEY.md section 8f.1); rows are gathered afterwards so that images, gradients and the meta
+        # contract are those of the reference's packed mode.
+        sel = (radii > 0).all(dim=-1)  # [..., C, N]
+        flat_sel = sel.reshape(-1)
+        rows = torch.nonzero(flat_sel, as_tuple=False).squeeze(-1)  # ascending (b, c, n) order
+        inv = torch.cumsum(flat_sel, 0, dtype=torch.int64) - 1
+        gaussian_ids = (rows % N).to(torch.int32)
+        camera_ids = ((rows // N) % C).to(torch.int32)
+        batch_ids = (rows // (N * C)).to(torch.int32)
+        radii = radii.reshape(-1, 2)[rows]
+        means2d = means2d.reshape(-1, 2)[rows]
+        depths = depths.reshape(-1)[rows]
+        conics = conics.reshape(-1, 3)[rows]
+        opac = opac.reshape(-1)[rows]
+        if feat is not None:
+            feat = feat.reshape(-1, feat.shape[-1])[rows]
+        tiles_per_gauss = tiles_per_gauss.reshape(-1)[rows]
+        flatten_ids = inv[flatten_ids.long()].to(torch.int32)
+
+    # ---- assemble channels: [colour | depth]
+    if has_color and has_depth:
+        feat = torch.cat((feat, depths[..., None]), dim=-1)
+        if backgrounds is not None:
+            backgrounds = torch.cat([backgrounds, torch.zeros(batch_dims + (C, 1), device=backgrounds.device)], dim=-1)
+    elif not has_color:
+        feat = depths[..., None]
+        if backgrounds is not None:
+            backgrounds = torch.zeros(batch_dims + (C, 1), device=backgrounds.device)
+
+    # ---- compositing (chunked over channels, reference Rendering.cpp:1353-1447)
+    n_ch = feat.shape[-1]
+    if n_ch > channel_chunk:
+        outs, render_alphas = [], None
+        for lo in range(0, n_ch, channel_chunk):
+            bg = backgrounds[..., lo : lo + channel_chunk] if backgrounds is not None else None
+            rc, ra = rasterize_to_pixels(
+                means2d, conics, feat[..., lo : lo + channel_chunk], opac, width, height, tile_size, isect_offsets,
+                flatten_ids, backgrounds=bg, packed=packed, absgrad=absgrad,
+            )
+            outs.append(rc)
+            if render_alphas is None:
+                render_alphas = ra
+        render_colors = torch.cat(outs, dim=-1)
+    else:
+        render_colors, render_alphas = rasterize_to_pixels(
+            means2d, conics, feat, opac, width, height, tile_size, isect_offsets, flatten_ids, backgrounds=backgrounds,
+            packed=packed, absgrad=absgrad,
+        )
+
+    if render_mode in _EXPECTED_MODES:  # ED / RGB+ED: normalise accumulated depth
+        depth = render_colors[..., -1:] / render_alphas.clamp(min=1e-10)
+        render_colors = torch.cat([render_colors[..., :-1], depth], dim=-1)
+
+    meta = {
+        "batch_ids": batch_ids,
+        "camera_ids": camera_ids,
+        "gaussian_ids": gaussian_ids,
+        "radii": radii,
+        "means2d": means2d,
+        "depths": depths,
+        "conics": conics,
+        "opacities": opac,
+        "tile_width": tile_width,
+        "tile_height": tile_height,
+        "tiles_per_gauss": tiles_per_gauss,
+        "isect_ids": isect_ids,
+        "flatten_ids": flatten_ids,
+        "isect_offsets": isect_offsets,
+        "width": width,
+        "height": height,
+        "tile_size": tile_size,
+        "n_batches": B,
+        "n_cameras": C,
+    }
+    return render_colors, render_alphas, meta

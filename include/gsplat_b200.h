@@ -1,0 +1,179 @@
+/*
+ * gsplat_b200.h -- C ABI of libgsplat_b200.so: the B200-native (sm_100a) replacement for the
+ * CUDA operators behind gsplat.rasterization().
+ *
+ * This is the drop-in boundary.  Every entry point takes plain DEVICE pointers, sizes and a
+ * cudaStream_t (passed as void*), allocates nothing that outlives the call (scratch comes from the
+ * caller through *_workspace_bytes queries) and returns 0 on success or a negative GSB200_E_* code
+ * (gsb200_error_string() gives the text).  The host side (gsplat_b200/*.py: torch.autograd.Function
+ * wrappers with the reference's names and argument meaning) owns allocation, autograd and streams.
+ *
+ * Each function cites the reference operator schema it replaces
+ * (/root/reference/gsplat/cuda/ext.cpp) and the Python wrapper that calls it
+ * (/root/reference/gsplat/cuda/_wrapper.py).
+ *
+ * Layout conventions (the reference's): row-major contiguous fp32 unless noted; quaternions wxyz;
+ * conics = (a, b, c) upper triangle of the inverse 2-D covariance; radii int32 [.., 2];
+ * isect_ids int64 = image << (32 + tile_bits) | tile << 32 | float_bits(depth);
+ * flatten_ids int32 index into [I * N].
+ */
+#ifndef GSPLAT_B200_H
+#define GSPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define GSB200_OK 0
+#define GSB200_E_INVALID -1     /* bad argument (null pointer, negative size, ...)            */
+#define GSB200_E_UNSUPPORTED -2 /* valid in the reference, not built here (camera model, channels, tile size) */
+#define GSB200_E_CUDA -3        /* a CUDA runtime call / kernel launch failed (see gsb200_last_cuda_error) */
+#define GSB200_E_WORKSPACE -4   /* workspace too small                                        */
+#define GSB200_E_KEYBITS -5     /* (image, tile) id needs more than 32 key bits (csrc/Intersect.cpp:219-228) */
+
+    const char *gsb200_version(void);
+    const char *gsb200_error_string(int code);
+    /* cudaGetErrorString of the last CUDA failure seen by this library on the calling thread. */
+    const char *gsb200_last_cuda_error(void);
+    /* Bits needed to index `count` items (csrc/MathUtils.h:26-36 bits_for_count). Host-only. */
+    uint32_t gsb200_bits_for_count(int64_t count);
+    /* 1 when colour channel count D is compiled into the rasterizer (Config.h GSPLAT_NUM_CHANNELS analogue). */
+    int gsb200_raster_supports_channels(int D);
+
+    /* ---- quat_scale_to_covar_preci / _bwd : ext.cpp:984-991, _wrapper.py:657-716 ----
+     * covars / precis: [N,3,3] or [N,6] when triu; either may be NULL (not requested). */
+    int gsb200_quat_scale_to_covar_preci_fwd(
+        int64_t N, const float *quats, const float *scales, int triu, float *covars, float *precis, void *stream
+    );
+    int gsb200_quat_scale_to_covar_preci_bwd(
+        int64_t N, const float *quats, const float *scales, int triu, const float *v_covars, const float *v_precis,
+        float *v_quats, float *v_scales, void *stream
+    );
+
+    /* ---- projection_ewa_3dgs_fused / _bwd : ext.cpp:1052-1063, _wrapper.py:819-963, 966-1063 ----
+     * means [B,N,3]; covars [B,N,6] XOR (quats [B,N,4], scales [B,N,3]); opacities [B,N] or NULL;
+     * viewmats [B,C,4,4]; Ks [B,C,3,3].  Outputs [B,C,N,*]; compensations NULL unless requested.
+     * Culled gaussians get radii = 0 and ZEROED float outputs (the reference leaves them
+     * uninitialised, csrc/Projection.cpp:395-404).  camera_model: 0 = pinhole (others: UNSUPPORTED). */
+    int gsb200_projection_fwd(
+        int64_t B, int64_t C, int64_t N, const float *means, const float *covars, const float *quats,
+        const float *scales, const float *opacities, const float *viewmats, const float *Ks, uint32_t image_width,
+        uint32_t image_height, float eps2d, float near_plane, float far_plane, float radius_clip, int camera_model,
+        int32_t *radii, float *means2d, float *depths, float *conics, float *compensations, void *stream
+    );
+    /* v_* inputs are addressed as ptr[row * stride + k] with row = (b*C + c)*N + n, so that they may be
+     * views into a packed gradient record (stride in floats; 2 / 1 / 3 / 1 for contiguous tensors).
+     * Outputs are fully written (no pre-zeroing needed): v_means [B,N,3]; v_covars [B,N,6] or
+     * (v_quats [B,N,4], v_scales [B,N,3]); v_viewmats [B,C,4,4] or NULL. Deterministic (no atomics
+     * except for v_viewmats). */
+    int gsb200_projection_bwd(
+        int64_t B, int64_t C, int64_t N, const float *means, const float *covars, const float *quats,
+        const float *scales, const float *viewmats, const float *Ks, uint32_t image_width, uint32_t image_height,
+        float eps2d, int camera_model, const int32_t *radii, const float *conics, const float *compensations,
+        const float *v_means2d, int64_t v_means2d_stride, const float *v_depths, int64_t v_depths_stride,
+        const float *v_conics, int64_t v_conics_stride, const float *v_compensations, float *v_means,
+        float *v_covars, float *v_quats, float *v_scales, float *v_viewmats, void *stream
+    );
+
+    /* ---- spherical_harmonics / _bwd : ext.cpp:994-1002, _wrapper.py:436-489 ----
+     * Dense layout: means [B,N,3], viewmats [B,C,4,4], coeffs [N,K,D], masks [B,C,N] (bool bytes) or NULL
+     * -> colors [B,C,N,D]; masked rows are written as 0.  degree in 0..4, (degree+1)^2 <= K. */
+    int gsb200_sh_fwd(
+        int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, int degrees_to_use, const float *means,
+        const float *viewmats, const float *coeffs, const uint8_t *masks, float *colors, void *stream
+    );
+    /* v_coeffs [N,K,D] fully written (zeros for unused bands / masked rows); v_means [B,N,3] or NULL. */
+    int gsb200_sh_bwd(
+        int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, int degrees_to_use, const float *means,
+        const float *viewmats, const float *coeffs, const uint8_t *masks, const float *v_colors, float *v_coeffs,
+        float *v_means, void *stream
+    );
+
+    /* ---- fused projection + conic + SH->RGB : the orchestrator's default training path
+     * (csrc/Rendering.cpp:976-1117: projection_ewa_3dgs_fused then assemble_proj_features with
+     * color_post = max(x + 0.5, 0)).  One pass over the gaussians, B = 1, D = 3, quats/scales input.
+     * colors [C,N,3] = max(SH + 0.5, 0) for visible gaussians, 0 otherwise. */
+    int gsb200_project_sh_fwd(
+        int64_t C, int64_t N, int64_t K, int degrees_to_use, const float *means, const float *quats,
+        const float *scales, const float *opacities, const float *sh_coeffs, const float *viewmats, const float *Ks,
+        uint32_t image_width, uint32_t image_height, float eps2d, float near_plane, float far_plane,
+        float radius_clip, int calc_compensations, int32_t *radii, float *means2d, float *depths, float *conics,
+        float *compensations, float *colors, void *stream
+    );
+    /* Backward of the fused pass.  v_colors is the gradient w.r.t. the post-activation colours
+     * (the relu mask is re-derived).  All outputs fully written; deterministic. */
+    int gsb200_project_sh_bwd(
+        int64_t C, int64_t N, int64_t K, int degrees_to_use, const float *means, const float *quats,
+        const float *scales, const float *sh_coeffs, const float *viewmats, const float *Ks, uint32_t image_width,
+        uint32_t image_height, float eps2d, const int32_t *radii, const float *conics, const float *compensations,
+        const float *colors, const float *v_means2d, int64_t v_means2d_stride, const float *v_depths,
+        int64_t v_depths_stride, const float *v_conics, int64_t v_conics_stride, const float *v_colors,
+        int64_t v_colors_stride, const float *v_compensations, float *v_means, float *v_quats, float *v_scales,
+        float *v_sh_coeffs, void *stream
+    );
+
+    /* ---- intersect_tile : ext.cpp:1022-1026, _wrapper.py:1196-1266, host csrc/Intersect.cpp:170-329 ----
+     * Pass 1: tiles_per_gauss int32 [I*N] and its inclusive scan cum_tiles int64 [I*N] (device).
+     * conics + opacities given -> AccuTile/SNUGBOX ellipse test, else AABB from radii.
+     * The caller reads cum_tiles[I*N-1] (= n_isects) to size the pass-2 outputs. */
+    size_t gsb200_isect_scan_workspace_bytes(int64_t n_elements);
+    int gsb200_isect_count(
+        int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *conics,
+        const float *opacities, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+        int32_t *tiles_per_gauss, int64_t *cum_tiles, void *workspace, size_t workspace_bytes, void *stream
+    );
+    /* Pass 2: unsorted isect_ids int64 [n_isects], flatten_ids int32 [n_isects]. */
+    int gsb200_isect_emit(
+        int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *depths, const float *conics,
+        const float *opacities, const int64_t *cum_tiles, uint32_t tile_size, uint32_t tile_width,
+        uint32_t tile_height, int64_t *isect_ids, int32_t *flatten_ids, void *stream
+    );
+    /* Stable radix sort of (isect_ids, flatten_ids) on key bits [0, end_bit)
+     * (cub::DeviceRadixSort::SortPairs, csrc/IntersectTile.cu:1078-1121). */
+    size_t gsb200_sort_workspace_bytes(int64_t n_isects, int end_bit);
+    int gsb200_sort_pairs(
+        int64_t n_isects, int end_bit, const int64_t *keys_in, const int32_t *vals_in, int64_t *keys_out,
+        int32_t *vals_out, void *workspace, size_t workspace_bytes, void *stream
+    );
+    /* ---- intersect_offset : ext.cpp:1027, _wrapper.py:1328-1347 ---- offsets int32 [I, th, tw]. */
+    int gsb200_isect_offsets(
+        int64_t n_isects, const int64_t *isect_ids, int64_t I, uint32_t tile_width, uint32_t tile_height,
+        int32_t *offsets, void *stream
+    );
+
+    /* ---- rasterize_to_pixels_3dgs / _bwd : ext.cpp:1079-1089, _wrapper.py:1497-1562, 2010-2117 ----
+     * Dense layout: means2d [I,N,2] conics [I,N,3] colors [I,N,D] opacities [I,N]
+     * backgrounds [I,D] or NULL, masks [I,th,tw] bool bytes or NULL, offsets [I,th,tw], flatten_ids [n_isects].
+     * tile_size must be 16.  `records` is caller scratch of gsb200_raster_records_bytes(n_isects, D):
+     * the forward packs the depth-sorted per-intersection records there (TMA-streamed by both passes);
+     * the caller keeps it alive for the backward.
+     * Outputs: render_colors [I,H,W,D], render_alphas [I,H,W,1], last_ids int32 [I,H,W]. */
+    size_t gsb200_raster_records_bytes(int64_t n_isects, int D);
+    int gsb200_raster_fwd(
+        int64_t I, int64_t N, int D, const float *means2d, const float *conics, const float *colors,
+        const float *opacities, const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+        uint32_t image_height, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, const int32_t *offsets,
+        const int32_t *flatten_ids, int64_t n_isects, void *records, float *render_colors, float *render_alphas,
+        int32_t *last_ids, void *stream
+    );
+    /* Gradient outputs are ACCUMULATED into (caller zero-initialises): each is addressed as
+     * ptr[g * stride + k], g in [0, I*N), so they may be views into one packed record per gaussian.
+     * v_means2d_abs may be NULL (absgrad off). */
+    int gsb200_raster_bwd(
+        int64_t I, int64_t N, int D, const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+        uint32_t image_height, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, const int32_t *offsets,
+        const int32_t *flatten_ids, int64_t n_isects, const void *records, const float *render_alphas,
+        const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas, float *v_means2d,
+        int64_t v_means2d_stride, float *v_conics, int64_t v_conics_stride, float *v_colors, int64_t v_colors_stride,
+        float *v_opacities, int64_t v_opacities_stride, float *v_means2d_abs, int64_t v_means2d_abs_stride,
+        void *stream
+    );
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPLAT_B200_H */
