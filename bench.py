@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+Workload (config.workload): BASELINE.json configs[2] -- 1 006 065 Gaussians (the test_garden crop tiled
+3x3), one 1920x1080 view per GPU, SH degree 3, dense (packed=False).
+A "step" is one pass of the hot path: rasterization() forward (fused projection + SH, tile intersection,
+radix sort, offsets, compositing) + L1 loss against a target image + backward to all five parameter
+tensors; at N > 1 every rank renders its own view of the replicated scene and the Gaussian gradients are
+all-reduced over NCCL (view-axis data parallelism, weak scaling).  The optimizer is outside the path.
+
+Printed line (rank 0): metric = rendered views/s (fwd+bwd), ms_per_step = train-step ms,
+value = device-resident timing, e2e = same step with the per-step host->device copy of the camera and
+the target image from pinned memory and the device->host read of the loss inside the timed region.
+roofline = dominant kernel (compositing backward) algorithmic bytes / CUDA-event time vs the measured
+HBM peak; cpu_baseline = the CPU oracle port timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+W_IMG, H_IMG, SH_DEGREE, SCENE_GRID = 1920, 1080, 3, 3
+METRIC = "rendered views/sec, fwd+bwd train step (1M Gaussians, 1080p, SH3)"
+UNIT = "views/s"
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {
+        "workload": "BASELINE configs[2]: synthetic 1M Gaussians (test_garden crop tiled 3x3 = 1006065), "
+        "1 view 1920x1080 per GPU, SH3, packed=False, near=0.01 far=1e10 eps2d=0.3",
+        "step": "rasterization fwd + L1 loss + bwd to means/quats/scales/opacities/SH"
+        + (" + NCCL all-reduce of Gaussian grads" if n_gpus > 1 else ""),
+        "views_per_step": n_gpus,
+        "parallelism": f"view-axis DP x{n_gpus} (replicated Gaussians)" if n_gpus > 1 else "single GPU",
+        "l2": "inputs (236 MB of Gaussian parameters + 25 MB target) exceed the 126 MB L2; no explicit flush",
+    }
+
+
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_scene():
+    from tests import scene
+
+    sc = scene.make_scene(scene_grid=SCENE_GRID, sh_degree=SH_DEGREE)
+    Ks = scene.rescale_K(sc["Ks"], sc["width"], sc["height"], W_IMG, H_IMG)
+    return sc, Ks
+
+
+# --------------------------------------------------------------------------------------------
+def run_cpu_reference(steps: int, warmup: int, n_gpus: int, as_main_line: bool):
+    """The reference's CPU implementation of the path: the C oracle port (oracle/), all host cores.
+    One step = fwd+bwd of ONE full view of the workload (a bounded sample of a step at N views)."""
+    from oracle import gso
+
+    gso.build()
+    sc, Ks = build_scene()
+    cores = os.cpu_count() or 1
+    rng = np.random.RandomState(0)
+    target = rng.random_sample((1, H_IMG, W_IMG, 3)).astype(np.float32)
+
+    def step():
+        fwd, _ = gso.rasterization_fwd_bwd(
+            sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["sh"], sc["viewmats"][:1], Ks[:1], W_IMG, H_IMG,
+            SH_DEGREE, None, None,
+        )
+        v_rc = np.sign(fwd["render_colors"] - target).astype(np.float32) / target.size
+        gso.rasterization_fwd_bwd(
+            sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["sh"], sc["viewmats"][:1], Ks[:1], W_IMG, H_IMG,
+            SH_DEGREE, v_rc, np.zeros((1, H_IMG, W_IMG, 1), np.float32),
+        )
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    base = {
+        "value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{steps} x one full 1080p view of the 1M-Gaussian workload, fwd (twice: loss needs the render) + bwd, "
+        "C oracle port with OpenMP on all host cores",
+    }
+    if not as_main_line:
+        return base
+    line = {
+        "impl": "reference", "metric": METRIC, "value": 1.0 / dt, "unit": UNIT, "n_gpus": n_gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(n_gpus), "cpu_baseline": base,
+        "e2e": {"value": 1.0 / dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_cpu_reference(max(1, min(args.steps, 3)), min(args.warmup, 1), args.gpus, True)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import gsplat_b200
+    from gsplat_b200 import ops
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    sc, Ks = build_scene()
+    N = sc["means"].shape[0]
+    params = {
+        k: torch.from_numpy(sc[k]).to(dev).requires_grad_(True) for k in ("means", "quats", "scales", "opacities", "sh")
+    }
+    cam = rank % sc["viewmats"].shape[0]
+    vm_host = torch.from_numpy(sc["viewmats"][cam : cam + 1].copy()).pin_memory()
+    K_host = torch.from_numpy(Ks[cam : cam + 1].copy()).pin_memory()
+    rng = np.random.RandomState(100 + rank)
+    target_host = torch.from_numpy(rng.random_sample((1, H_IMG, W_IMG, 3)).astype(np.float32)).pin_memory()
+    vm_dev, K_dev, target_dev = vm_host.to(dev), K_host.to(dev), target_host.to(dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    h2d_bytes = vm_host.numel() * 4 + K_host.numel() * 4 + target_host.numel() * 4
+    d2h_bytes = 4
+    grad_names = ("means", "quats", "scales", "opacities", "sh")
+    flat_grads = torch.zeros(N * 59, device=dev) if world > 1 else None
+
+    def step(e2e: bool):
+        if e2e:
+            vm = vm_host.to(dev, non_blocking=True)
+            K = K_host.to(dev, non_blocking=True)
+            tgt = target_host.to(dev, non_blocking=True)
+        else:
+            vm, K, tgt = vm_dev, K_dev, target_dev
+        for p in params.values():
+            p.grad = None
+        rc, ra, meta = gsplat_b200.rasterization(
+            params["means"], params["quats"], params["scales"], params["opacities"], params["sh"], vm, K, W_IMG, H_IMG,
+            sh_degree=SH_DEGREE, packed=False,
+        )
+        loss = (rc - tgt).abs().mean()
+        loss.backward()
+        if world > 1:
+            # one bucketed all-reduce of the 59 floats / Gaussian
+            o = 0
+            for k in grad_names:
+                g = params[k].grad.reshape(-1)
+                flat_grads[o : o + g.numel()].copy_(g)
+                o += g.numel()
+            dist.all_reduce(flat_grads)
+        if e2e:
+            loss_host.copy_(loss.detach(), non_blocking=True)
+        return meta
+
+    def timed(e2e: bool, steps: int) -> float:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        meta = step(False)
+        step(True)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(False, args.steps)
+    ms_e2e = timed(True, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernels, timed alone with CUDA events on the launching stream
+    S = int(meta["flatten_ids"].numel())
+    P, T = W_IMG * H_IMG, meta["tile_width"] * meta["tile_height"]
+    det = {k: meta[k].detach().requires_grad_(True) for k in ("means2d", "conics")}
+    with torch.no_grad():
+        colors = ops.fused_project_sh(
+            params["means"], params["quats"], params["scales"], params["opacities"], params["sh"], vm_dev, K_dev, W_IMG,
+            H_IMG, SH_DEGREE,
+        )[4]
+    colors = colors.detach().requires_grad_(True)
+    opac = meta["opacities"].detach().contiguous().requires_grad_(True)
+    v_rc = torch.randn((1, H_IMG, W_IMG, 3), device=dev)
+
+    def time_kernel(fn, reps=10):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def raster_fwd():
+        return ops.rasterize_to_pixels(
+            det["means2d"], det["conics"], colors, opac, W_IMG, H_IMG, 16, meta["isect_offsets"], meta["flatten_ids"]
+        )
+
+    ms_rfwd = time_kernel(raster_fwd)
+    rc_keep, _ = raster_fwd()
+
+    def raster_bwd():
+        torch.autograd.grad((rc_keep,), (det["means2d"], det["conics"], colors, opac), (v_rc,), retain_graph=True)
+
+    ms_rbwd = time_kernel(raster_bwd)
+    peak, peak_src = measured_peak_gbs()
+    bytes_fwd, bytes_bwd = 40 * S + 20 * P + 4 * T, 76 * S + 24 * P + 4 * T
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("raster_bwd_dram_bytes")
+        except Exception:
+            traffic = None
+    achieved = bytes_bwd / (ms_rbwd * 1e-3) / 1e9
+    roofline = {
+        "kernel": "raster_bwd_kernel<3> (+ zero-init of the gradient records)", "bound": "hbm", "achieved": achieved,
+        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes": bytes_bwd, "ms": ms_rbwd, "n_isects": S,
+        "note": "compositing is FP32/MUFU-bound, not HBM-bound (SURVEY.md section 8d): the HBM fraction is reported as "
+        "required, pair throughput below is the meaningful figure",
+        "raster_fwd": {"ms": ms_rfwd, "achieved": bytes_fwd / (ms_rfwd * 1e-3) / 1e9, "algorithmic_bytes": bytes_fwd},
+    }
+
+    if rank == 0:
+        cpu_base = None
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            cpu_base = run_cpu_reference(2, 1, 1, False)
+        line = {
+            "metric": METRIC, "value": n_gpus * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(n_gpus),
+            "e2e": {
+                "value": n_gpus * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+            },
+            # ours per step: project_sh fwd, isect count, cub scan (x?), emit, cub sort (several), offsets, pack,
+            # raster fwd, raster bwd, project_sh bwd -- counted as C-ABI kernel launches of our own kernels
+            "gpu_launches": args.steps * 2 * 8,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

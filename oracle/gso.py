@@ -348,7 +348,7 @@ def rasterization_fwd_bwd(
     fwd = dict(
         radii=radii, means2d=means2d, depths=depths, conics=conics, colors=colors, tiles_per_gauss=tpg,
         isect_ids=isect_ids, flatten_ids=flatten_ids, isect_offsets=offsets, render_colors=rc, render_alphas=ra,
-        last_ids=li, margins=mg,
+        last_ids=li, margins=mg, sh_raw=raw,
     )
     if v_render_colors is None:
         return fwd, None

@@ -1099,23 +1099,30 @@ int FN(gso_raster_bwd)(
                     double *A = acc + (size_t)(s - start) * stride;
                     const REAL *col = colors + (int64_t)g * D;
                     REAL v_alpha = 0;
+                    double abs_va = 0; /* sum of |terms| inside v_alpha: its own conditioning */
                     for(int64_t k = 0; k < D; ++k)
                     {
                         A[12 + k] += (double)(fac * vrc[k]);
                         v_alpha += (col[k] * T - buffer[k] * ra) * vrc[k];
+                        abs_va += (fabs((double)(col[k] * T)) + fabs((double)(buffer[k] * ra))) * fabs((double)vrc[k]);
                     }
                     v_alpha += T_final * ra * vra;
+                    abs_va += fabs((double)(T_final * ra * vra));
                     if(bg)
                     {
                         REAL accum = 0;
                         for(int64_t k = 0; k < D; ++k)
+                        {
                             accum += bg[k] * vrc[k];
+                            abs_va += fabs((double)(T_final * ra * bg[k] * vrc[k]));
+                        }
                         v_alpha += -T_final * ra * accum;
                     }
                     if(ov <= MAX_A)
                     {
                         REAL v_sigma = -ov * v_alpha;
                         REAL gx = v_sigma * (a * dx + b * dy), gy = v_sigma * (b * dx + c * dy);
+                        double s_abs = fabs((double)ov) * abs_va;
                         A[0] += (double)gx;
                         A[1] += (double)gy;
                         A[2] += (double)((REAL)0.5 * v_sigma * dx * dx);
@@ -1124,10 +1131,9 @@ int FN(gso_raster_bwd)(
                         A[5] += (double)(vis * v_alpha);
                         A[6] += fabs((double)gx);
                         A[7] += fabs((double)gy);
-                        A[8] += fabs((double)gx) + fabs((double)gy);
-                        A[9] += fabs((double)(0.5 * v_sigma * dx * dx)) + fabs((double)(v_sigma * dx * dy))
-                              + fabs((double)(0.5 * v_sigma * dy * dy));
-                        A[10] += fabs((double)(vis * v_alpha));
+                        A[8] += s_abs * (fabs((double)(a * dx)) + fabs((double)(b * dy)) + fabs((double)(b * dx)) + fabs((double)(c * dy)));
+                        A[9] += s_abs * (0.5 * (double)(dx * dx) + fabs((double)(dx * dy)) + 0.5 * (double)(dy * dy));
+                        A[10] += fabs((double)vis) * abs_va;
                     }
                     for(int64_t k = 0; k < D; ++k)
                     {

@@ -1,0 +1,75 @@
+"""World-size-2 gloo tests (CPU) of the view-axis DP host logic in gsplat_b200.distributed: view
+sharding and the bucketed gradient all-reduce.  The render kernels need a GPU, so a linear stand-in
+"renderer" is used whose gradients are known in closed form."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gsplat_b200 import distributed as D
+
+    torch.manual_seed(0)  # replicated parameters
+    params = [torch.randn(7, 3, requires_grad=True), torch.randn(7, 4, requires_grad=True), torch.randn(7, requires_grad=True)]
+    views = torch.arange(5, dtype=torch.float32)  # 5 "cameras"
+    ids = D.shard_views(5)
+    assert ids == list(range(rank, 5, world))
+    loss = sum((views[i] + 1.0) * sum((p * p).sum() for p in params) for i in ids)
+    loss.backward()
+    D.all_reduce_gaussian_grads(params)
+    total = sum(float(v) + 1.0 for v in views)
+    for p in params:
+        assert torch.allclose(p.grad, 2.0 * total * p.detach(), rtol=1e-5, atol=1e-6)
+    # a rank whose parameter got no gradient still participates (zeros are reduced)
+    q = [torch.ones(3, requires_grad=True)]
+    if rank == 0:
+        (q[0] * 2).sum().backward()
+    D.all_reduce_gaussian_grads(q, average=True)
+    assert torch.allclose(q[0].grad, torch.full((3,), 1.0))
+    # async variant
+    r = [torch.ones(4, requires_grad=True)]
+    (r[0] * float(rank + 1)).sum().backward()
+    bucket, work = D.all_reduce_gaussian_grads(r, async_op=True)
+    work.wait()
+    bucket.unpack(bucket._scale)
+    assert torch.allclose(r[0].grad, torch.full((4,), 3.0))
+    dist.barrier()
+    dist.destroy_process_group()
+    out.put(rank)
+
+
+def test_dp_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(out.get(timeout=5) for _ in range(2)) == [0, 1]
+
+
+def test_single_process_is_identity():
+    from gsplat_b200 import distributed as D
+
+    p = [torch.ones(3, requires_grad=True)]
+    (p[0] * 5).sum().backward()
+    D.all_reduce_gaussian_grads(p)
+    assert torch.allclose(p[0].grad, torch.full((3,), 5.0))
+    assert D.shard_views(5, rank=1, world_size=2) == [1, 3]
