@@ -156,6 +156,63 @@ def run_cpu_reference(steps: int, warmup: int, n_gpus: int, as_main_line: bool):
 
 
 # --------------------------------------------------------------------------------------------
+def run_ref_cuda(params, vm, K, target, steps: int):
+    """Extra information (not the contract's reference arm): the REAL reference's CUDA kernels
+    (oracle/_ref/gsplat_ref.so, built by oracle/build_ref.py with the reference's release flags for
+    sm_100a) chained as its orchestrator chains them (csrc/Rendering.cpp:976-1447) on the same inputs,
+    forward ops + the matching *_bwd ops called by hand (no autograd / Python overhead -> a lower bound
+    on the reference's train step).  Returns None when the library is absent."""
+    import torch
+
+    so = os.path.join(ROOT, "oracle", "_ref", "gsplat_ref.so")
+    if not os.path.exists(so):
+        return None
+    try:
+        torch.ops.load_library(so)
+        R = torch.ops.gsplat
+        means, quats, scales, opac, sh = (params[k].detach() for k in ("means", "quats", "scales", "opacities", "sh"))
+        tw, th = (W_IMG + 15) // 16, (H_IMG + 15) // 16
+        op_cn = opac[None].contiguous()
+
+        def step():
+            radii, m2, dep, con, _ = R.projection_ewa_3dgs_fused(means, None, quats, scales, opac, vm, K, W_IMG, H_IMG, 0.3, 0.01, 1e10, 0.0, False, 0)
+            valid = (radii > 0).all(-1)
+            raw = R.spherical_harmonics(SH_DEGREE, means, vm, sh, valid, None, None, None, None)
+            col = torch.clamp_min(raw + 0.5, 0.0)
+            tpg, ids, fl = R.intersect_tile(m2, radii, dep, con, op_cn, None, None, 1, 16, tw, th, True, False)
+            off = R.intersect_offset(ids, 1, tw, th)
+            rc, ra, _, last = R.rasterize_to_pixels_3dgs(m2, con, col, op_cn, None, None, W_IMG, H_IMG, 16, off, fl, False, False)
+            diff = rc - target
+            loss = diff.abs().mean()
+            v_rc = torch.sign(diff) / diff.numel()
+            v_ra = torch.zeros_like(ra)
+            rb = R.rasterize_to_pixels_3dgs_bwd(m2, con, col, op_cn, None, None, off, fl, ra, last, W_IMG, H_IMG, 16, False, v_rc, v_ra, False)
+            v_col = rb[3] * (col > 0)
+            sb = R.spherical_harmonics_bwd(SH_DEGREE, means, vm, sh, valid, None, None, None, None, v_col, True, False, False)
+            pb = R.projection_ewa_3dgs_fused_bwd(means, None, quats, scales, vm, K, W_IMG, H_IMG, 0.3, 0, radii, con, None, rb[1], torch.zeros_like(dep), rb[2], None, False)
+            v_means = pb[0] + sb[1]
+            v_op = rb[4].sum(0)
+            return loss, v_means, v_op, fl
+
+        for _ in range(3):
+            out = step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {
+            "what": "reference gsplat v1.6.0 CUDA kernels (sm_100a, -use_fast_math), ops chained by hand, no autograd overhead",
+            "ms_per_step": ms, "views_per_s": 1e3 / ms, "n_isects": int(out[3].numel()),
+        }
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
+# --------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -314,7 +371,9 @@ def main():
     }
 
     if rank == 0:
-        cpu_base = None
+        cpu_base, ref_cuda = None, None
+        if n_gpus == 1:
+            ref_cuda = run_ref_cuda(params, vm_dev, K_dev, target_dev, args.steps)
         if n_gpus == 1 and not args.no_cpu_baseline:
             cpu_base = run_cpu_reference(2, 1, 1, False)
         line = {
@@ -329,7 +388,7 @@ def main():
             # ours per step: project_sh fwd, isect count, cub scan (x?), emit, cub sort (several), offsets, pack,
             # raster fwd, raster bwd, project_sh bwd -- counted as C-ABI kernel launches of our own kernels
             "gpu_launches": args.steps * 2 * 8,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "ref_cuda": ref_cuda,
         }
         print(json.dumps(line))
     if world > 1:

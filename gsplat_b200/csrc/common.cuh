@@ -116,6 +116,21 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4 *p)
     return r;
 }
 
+// ex2 / rcp exactly as the reference evaluates them (it is built with -use_fast_math, so its __expf is
+// ex2.approx.ftz(x * log2e) and its 1.0f / x is rcp.approx.ftz): one MUFU each, no range fix-up code.
+__device__ __forceinline__ float fast_exp(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // Butterfly ("transpose") warp reduction of M per-lane values: after the call, lane L holds in v[0]
 // the full 32-lane sum of slot butterfly_slot<M>(L) (if that slot is < M).  Costs
 // ceil(M/2)+ceil(M/4)+... shuffles instead of 5*M.

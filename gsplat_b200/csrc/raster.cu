@@ -17,6 +17,8 @@
 //  * the backward walks the same ring back to front, reduces the 9(+2) per-gaussian partial sums of a
 //    warp with a butterfly transpose (12 shuffles instead of 45) and lets the lanes that end up owning
 //    a sum issue one red.global.add each.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gsb
@@ -34,9 +36,10 @@ struct RecLayout
 
 struct RecordStreams
 {
-    float4 *cull;  // [S] {mx, my, ex, ey}
-    float4 *geom;  // [S] {a, b, c, opacity}
-    float4 *color; // [S * kColorVec4]
+    float4 *cull;   // [S] {mx, my, ex, ey}
+    float4 *geom;   // [S] {a, b, c, opacity}
+    float4 *color;  // [S * kColorVec4]
+    int32_t *order; // [n_tiles] tile indices, longest list first
 };
 
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -50,8 +53,45 @@ static inline RecordStreams carve_records(void *base, int64_t S, int cvec4)
     r.geom = (float4 *)p;
     p += align256((size_t)S * 16);
     r.color = (float4 *)p;
-    (void)cvec4;
+    p += align256((size_t)S * 16 * (size_t)cvec4);
+    r.order = (int32_t *)p;
     return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Longest-list-first tile order.  A tile is one CTA and its list is walked sequentially, so a long list
+// that starts late is the tail of the whole launch; CTAs are dispatched in blockIdx order, hence the
+// permutation.  One CTA: 256-bin counting sort on (length / 32), descending.
+__global__ void __launch_bounds__(1024) tile_order_kernel(
+    const int32_t *__restrict__ offsets, const int32_t n_tiles, const int32_t n_isects, int32_t *__restrict__ order
+)
+{
+    __shared__ int32_t hist[256];
+    __shared__ int32_t cursor[256];
+    for(int i = threadIdx.x; i < 256; i += blockDim.x)
+        hist[i] = 0;
+    __syncthreads();
+    auto bin_of = [&](int t) {
+        const int32_t end = (t == n_tiles - 1) ? n_isects : offsets[t + 1];
+        const int32_t len = end - offsets[t];
+        const int b       = len >> 5;
+        return 255 - (b > 255 ? 255 : b); // bin 0 = longest
+    };
+    for(int t = threadIdx.x; t < n_tiles; t += blockDim.x)
+        atomicAdd(&hist[bin_of(t)], 1);
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        int32_t run = 0;
+        for(int i = 0; i < 256; ++i)
+        {
+            cursor[i] = run;
+            run += hist[i];
+        }
+    }
+    __syncthreads();
+    for(int t = threadIdx.x; t < n_tiles; t += blockDim.x)
+        order[atomicAdd(&cursor[bin_of(t)], 1)] = t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -107,8 +147,9 @@ struct TileGeom
     int image_id, tile_id, tile_x, tile_y;
 };
 
-__device__ __forceinline__ TileGeom decode_tile(uint32_t block, uint32_t tw, uint32_t th)
+__device__ __forceinline__ TileGeom decode_tile(const int32_t *__restrict__ order, uint32_t tw, uint32_t th)
 {
+    const uint32_t block = order ? (uint32_t)order[blockIdx.x] : blockIdx.x;
     TileGeom t;
     const uint32_t per = tw * th;
     t.image_id         = block / per;
@@ -160,9 +201,10 @@ constexpr size_t ring_smem_bytes()
 template<int CDIM>
 __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
     const uint32_t I, const int64_t n_isects, const float4 *__restrict__ gcull, const float4 *__restrict__ ggeom,
-    const float4 *__restrict__ gcolor, const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
-    const uint32_t W, const uint32_t H, const uint32_t tw, const uint32_t th, const int32_t *__restrict__ offsets,
-    float *__restrict__ render_colors, float *__restrict__ render_alphas, int32_t *__restrict__ last_ids
+    const float4 *__restrict__ gcolor, const int32_t *__restrict__ order, const float *__restrict__ backgrounds,
+    const uint8_t *__restrict__ masks, const uint32_t W, const uint32_t H, const uint32_t tw, const uint32_t th,
+    const int32_t *__restrict__ offsets, float *__restrict__ render_colors, float *__restrict__ render_alphas,
+    int32_t *__restrict__ last_ids
 )
 {
     constexpr int CV = RecLayout<CDIM>::kColorVec4;
@@ -170,7 +212,7 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
     Ring<CDIM> ring;
     ring.carve(smem_raw);
 
-    const TileGeom tg   = decode_tile(blockIdx.x, tw, th);
+    const TileGeom tg   = decode_tile(order, tw, th);
     const unsigned tid  = threadIdx.x;
     const unsigned warp = tid >> 5, lane = tid & 31;
     // warp -> 8x4 pixel block inside the 16x16 tile
@@ -230,85 +272,84 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
     for(int k = 0; k < CDIM; ++k)
         pix_out[k] = 0.f;
     int32_t cur_idx = 0;
-    bool done       = !inside;
+    uint32_t done   = inside ? 0u : 1u;
     int last_b      = num_batches; // batch at which the tile-level early exit happened
 
     for(int b = 0; b < num_batches; ++b)
     {
         const int stage       = b % kStages;
         const uint32_t parity = (uint32_t)(b / kStages) & 1u;
-        const int64_t first   = (int64_t)range_start + (int64_t)b * kBatch;
+        const int32_t first   = range_start + b * kBatch;
         const int count       = min(kBatch, (int)(range_end - first));
-        const bool warp_done  = __all_sync(0xffffffffu, done);
-        if(!warp_done)
+        if(!__all_sync(0xffffffffu, done != 0u))
         {
             mbar_wait(ring.full(stage), parity);
             const float4 *scull = ring.cull(stage);
             const float4 *sgeom = ring.geom(stage);
             const float4 *scol  = ring.color(stage);
-            bool stop           = false;
-            for(int c0 = 0; c0 < count && !stop; c0 += 32)
+            for(int c0 = 0; c0 < count; c0 += 32)
             {
-                // each lane tests one gaussian's extent box against this warp's pixel block
-                const int mine = c0 + (int)lane;
+                // Each lane tests one gaussian's extent box against this warp's pixel block.  Lane L looks at
+                // record c0 + 31 - L so that the HIGHEST set ballot bit is the FRONT-most survivor (one FLO,
+                // no bit reversal, to walk the survivors front to back).
+                const int mine = c0 + 31 - (int)lane;
                 bool hit       = false;
                 if(mine < count)
                 {
                     const float4 q = scull[mine];
                     hit            = (fabsf(q.x - cx) <= q.z + hx) && (fabsf(q.y - cy) <= q.w + hy);
                 }
-                unsigned mask = __ballot_sync(0xffffffffu, hit);
+                uint32_t mask = __ballot_sync(0xffffffffu, hit);
                 while(mask)
                 {
-                    const int j = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int t    = c0 + j;
-                    const float4 q = scull[t];
-                    const float4 g = sgeom[t];
+                    const int j = 31 - __clz(mask);
+                    mask ^= 1u << j;
+                    const int t     = c0 + 31 - j;
+                    const float4 q  = scull[t];
+                    const float4 g  = sgeom[t];
+                    const float4 cc = scol[t * CV];
                     const float dx = q.x - px, dy = q.y - py;
                     const float sigma = 0.5f * (g.x * dx * dx + g.z * dy * dy) + g.y * dx * dy;
-                    const float vis   = __expf(-sigma);
+                    const float vis   = fast_exp(-sigma);
                     const float alpha = fminf(kMaxAlpha, g.w * vis);
-                    bool valid        = !done && !(sigma < 0.f || alpha < kAlphaThreshold);
-                    float next_T      = 0.f;
-                    if(valid)
+                    if(done == 0u && sigma >= 0.f && alpha >= kAlphaThreshold)
                     {
-                        next_T = T * (1.0f - alpha);
+                        const float next_T = T * (1.0f - alpha);
                         if(next_T <= kTransmittanceThreshold)
-                        { // this pixel is done: exclusive of the current gaussian
-                            done  = true;
-                            valid = false;
-                        }
-                    }
-                    if(__any_sync(0xffffffffu, valid))
-                    {
-                        float col[CV * 4];
-#pragma unroll
-                        for(int v = 0; v < CV; ++v)
-                        {
-                            const float4 cc = scol[t * CV + v];
-                            col[4 * v] = cc.x, col[4 * v + 1] = cc.y, col[4 * v + 2] = cc.z, col[4 * v + 3] = cc.w;
-                        }
-                        if(valid)
+                            done = 1u; // this pixel is done: exclusive of the current gaussian
+                        else
                         {
                             const float w = alpha * T;
+                            pix_out[0] += cc.x * w;
+                            if constexpr(CDIM > 1)
+                                pix_out[1] += cc.y * w;
+                            if constexpr(CDIM > 2)
+                                pix_out[2] += cc.z * w;
+                            if constexpr(CDIM > 3)
+                                pix_out[3] += cc.w * w;
+                            if constexpr(CDIM > 4)
+                            {
 #pragma unroll
-                            for(int k = 0; k < CDIM; ++k)
-                                pix_out[k] += col[k] * w;
-                            cur_idx = (int32_t)(first + t);
+                                for(int v = 1; v < CV; ++v)
+                                {
+                                    const float4 c2 = scol[t * CV + v];
+                                    if(4 * v + 0 < CDIM) pix_out[4 * v + 0] += c2.x * w;
+                                    if(4 * v + 1 < CDIM) pix_out[4 * v + 1] += c2.y * w;
+                                    if(4 * v + 2 < CDIM) pix_out[4 * v + 2] += c2.z * w;
+                                    if(4 * v + 3 < CDIM) pix_out[4 * v + 3] += c2.w * w;
+                                }
+                            }
+                            cur_idx = first + t;
                             T       = next_T;
                         }
                     }
-                    if(__all_sync(0xffffffffu, done))
-                    { // every pixel of this warp is saturated: drop out of the list
-                        stop = true;
-                        break;
-                    }
                 }
+                if(__all_sync(0xffffffffu, done != 0u))
+                    break; // every pixel of this warp is saturated: drop out of the list
             }
         }
         // everyone finished reading this stage; tile-level early exit
-        const int n_done = __syncthreads_count(done);
+        const int n_done = __syncthreads_count(done != 0u);
         if(tid == 0)
             mbar_wait(ring.full(stage), parity); // batch b has landed even if no warp needed it
         if(n_done == kWarps * 32)
@@ -350,7 +391,8 @@ struct GradDst
 template<int CDIM, bool ABS>
 __global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
     const uint32_t I, const int64_t n_isects, const float4 *__restrict__ gcull, const float4 *__restrict__ ggeom,
-    const float4 *__restrict__ gcolor, const int32_t *__restrict__ flatten_ids, const float *__restrict__ backgrounds,
+    const float4 *__restrict__ gcolor, const int32_t *__restrict__ order, const int32_t *__restrict__ flatten_ids,
+    const float *__restrict__ backgrounds,
     const uint8_t *__restrict__ masks, const uint32_t W, const uint32_t H, const uint32_t tw, const uint32_t th,
     const int32_t *__restrict__ offsets, const float *__restrict__ render_alphas, const int32_t *__restrict__ last_ids,
     const float *__restrict__ v_render_colors, const float *__restrict__ v_render_alphas, const GradDst dst
@@ -365,7 +407,7 @@ __global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
     __shared__ int32_t s_ids[kStages][kBatch];
     __shared__ int32_t s_tile_bin;
 
-    const TileGeom tg      = decode_tile(blockIdx.x, tw, th);
+    const TileGeom tg      = decode_tile(order, tw, th);
     const unsigned tid     = threadIdx.x;
     const unsigned warp    = tid >> 5, lane = tid & 31;
     const int64_t tile_lin = (int64_t)tg.image_id * tw * th + tg.tile_id;
@@ -436,13 +478,15 @@ __global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
             p = dst.abs + (slot - 6 - CDIM), stride = dst.s_abs;
     };
     float *my_dst, *my_dst_b = nullptr;
-    int64_t my_stride, my_stride_b = 0;
-    slot_dst(butterfly_slot<MA>(lane), my_dst, my_stride);
+    int64_t my_stride64, my_stride_b64 = 0;
+    slot_dst(butterfly_slot<MA>(lane), my_dst, my_stride64);
     if constexpr(MB > 0)
     {
         const int sb = butterfly_slot<MB>(lane);
-        slot_dst(sb >= 0 ? sb + MA : -1, my_dst_b, my_stride_b);
+        slot_dst(sb >= 0 ? sb + MA : -1, my_dst_b, my_stride_b64);
     }
+    // element offsets fit 32 bits (checked on the host: rows * stride < 2^32)
+    const uint32_t my_stride = (uint32_t)my_stride64, my_stride_b = (uint32_t)my_stride_b64;
 
     const int num_batches = (range_end - range_start + kBatch - 1) / kBatch;
     // batch b covers sorted indices [first, first + count), walking back to front
@@ -464,47 +508,52 @@ __global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
     const float cx = (float)bx0 + 4.0f, cy = (float)by0 + 2.0f;
     constexpr float hx = 3.5f, hy = 1.5f;
 
+    const float neg_Tf_bg = bg ? -T_final * bg_dot : 0.f;
+    const float Tf_va     = T_final * v_render_a + neg_Tf_bg; // T_final * (v_render_a - bg . v_render_c)
     for(int b = 0; b < num_batches; ++b)
     {
         const int stage       = b % kStages;
         const uint32_t parity = (uint32_t)(b / kStages) & 1u;
-        const int64_t first   = batch_first(b);
+        const int32_t first   = (int32_t)batch_first(b);
         const int count       = batch_count(b);
         // gaussian ids of this batch (coalesced; needed for the scatter)
         if((int)tid < count)
             s_ids[stage][tid] = flatten_ids[first + tid];
         __syncthreads();
         // the whole batch lies behind this warp's deepest contributor -> nothing to do for the warp
-        if(first <= (int64_t)warp_bin_final)
+        if(first <= warp_bin_final)
         {
             mbar_wait(ring.full(stage), parity);
-            const float4 *scull = ring.cull(stage);
-            const float4 *sgeom = ring.geom(stage);
-            const float4 *scol  = ring.color(stage);
+            const float4 *scull   = ring.cull(stage);
+            const float4 *sgeom   = ring.geom(stage);
+            const float4 *scol    = ring.color(stage);
+            const int32_t *sid    = s_ids[stage];
+            const int lim         = bin_final - first;      // local index of this pixel's last contributor
+            const int warp_lim    = warp_bin_final - first; // ... of the warp's
             for(int c1 = count; c1 > 0; c1 -= 32)
             {
                 const int c0   = c1 - 32; // chunk covers local [c0, c1); c0 may be negative
                 const int mine = c0 + (int)lane;
                 bool hit       = false;
-                if(mine >= 0 && first + mine <= (int64_t)warp_bin_final)
+                if(mine >= 0 && mine <= warp_lim)
                 {
                     const float4 q = scull[mine];
                     hit            = (fabsf(q.x - cx) <= q.z + hx) && (fabsf(q.y - cy) <= q.w + hy);
                 }
-                unsigned mask = __ballot_sync(0xffffffffu, hit);
+                uint32_t mask = __ballot_sync(0xffffffffu, hit);
                 while(mask)
                 {
                     const int j = 31 - __clz(mask); // back to front
-                    mask &= ~(1u << j);
+                    mask ^= 1u << j;
                     const int t    = c0 + j;
                     const float4 q = scull[t];
                     const float4 g = sgeom[t];
                     const float dx = q.x - px, dy = q.y - py;
                     const float sigma = 0.5f * (g.x * dx * dx + g.z * dy * dy) + g.y * dx * dy;
-                    const float vis   = __expf(-sigma);
-                    const float alpha = fminf(kMaxAlpha, g.w * vis);
-                    const bool valid
-                        = inside && (first + t <= (int64_t)bin_final) && !(sigma < 0.f || alpha < kAlphaThreshold);
+                    const float vis   = fast_exp(-sigma);
+                    const float ov    = g.w * vis;
+                    const float alpha = fminf(kMaxAlpha, ov);
+                    const bool valid  = (t <= lim) && sigma >= 0.f && alpha >= kAlphaThreshold;
                     if(!__any_sync(0xffffffffu, valid))
                         continue;
                     float col[CV * 4];
@@ -520,7 +569,7 @@ __global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
                         part[k] = 0.f;
                     if(valid)
                     {
-                        const float ra = 1.0f / fmaxf(kMinOneMinusAlpha, 1.0f - alpha);
+                        const float ra = fast_rcp(fmaxf(kMinOneMinusAlpha, 1.0f - alpha));
                         T *= ra;
                         const float fac = alpha * T;
                         float v_alpha   = 0.f;
@@ -529,13 +578,12 @@ __global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
                         {
                             part[6 + k] = fac * v_render_c[k];
                             v_alpha += (col[k] * T - buffer[k] * ra) * v_render_c[k];
+                            buffer[k] += col[k] * fac;
                         }
-                        v_alpha += T_final * ra * v_render_a;
-                        if(bg)
-                            v_alpha += -T_final * ra * bg_dot;
-                        if(g.w * vis <= kMaxAlpha)
+                        v_alpha += Tf_va * ra;
+                        if(ov <= kMaxAlpha)
                         {
-                            const float v_sigma = -g.w * vis * v_alpha;
+                            const float v_sigma = -ov * v_alpha;
                             part[0]             = v_sigma * (g.x * dx + g.y * dy);
                             part[1]             = v_sigma * (g.y * dx + g.z * dy);
                             part[2]             = 0.5f * v_sigma * dx * dx;
@@ -548,19 +596,16 @@ __global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
                                 part[6 + CDIM + 1] = fabsf(part[1]);
                             }
                         }
-#pragma unroll
-                        for(int k = 0; k < CDIM; ++k)
-                            buffer[k] += col[k] * fac;
                     }
                     Butterfly<MA, 16>::run(part, lane);
-                    const int64_t gid = s_ids[stage][t];
+                    const uint32_t gid = (uint32_t)sid[t];
                     if(my_dst != nullptr)
-                        atomicAdd(my_dst + gid * my_stride, part[0]);
+                        atomicAdd(my_dst + (size_t)(gid * my_stride), part[0]);
                     if constexpr(MB > 0)
                     {
                         Butterfly<MB, 16>::run(part + MA, lane);
                         if(my_dst_b != nullptr)
-                            atomicAdd(my_dst_b + gid * my_stride_b, part[MA]);
+                            atomicAdd(my_dst_b + (size_t)(gid * my_stride_b), part[MA]);
                     }
                 }
             }
@@ -597,8 +642,16 @@ static int launch_fwd(
     const size_t smem = ring_smem_bytes<CDIM>();
     GSB_CUDA_TRY(cudaFuncSetAttribute(raster_fwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned n_tiles = (unsigned)(I * tw * th);
+    const int32_t *order = nullptr;
+    if(S > 0 && n_tiles >= 2 * 148)
+    { // enough tiles for dispatch order to matter
+        tile_order_kernel<<<1, 1024, 0, st>>>(offsets, (int32_t)n_tiles, (int32_t)S, r.order);
+        if(int rc = check_launch())
+            return rc;
+        order = r.order;
+    }
     raster_fwd_kernel<CDIM><<<n_tiles, kWarps * 32, smem, st>>>(
-        (uint32_t)I, S, r.cull, r.geom, r.color, backgrounds, masks, W, H, tw, th, offsets, render_colors,
+        (uint32_t)I, S, r.cull, r.geom, r.color, order, backgrounds, masks, W, H, tw, th, offsets, render_colors,
         render_alphas, last_ids
     );
     return check_launch();
@@ -617,13 +670,14 @@ static int launch_bwd(
     RecordStreams r    = carve_records(const_cast<void *>(records), S, RecLayout<CDIM>::kColorVec4);
     const size_t smem  = ring_smem_bytes<CDIM>();
     const unsigned n_tiles = (unsigned)(I * tw * th);
+    const int32_t *order   = (n_tiles >= 2 * 148) ? r.order : nullptr; // written by the forward
     if(dst.abs != nullptr)
     {
         GSB_CUDA_TRY(cudaFuncSetAttribute(
             raster_bwd_kernel<CDIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem
         ));
         raster_bwd_kernel<CDIM, true><<<n_tiles, kWarps * 32, smem, st>>>(
-            (uint32_t)I, S, r.cull, r.geom, r.color, flatten_ids, backgrounds, masks, W, H, tw, th, offsets,
+            (uint32_t)I, S, r.cull, r.geom, r.color, order, flatten_ids, backgrounds, masks, W, H, tw, th, offsets,
             render_alphas, last_ids, v_render_colors, v_render_alphas, dst
         );
     }
@@ -633,7 +687,7 @@ static int launch_bwd(
             raster_bwd_kernel<CDIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem
         ));
         raster_bwd_kernel<CDIM, false><<<n_tiles, kWarps * 32, smem, st>>>(
-            (uint32_t)I, S, r.cull, r.geom, r.color, flatten_ids, backgrounds, masks, W, H, tw, th, offsets,
+            (uint32_t)I, S, r.cull, r.geom, r.color, order, flatten_ids, backgrounds, masks, W, H, tw, th, offsets,
             render_alphas, last_ids, v_render_colors, v_render_alphas, dst
         );
     }
@@ -658,12 +712,13 @@ extern "C" int gsb200_raster_supports_channels(int D)
     }
 }
 
-extern "C" size_t gsb200_raster_records_bytes(int64_t n_isects, int D)
+extern "C" size_t gsb200_raster_records_bytes(int64_t n_isects, int D, int64_t n_tiles)
 {
-    if(n_isects < 0 || D <= 0)
+    if(n_isects < 0 || D <= 0 || n_tiles < 0)
         return 0;
     const size_t cv = (size_t)((D + 3) / 4);
-    return 2 * gsb::align256((size_t)n_isects * 16) + gsb::align256((size_t)n_isects * 16 * cv) + 256;
+    return 2 * gsb::align256((size_t)n_isects * 16) + gsb::align256((size_t)n_isects * 16 * cv)
+         + gsb::align256((size_t)(n_tiles + 1) * 4) + 256;
 }
 
 extern "C" int gsb200_raster_fwd(
@@ -718,6 +773,11 @@ extern "C" int gsb200_raster_bwd(
     if(!offsets || !flatten_ids || !records || !render_alphas || !last_ids || !v_render_colors || !v_render_alphas
        || !v_means2d || !v_conics || !v_colors || !v_opacities)
         return GSB200_E_INVALID;
+    {   // the kernels address gradient rows with 32-bit element offsets
+        const int64_t smax = std::max(std::max(v_means2d_stride, v_conics_stride), std::max(std::max(v_colors_stride, v_opacities_stride), v_means2d_abs ? v_means2d_abs_stride : (int64_t)0));
+        if(smax < 0 || (double)I * (double)N * (double)smax >= 4294967296.0)
+            return GSB200_E_UNSUPPORTED;
+    }
     gsb::GradDst dst;
     dst.means2d = v_means2d, dst.s_means2d = v_means2d_stride;
     dst.conics = v_conics, dst.s_conics = v_conics_stride;

@@ -554,7 +554,7 @@ class _RasterizeToPixels(torch.autograd.Function):
             raise TypeError("isect_offsets and flatten_ids must be int32")
         S = fl.shape[0]
         L = lib()
-        records = torch.empty(max(L.gsb200_raster_records_bytes(S, D), 16), device=dev, dtype=torch.uint8)
+        records = torch.empty(max(L.gsb200_raster_records_bytes(S, D, I * th * tw), 16), device=dev, dtype=torch.uint8)
         o = dict(device=dev, dtype=torch.float32)
         render_colors = torch.empty(image_dims + (height, width, D), **o)
         render_alphas = torch.empty(image_dims + (height, width, 1), **o)

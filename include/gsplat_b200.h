@@ -148,11 +148,11 @@ extern "C"
     /* ---- rasterize_to_pixels_3dgs / _bwd : ext.cpp:1079-1089, _wrapper.py:1497-1562, 2010-2117 ----
      * Dense layout: means2d [I,N,2] conics [I,N,3] colors [I,N,D] opacities [I,N]
      * backgrounds [I,D] or NULL, masks [I,th,tw] bool bytes or NULL, offsets [I,th,tw], flatten_ids [n_isects].
-     * tile_size must be 16.  `records` is caller scratch of gsb200_raster_records_bytes(n_isects, D):
-     * the forward packs the depth-sorted per-intersection records there (TMA-streamed by both passes);
-     * the caller keeps it alive for the backward.
+     * tile_size must be 16.  `records` is caller scratch of gsb200_raster_records_bytes(n_isects, D, I*th*tw):
+     * the forward packs the depth-sorted per-intersection records there (TMA-streamed by both passes)
+     * plus a longest-list-first tile dispatch order; the caller keeps it alive for the backward.
      * Outputs: render_colors [I,H,W,D], render_alphas [I,H,W,1], last_ids int32 [I,H,W]. */
-    size_t gsb200_raster_records_bytes(int64_t n_isects, int D);
+    size_t gsb200_raster_records_bytes(int64_t n_isects, int D, int64_t n_tiles);
     int gsb200_raster_fwd(
         int64_t I, int64_t N, int D, const float *means2d, const float *conics, const float *colors,
         const float *opacities, const float *backgrounds, const uint8_t *masks, uint32_t image_width,

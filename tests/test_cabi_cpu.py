@@ -66,7 +66,7 @@ def test_host_only_entry_points():
     for count, bits in [(0, 0), (1, 0), (2, 1), (3, 2), (4, 2), (5, 3), (7, 3), (8, 3), (9, 4), (8160, 13)]:
         assert _cabi.bits_for_count(count) == bits
     assert L.gsb200_raster_supports_channels(3) == 1 and L.gsb200_raster_supports_channels(6) == 0
-    assert L.gsb200_raster_records_bytes(1000, 3) >= 1000 * 48
+    assert L.gsb200_raster_records_bytes(1000, 3, 64) >= 1000 * 48
     assert L.gsb200_error_string(-5).startswith(b"intersect_tile")
 
 
