@@ -443,17 +443,19 @@ __device__ __forceinline__ Dual<G> sadd(float s, const Dual<G> &a, float c)
     return r;
 }
 
-// Y[k] for k < (DEG+1)^2 at unit direction (ux,uy,uz).  Constants: Sloan, JCGT 2013.
-template<int DEG, bool G>
-__device__ __forceinline__ void sh_basis(float ux, float uy, float uz, Dual<G> *Y)
+// Visits Y[k], k = 0 .. (DEG+1)^2 - 1 in increasing k, at unit direction (ux,uy,uz): f(k, Y_k).
+// A visitor (instead of an array) keeps the 16-25 dual numbers out of the register file: each basis
+// function is consumed as soon as it is formed.  Constants: Sloan, JCGT 2013.
+template<int DEG, bool G, class F>
+__device__ __forceinline__ void sh_visit(float ux, float uy, float uz, F &&f)
 {
     const Dual<G> x = dmk<G>(ux, 1.f, 0.f, 0.f), y = dmk<G>(uy, 0.f, 1.f, 0.f), z = dmk<G>(uz, 0.f, 0.f, 1.f);
-    Y[0] = dmk<G>(0.2820947917738781f, 0.f, 0.f, 0.f);
+    f(0, dmk<G>(0.2820947917738781f, 0.f, 0.f, 0.f));
     if constexpr(DEG >= 1)
     {
-        Y[1] = sc(-0.48860251190292f, y);
-        Y[2] = sc(0.48860251190292f, z);
-        Y[3] = sc(-0.48860251190292f, x);
+        f(1, sc(-0.48860251190292f, y));
+        f(2, sc(0.48860251190292f, z));
+        f(3, sc(-0.48860251190292f, x));
     }
     if constexpr(DEG >= 2)
     {
@@ -461,24 +463,26 @@ __device__ __forceinline__ void sh_basis(float ux, float uy, float uz, Dual<G> *
         const Dual<G> fTmp0B = sc(-1.092548430592079f, z);
         const Dual<G> fC1 = x * x - y * y;
         const Dual<G> fS1 = sc(2.f, x * y);
-        Y[4] = sc(0.5462742152960395f, fS1);
-        Y[5] = fTmp0B * y;
-        Y[6] = sadd(0.9461746957575601f, z2, -0.3153915652525201f);
-        Y[7] = fTmp0B * x;
-        Y[8] = sc(0.5462742152960395f, fC1);
+        const Dual<G> Y6 = sadd(0.9461746957575601f, z2, -0.3153915652525201f);
+        f(4, sc(0.5462742152960395f, fS1));
+        f(5, fTmp0B * y);
+        f(6, Y6);
+        f(7, fTmp0B * x);
+        f(8, sc(0.5462742152960395f, fC1));
         if constexpr(DEG >= 3)
         {
             const Dual<G> fTmp0C = sadd(-2.285228997322329f, z2, 0.4570457994644658f);
             const Dual<G> fTmp1B = sc(1.445305721320277f, z);
             const Dual<G> fC2 = x * fC1 - y * fS1;
             const Dual<G> fS2 = x * fS1 + y * fC1;
-            Y[9]  = sc(-0.5900435899266435f, fS2);
-            Y[10] = fTmp1B * fS1;
-            Y[11] = fTmp0C * y;
-            Y[12] = z * sadd(1.865881662950577f, z2, -1.119528997770346f);
-            Y[13] = fTmp0C * x;
-            Y[14] = fTmp1B * fC1;
-            Y[15] = sc(-0.5900435899266435f, fC2);
+            const Dual<G> Y12 = z * sadd(1.865881662950577f, z2, -1.119528997770346f);
+            f(9, sc(-0.5900435899266435f, fS2));
+            f(10, fTmp1B * fS1);
+            f(11, fTmp0C * y);
+            f(12, Y12);
+            f(13, fTmp0C * x);
+            f(14, fTmp1B * fC1);
+            f(15, sc(-0.5900435899266435f, fC2));
             if constexpr(DEG >= 4)
             {
                 const Dual<G> fTmp0D = z * sadd(-4.683325804901025f, z2, 2.007139630671868f);
@@ -486,18 +490,25 @@ __device__ __forceinline__ void sh_basis(float ux, float uy, float uz, Dual<G> *
                 const Dual<G> fTmp2B = sc(-1.770130769779931f, z);
                 const Dual<G> fC3 = x * fC2 - y * fS2;
                 const Dual<G> fS3 = x * fS2 + y * fC2;
-                Y[16] = sc(0.6258357354491763f, fS3);
-                Y[17] = fTmp2B * fS2;
-                Y[18] = fTmp1C * fS1;
-                Y[19] = fTmp0D * y;
-                Y[20] = sc(1.984313483298443f, z * Y[12]) - sc(1.006230589874905f, Y[6]);
-                Y[21] = fTmp0D * x;
-                Y[22] = fTmp1C * fC1;
-                Y[23] = fTmp2B * fC2;
-                Y[24] = sc(0.6258357354491763f, fC3);
+                f(16, sc(0.6258357354491763f, fS3));
+                f(17, fTmp2B * fS2);
+                f(18, fTmp1C * fS1);
+                f(19, fTmp0D * y);
+                f(20, sc(1.984313483298443f, z * Y12) - sc(1.006230589874905f, Y6));
+                f(21, fTmp0D * x);
+                f(22, fTmp1C * fC1);
+                f(23, fTmp2B * fC2);
+                f(24, sc(0.6258357354491763f, fC3));
             }
         }
     }
+}
+
+// array form (used where all values are needed at once)
+template<int DEG, bool G>
+__device__ __forceinline__ void sh_basis(float ux, float uy, float uz, Dual<G> *Y)
+{
+    sh_visit<DEG, G>(ux, uy, uz, [&](int k, const Dual<G> &v) { Y[k] = v; });
 }
 
 // dir = mean + R^T t  (= mean - camera position for a rigid viewmat)

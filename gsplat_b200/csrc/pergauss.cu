@@ -396,8 +396,6 @@ __global__ void __launch_bounds__(kThreads) project_sh_fwd_kernel(
         sh_view_dir(mean, vm, dir);
         const float inorm = 1.f / sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
         constexpr int NB  = (DEG + 1) * (DEG + 1);
-        Dual<false> Y[NB];
-        sh_basis<DEG, false>(dir[0] * inorm, dir[1] * inorm, dir[2] * inorm, Y);
         const float *cf = sh + n * K * 3;
         float cbuf[NB * 3];
         if(((K * 3) & 3) == 0 && (NB * 3) % 4 == 0)
@@ -416,14 +414,16 @@ __global__ void __launch_bounds__(kThreads) project_sh_fwd_kernel(
             for(int k = 0; k < NB * 3; ++k)
                 cbuf[k] = __ldg(cf + k);
         }
+        float acc3[3] = {0.f, 0.f, 0.f};
+        sh_visit<DEG, false>(dir[0] * inorm, dir[1] * inorm, dir[2] * inorm, [&](int k, const Dual<false> &Yk) {
+#pragma unroll
+            for(int d = 0; d < 3; ++d)
+                acc3[d] += Yk.v * cbuf[k * 3 + d];
+        });
 #pragma unroll
         for(int d = 0; d < 3; ++d)
         {
-            float acc = 0.f;
-#pragma unroll
-            for(int k = 0; k < NB; ++k)
-                acc += Y[k].v * cbuf[k * 3 + d];
-            const float shifted = acc + 0.5f;
+            const float shifted = acc3[d] + 0.5f;
             rgb[d]              = shifted > 0.f ? shifted : 0.f;
         }
     }
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(kThreads) project_sh_fwd_kernel(
 
 // One thread per gaussian, looping over cameras: v_means / v_quats / v_scales / v_sh written once.
 template<int DEG>
-__global__ void __launch_bounds__(kThreads) project_sh_bwd_kernel(
+__global__ void __launch_bounds__(kThreads, 2) project_sh_bwd_kernel(
     int64_t C, int64_t N, int64_t K, const float *__restrict__ means, const float *__restrict__ quats,
     const float *__restrict__ scales, const float *__restrict__ sh, const float *__restrict__ viewmats,
     const float *__restrict__ Ks, uint32_t W, uint32_t H, float eps2d, const int32_t *__restrict__ radii,
@@ -491,23 +491,19 @@ __global__ void __launch_bounds__(kThreads) project_sh_bwd_kernel(
         sh_view_dir(mean, vm, dir);
         const float inorm = 1.f / sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
         const float u[3]  = {dir[0] * inorm, dir[1] * inorm, dir[2] * inorm};
-        Dual<true> Y[NB];
-        sh_basis<DEG, true>(u[0], u[1], u[2], Y);
         float vu[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for(int k = 0; k < NB; ++k)
-        {
+        sh_visit<DEG, true>(u[0], u[1], u[2], [&](int k, const Dual<true> &Yk) {
             float gk = 0.f;
 #pragma unroll
             for(int d = 0; d < 3; ++d)
             {
-                acc[k * 3 + d] += Y[k].v * vcol[d];
+                acc[k * 3 + d] += Yk.v * vcol[d];
                 gk += __ldg(cf + k * 3 + d) * vcol[d];
             }
-            vu[0] += gk * Y[k].x;
-            vu[1] += gk * Y[k].y;
-            vu[2] += gk * Y[k].z;
-        }
+            vu[0] += gk * Yk.x;
+            vu[1] += gk * Yk.y;
+            vu[2] += gk * Yk.z;
+        });
         if(DEG >= 1)
         {
             const float dot = vu[0] * u[0] + vu[1] * u[1] + vu[2] * u[2];
@@ -674,6 +670,81 @@ __global__ void __launch_bounds__(kThreads) isect_emit_kernel(
         flatten_ids[cur] = (int32_t)i;
         ++cur;
     });
+}
+
+// ---- tile-bucketed variant (no global sort): the count pass also histograms the tiles, the emit pass
+// drops each (depth, gaussian) key straight into its tile's segment; a per-tile segmented sort finishes.
+__global__ void __launch_bounds__(kThreads) isect_bucket_count_kernel(
+    int64_t total, int64_t N, int64_t n_tiles, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
+    const float *__restrict__ conics, const float *__restrict__ opacities, uint32_t tile_size, uint32_t tw, uint32_t th,
+    int32_t *__restrict__ tiles_per_gauss, int32_t *__restrict__ tile_counts
+)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= total)
+        return;
+    const int2 r = reinterpret_cast<const int2 *>(radii)[i];
+    int cnt      = 0;
+    if(r.x > 0 && r.y > 0)
+    {
+        const float2 m = reinterpret_cast<const float2 *>(means2d)[i];
+        float cn[3] = {0.f, 0.f, 0.f}, op = 0.f;
+        const bool accu = conics != nullptr && opacities != nullptr;
+        if(accu)
+            cn[0] = conics[i * 3], cn[1] = conics[i * 3 + 1], cn[2] = conics[i * 3 + 2], op = opacities[i];
+        int32_t *tc = tile_counts + (i / N) * n_tiles;
+        cnt = tiles_of_gaussian(m.x, m.y, r.x, r.y, accu ? cn : nullptr, accu ? &op : nullptr, tile_size, tw, th,
+                                [&](int64_t tile) { atomicAdd(tc + tile, 1); });
+    }
+    tiles_per_gauss[i] = cnt;
+}
+
+__global__ void __launch_bounds__(kThreads) isect_bucket_emit_kernel(
+    int64_t total, int64_t N, int64_t n_tiles, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
+    const float *__restrict__ depths, const float *__restrict__ conics, const float *__restrict__ opacities,
+    uint32_t tile_size, uint32_t tw, uint32_t th, const int32_t *__restrict__ offsets, int32_t *__restrict__ cursor,
+    uint64_t *__restrict__ keys
+)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= total)
+        return;
+    const int2 r = reinterpret_cast<const int2 *>(radii)[i];
+    if(r.x <= 0 || r.y <= 0)
+        return;
+    const float2 m = reinterpret_cast<const float2 *>(means2d)[i];
+    float cn[3] = {0.f, 0.f, 0.f}, op = 0.f;
+    const bool accu = conics != nullptr && opacities != nullptr;
+    if(accu)
+        cn[0] = conics[i * 3], cn[1] = conics[i * 3 + 1], cn[2] = conics[i * 3 + 2], op = opacities[i];
+    const int64_t base = (i / N) * n_tiles;
+    // depth in the high word, gaussian index in the low word: unique keys, so the per-tile order
+    // (depth, then emit order) does not depend on which thread won which slot
+    const uint64_t key = ((uint64_t)__float_as_uint(depths[i]) << 32) | (uint64_t)(uint32_t)i;
+    tiles_of_gaussian(m.x, m.y, r.x, r.y, accu ? cn : nullptr, accu ? &op : nullptr, tile_size, tw, th, [&](int64_t tile) {
+        const int32_t pos = offsets[base + tile] + atomicAdd(cursor + base + tile, 1);
+        keys[pos]         = key;
+    });
+}
+
+// one warp per tile: sorted per-tile keys -> reference-format isect_ids / flatten_ids
+__global__ void __launch_bounds__(kThreads) isect_bucket_finalize_kernel(
+    int64_t total_tiles, int64_t n_tiles, uint32_t tile_n_bits, const int32_t *__restrict__ offsets,
+    const uint64_t *__restrict__ keys, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids
+)
+{
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if(t >= total_tiles)
+        return;
+    const unsigned lane = threadIdx.x & 31;
+    const int64_t hi    = (((t / n_tiles) << tile_n_bits) | (t % n_tiles)) << 32;
+    const int32_t b = offsets[t], e = offsets[t + 1];
+    for(int32_t s = b + (int32_t)lane; s < e; s += 32)
+    {
+        const uint64_t k = keys[s];
+        isect_ids[s]     = hi | (int64_t)(k >> 32);
+        flatten_ids[s]   = (int32_t)(uint32_t)k;
+    }
 }
 
 // offsets[(image, tile)] = first sorted index of that tile's run.  One thread per sorted
@@ -987,6 +1058,89 @@ extern "C" int gsb200_isect_offsets(
         return GSB200_E_INVALID;
     isect_offsets_kernel<<<grid_for(n_isects, kThreads), kThreads, 0, st>>>(
         n_isects, isect_ids, total, n_tiles, bits_for_count(n_tiles), offsets
+    );
+    return check_launch();
+}
+
+// ---- tile-bucketed intersection (used by rasterization(); same outputs as count/emit/sort/offsets)
+extern "C" size_t gsb200_isect_bucket_scan_workspace_bytes(int64_t total_tiles)
+{
+    size_t bytes = 0;
+    if(total_tiles <= 0)
+        return 0;
+    cub::DeviceScan::ExclusiveSum((void *)nullptr, bytes, (const int32_t *)nullptr, (int32_t *)nullptr, total_tiles + 1);
+    return bytes + 256;
+}
+
+extern "C" int gsb200_isect_bucket_count(
+    int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *conics, const float *opacities,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int32_t *tiles_per_gauss, int32_t *tile_counts,
+    int32_t *offsets, void *workspace, size_t workspace_bytes, void *stream
+)
+{
+    if(I < 0 || N < 0 || tile_size == 0)
+        return GSB200_E_INVALID;
+    const int64_t n_tiles = (int64_t)tile_width * tile_height, total_tiles = I * n_tiles, total = I * N;
+    if(total_tiles == 0)
+        return GSB200_OK;
+    if(!tile_counts || !offsets || !workspace || (total > 0 && (!means2d || !radii || !tiles_per_gauss)))
+        return GSB200_E_INVALID;
+    if(bits_for_count(I) + bits_for_count(n_tiles) > 32)
+        return GSB200_E_KEYBITS;
+    cudaStream_t st = (cudaStream_t)stream;
+    // tile_counts has total_tiles + 1 entries (the last stays 0 so that the exclusive scan ends with the total)
+    GSB_CUDA_TRY(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * (size_t)(total_tiles + 1), st));
+    if(total > 0)
+    {
+        isect_bucket_count_kernel<<<grid_for(total, kThreads), kThreads, 0, st>>>(
+            total, N, n_tiles, means2d, radii, conics, opacities, tile_size, tile_width, tile_height, tiles_per_gauss,
+            tile_counts
+        );
+        if(int rc = check_launch())
+            return rc;
+    }
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum((void *)nullptr, need, tile_counts, offsets, total_tiles + 1, st);
+    if(need > workspace_bytes)
+        return GSB200_E_WORKSPACE;
+    GSB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(workspace, need, tile_counts, offsets, total_tiles + 1, st));
+    return GSB200_OK;
+}
+
+extern "C" int gsb200_isect_bucket_emit(
+    int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *depths, const float *conics,
+    const float *opacities, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, const int32_t *offsets,
+    int32_t *cursor, uint64_t *keys, void *stream
+)
+{
+    if(I < 0 || N < 0 || tile_size == 0)
+        return GSB200_E_INVALID;
+    const int64_t n_tiles = (int64_t)tile_width * tile_height, total = I * N;
+    if(total == 0 || n_tiles == 0)
+        return GSB200_OK;
+    if(!means2d || !radii || !depths || !offsets || !cursor || !keys)
+        return GSB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    GSB_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)(I * n_tiles), st));
+    isect_bucket_emit_kernel<<<grid_for(total, kThreads), kThreads, 0, st>>>(
+        total, N, n_tiles, means2d, radii, depths, conics, opacities, tile_size, tile_width, tile_height, offsets, cursor,
+        keys
+    );
+    return check_launch();
+}
+
+extern "C" int gsb200_isect_bucket_finalize(
+    int64_t I, uint32_t tile_width, uint32_t tile_height, const int32_t *offsets, const uint64_t *keys_sorted,
+    int64_t *isect_ids, int32_t *flatten_ids, void *stream
+)
+{
+    const int64_t n_tiles = (int64_t)tile_width * tile_height, total_tiles = I * n_tiles;
+    if(total_tiles <= 0)
+        return GSB200_OK;
+    if(!offsets || !keys_sorted || !isect_ids || !flatten_ids)
+        return GSB200_E_INVALID;
+    isect_bucket_finalize_kernel<<<grid_for(total_tiles * 32, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        total_tiles, n_tiles, bits_for_count(n_tiles), offsets, keys_sorted, isect_ids, flatten_ids
     );
     return check_launch();
 }

@@ -31,12 +31,13 @@ template<int CDIM>
 struct RecLayout
 {
     static constexpr int kColorVec4 = (CDIM + 3) / 4; // float4 per record for colours
-    static constexpr int kStageBytes = kBatch * (16 + 16 + 16 * kColorVec4);
+    static constexpr int kStageBytes = kBatch * (16 + 16 + 16 + 16 * kColorVec4);
 };
 
 struct RecordStreams
 {
-    float4 *cull;   // [S] {mx, my, ex, ey}
+    float4 *cull;   // [S] {mx, my, ex, ey}: mean + half extents of the axis-aligned box of {alpha >= 1/255}
+    float4 *axis;   // [S] {ux, uy, lu, lv}: unit major-curvature axis and half lengths of its oriented box
     float4 *geom;   // [S] {a, b, c, opacity}
     float4 *color;  // [S * kColorVec4]
     int32_t *order; // [n_tiles] tile indices, longest list first
@@ -49,6 +50,8 @@ static inline RecordStreams carve_records(void *base, int64_t S, int cvec4)
     RecordStreams r;
     char *p = (char *)base;
     r.cull  = (float4 *)p;
+    p += align256((size_t)S * 16);
+    r.axis = (float4 *)p;
     p += align256((size_t)S * 16);
     r.geom = (float4 *)p;
     p += align256((size_t)S * 16);
@@ -100,7 +103,7 @@ template<int CDIM>
 __global__ void __launch_bounds__(256) pack_records_kernel(
     const int64_t S, const int32_t *__restrict__ flatten_ids, const float *__restrict__ means2d,
     const float *__restrict__ conics, const float *__restrict__ colors, const float *__restrict__ opacities,
-    float4 *__restrict__ cull, float4 *__restrict__ geom, float4 *__restrict__ color
+    float4 *__restrict__ cull, float4 *__restrict__ axis, float4 *__restrict__ geom, float4 *__restrict__ color
 )
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,7 +114,9 @@ __global__ void __launch_bounds__(256) pack_records_kernel(
     const float a = conics[g * 3], b = conics[g * 3 + 1], c = conics[g * 3 + 2];
     const float op = opacities[g];
     // conservative half extents of {alpha >= 1/255}: |dx| <= sqrt(t c / det), t = 2 ln(255 op)
-    float ex, ey;
+    // and of the box oriented along the ellipse axes (unit u = eigenvector of the larger eigenvalue l1 of
+    // [[a,b],[b,c]], v = (-uy, ux)): |d.u| <= sqrt(t / l1), |d.v| <= sqrt(t / l2).  All bounds inflated.
+    float ex, ey, ux = 1.f, uy = 0.f, lu = 1e30f, lv = 1e30f;
     const float det = a * c - b * b;
     if(!(op >= kAlphaThreshold))
     {
@@ -128,8 +133,27 @@ __global__ void __launch_bounds__(256) pack_records_kernel(
         ey            = sqrtf(t * a / det) * 1.0001f + 0.01f;
         if(!isfinite(ex) || !isfinite(ey))
             ex = ey = 1e30f;
+        const float hd = 0.5f * (a - c);
+        const float l1 = 0.5f * (a + c) + sqrtf(hd * hd + b * b);
+        const float l2 = det / l1;
+        float vx1 = b, vy1 = l1 - a, vx2 = l1 - c, vy2 = b;
+        if(vx2 * vx2 + vy2 * vy2 > vx1 * vx1 + vy1 * vy1)
+            vx1 = vx2, vy1 = vy2;
+        const float nn = vx1 * vx1 + vy1 * vy1;
+        if(nn > 1e-30f && l2 > 0.f && isfinite(l1))
+        {
+            const float inv = rsqrtf(nn);
+            ux = vx1 * inv, uy = vy1 * inv;
+            const float ru = sqrtf(t / l1), rv = sqrtf(t / l2);
+            // an axis direction error delta (~1e-6 rad) shifts the far end of the other axis by delta * length
+            lu = ru * 1.0001f + 0.01f + 4e-6f * rv;
+            lv = rv * 1.0001f + 0.01f + 4e-6f * ru;
+            if(!isfinite(lu) || !isfinite(lv))
+                lu = lv = 1e30f;
+        }
     }
     cull[s] = make_float4(m.x, m.y, ex, ey);
+    axis[s] = make_float4(ux, uy, lu, lv);
     geom[s] = make_float4(a, b, c, op);
     constexpr int CV = RecLayout<CDIM>::kColorVec4;
     float cbuf[CV * 4];
@@ -159,7 +183,13 @@ __device__ __forceinline__ TileGeom decode_tile(const int32_t *__restrict__ orde
     return t;
 }
 
-// shared-memory ring: per stage [cull | geom | color] + one full-barrier per stage
+// the axis stream lies between the cull and geom streams, equally sized: midpoint of the two pointers
+__device__ __forceinline__ const float4 *gaxis_from(const float4 *gcull, const float4 *ggeom)
+{
+    return gcull + ((ggeom - gcull) >> 1);
+}
+
+// shared-memory ring: per stage [cull | axis | geom | color] + one full-barrier per stage
 template<int CDIM>
 struct Ring
 {
@@ -171,8 +201,9 @@ struct Ring
     {
         return reinterpret_cast<float4 *>(base + (size_t)s * RecLayout<CDIM>::kStageBytes);
     }
-    __device__ __forceinline__ float4 *geom(int s) const { return cull(s) + kBatch; }
-    __device__ __forceinline__ float4 *color(int s) const { return cull(s) + 2 * kBatch; }
+    __device__ __forceinline__ float4 *axis(int s) const { return cull(s) + kBatch; }
+    __device__ __forceinline__ float4 *geom(int s) const { return cull(s) + 2 * kBatch; }
+    __device__ __forceinline__ float4 *color(int s) const { return cull(s) + 3 * kBatch; }
     __device__ __forceinline__ uint64_t *full(int s) const
     {
         return reinterpret_cast<uint64_t *>(base + (size_t)kStages * RecLayout<CDIM>::kStageBytes) + s;
@@ -182,9 +213,11 @@ struct Ring
         int stage, const float4 *gcull, const float4 *ggeom, const float4 *gcolor, int64_t first, int count
     ) const
     {
+        // the axis stream sits right behind the cull stream at a fixed distance (see carve_records)
         const uint32_t n16 = (uint32_t)count * 16u;
-        mbar_arrive_expect_tx(full(stage), n16 * (2u + CV));
+        mbar_arrive_expect_tx(full(stage), n16 * (3u + CV));
         bulk_g2s(cull(stage), gcull + first, n16, full(stage));
+        bulk_g2s(axis(stage), gaxis_from(gcull, ggeom) + first, n16, full(stage));
         bulk_g2s(geom(stage), ggeom + first, n16, full(stage));
         bulk_g2s(color(stage), gcolor + first * CV, n16 * CV, full(stage));
     }
@@ -194,6 +227,17 @@ template<int CDIM>
 constexpr size_t ring_smem_bytes()
 {
     return (size_t)kStages * RecLayout<CDIM>::kStageBytes + kStages * sizeof(uint64_t);
+}
+
+// Can the gaussian reach alpha >= 1/255 anywhere in the 8x4 pixel block centred at (cx, cy)?  Conservative:
+// its axis-aligned AND its oriented bounding box must both overlap the block (pixel centres span +-3.5, +-1.5).
+__device__ __forceinline__ bool block_may_touch(const float4 q, const float4 ax, const float cx, const float cy)
+{
+    constexpr float hx = 3.5f, hy = 1.5f;
+    const float dx = q.x - cx, dy = q.y - cy;
+    const float au = fabsf(ax.x), av = fabsf(ax.y);
+    return (fabsf(dx) <= q.z + hx) && (fabsf(dy) <= q.w + hy) && (fabsf(dx * ax.x + dy * ax.y) <= ax.z + hx * au + hy * av)
+        && (fabsf(dy * ax.x - dx * ax.y) <= ax.w + hx * av + hy * au);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -264,7 +308,6 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
 
     // pixel-block centre extents for the cull test: centres span [bx0+0.5, bx0+7.5] x [by0+0.5, by0+3.5]
     const float cx = (float)bx0 + 4.0f, cy = (float)by0 + 2.0f;
-    constexpr float hx = 3.5f, hy = 1.5f;
 
     float T = 1.f;
     float pix_out[CDIM];
@@ -285,6 +328,7 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
         {
             mbar_wait(ring.full(stage), parity);
             const float4 *scull = ring.cull(stage);
+            const float4 *saxis = ring.axis(stage);
             const float4 *sgeom = ring.geom(stage);
             const float4 *scol  = ring.color(stage);
             for(int c0 = 0; c0 < count; c0 += 32)
@@ -295,10 +339,7 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
                 const int mine = c0 + 31 - (int)lane;
                 bool hit       = false;
                 if(mine < count)
-                {
-                    const float4 q = scull[mine];
-                    hit            = (fabsf(q.x - cx) <= q.z + hx) && (fabsf(q.y - cy) <= q.w + hy);
-                }
+                    hit = block_may_touch(scull[mine], saxis[mine], cx, cy);
                 uint32_t mask = __ballot_sync(0xffffffffu, hit);
                 while(mask)
                 {
@@ -506,7 +547,6 @@ __global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
                 ring.issue(s, gcull, ggeom, gcolor, batch_first(s), batch_count(s));
     }
     const float cx = (float)bx0 + 4.0f, cy = (float)by0 + 2.0f;
-    constexpr float hx = 3.5f, hy = 1.5f;
 
     const float neg_Tf_bg = bg ? -T_final * bg_dot : 0.f;
     const float Tf_va     = T_final * v_render_a + neg_Tf_bg; // T_final * (v_render_a - bg . v_render_c)
@@ -525,6 +565,7 @@ __global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
         {
             mbar_wait(ring.full(stage), parity);
             const float4 *scull   = ring.cull(stage);
+            const float4 *saxis   = ring.axis(stage);
             const float4 *sgeom   = ring.geom(stage);
             const float4 *scol    = ring.color(stage);
             const int32_t *sid    = s_ids[stage];
@@ -536,10 +577,7 @@ __global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
                 const int mine = c0 + (int)lane;
                 bool hit       = false;
                 if(mine >= 0 && mine <= warp_lim)
-                {
-                    const float4 q = scull[mine];
-                    hit            = (fabsf(q.x - cx) <= q.z + hx) && (fabsf(q.y - cy) <= q.w + hy);
-                }
+                    hit = block_may_touch(scull[mine], saxis[mine], cx, cy);
                 uint32_t mask = __ballot_sync(0xffffffffu, hit);
                 while(mask)
                 {
@@ -634,7 +672,7 @@ static int launch_fwd(
     if(S > 0)
     {
         pack_records_kernel<CDIM><<<grid_for(S, 256), 256, 0, st>>>(
-            S, flatten_ids, means2d, conics, colors, opacities, r.cull, r.geom, r.color
+            S, flatten_ids, means2d, conics, colors, opacities, r.cull, r.axis, r.geom, r.color
         );
         if(int rc = check_launch())
             return rc;
@@ -717,7 +755,7 @@ extern "C" size_t gsb200_raster_records_bytes(int64_t n_isects, int D, int64_t n
     if(n_isects < 0 || D <= 0 || n_tiles < 0)
         return 0;
     const size_t cv = (size_t)((D + 3) / 4);
-    return 2 * gsb::align256((size_t)n_isects * 16) + gsb::align256((size_t)n_isects * 16 * cv)
+    return 3 * gsb::align256((size_t)n_isects * 16) + gsb::align256((size_t)n_isects * 16 * cv)
          + gsb::align256((size_t)(n_tiles + 1) * 4) + 256;
 }
 

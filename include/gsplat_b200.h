@@ -145,6 +145,36 @@ extern "C"
         int32_t *offsets, void *stream
     );
 
+    /* ---- tile-bucketed intersection: same four outputs as intersect_tile(sort=True) + intersect_offset
+     * (ext.cpp:1022-1027) without the global radix sort.  Used by rasterization().
+     *   1. bucket_count : tiles_per_gauss [I*N] + per-tile histogram tile_counts [I*T+1] + its exclusive scan
+     *                     offsets [I*T+1] (offsets[I*T] = n_isects; the first I*T entries ARE isect_offsets)
+     *   2. bucket_emit  : keys[n_isects] = depth_bits << 32 | flatten_id, dropped into the tile's segment
+     *                     (cursor [I*T] scratch)
+     *   3. segsort_keys : cub::DeviceSegmentedSort over the tile segments
+     *   4. bucket_finalize: isect_ids / flatten_ids in the reference's format and order. */
+    size_t gsb200_isect_bucket_scan_workspace_bytes(int64_t total_tiles);
+    int gsb200_isect_bucket_count(
+        int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *conics,
+        const float *opacities, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+        int32_t *tiles_per_gauss, int32_t *tile_counts, int32_t *offsets, void *workspace, size_t workspace_bytes,
+        void *stream
+    );
+    int gsb200_isect_bucket_emit(
+        int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *depths, const float *conics,
+        const float *opacities, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+        const int32_t *offsets, int32_t *cursor, uint64_t *keys, void *stream
+    );
+    size_t gsb200_segsort_workspace_bytes(int64_t n_items, int64_t n_segments);
+    int gsb200_segsort_keys(
+        int64_t n_items, int64_t n_segments, const int32_t *offsets, const uint64_t *keys_in, uint64_t *keys_out,
+        void *workspace, size_t workspace_bytes, void *stream
+    );
+    int gsb200_isect_bucket_finalize(
+        int64_t I, uint32_t tile_width, uint32_t tile_height, const int32_t *offsets, const uint64_t *keys_sorted,
+        int64_t *isect_ids, int32_t *flatten_ids, void *stream
+    );
+
     /* ---- rasterize_to_pixels_3dgs / _bwd : ext.cpp:1079-1089, _wrapper.py:1497-1562, 2010-2117 ----
      * Dense layout: means2d [I,N,2] conics [I,N,3] colors [I,N,D] opacities [I,N]
      * backgrounds [I,D] or NULL, masks [I,th,tw] bool bytes or NULL, offsets [I,th,tw], flatten_ids [n_isects].

@@ -218,6 +218,34 @@ def test_isect_accutile_exact_on_scene(gs):
     assert offn[0] == 0 and (np.diff(offn) >= 0).all() and offn[-1] <= len(ids)
 
 
+def test_isect_bucketed_equals_sorted_path(gs):
+    from gsplat_b200 import ops
+
+    sc = scene.make_scene(n_max=80000)
+    W, H = 800, 450
+    Ks = scene.rescale_K(sc["Ks"], sc["width"], sc["height"], W, H)
+    radii, m2, dep, con, _ = _project_scene(sc, W, H, Ks, C=3)
+    op = np.ascontiguousarray(np.broadcast_to(sc["opacities"][None], dep.shape))
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    for accu in (True, False):
+        kw = dict(conics=_t(con), opacities=_t(op)) if accu else {}
+        a = gs.isect_tiles(_t(m2), _t(radii), _t(dep), 16, tw, th, **kw)
+        off = gs.isect_offset_encode(a[1], 3, tw, th)
+        b = ops.isect_tiles_bucketed(_t(m2), _t(radii), _t(dep), 16, tw, th, **kw)
+        assert a[1].numel() > 10000
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(off, b[3])
+    # ties in depth inside a tile keep emit (gaussian index) order
+    m2t = np.tile(np.array([[20.0, 20.0]], np.float32), (1, 64, 1))
+    r = np.full((1, 64, 2), 10, np.int32)
+    d = np.full((1, 64), 1.5, np.float32)
+    a = gs.isect_tiles(_t(m2t), _t(r), _t(d), 16, 4, 4)
+    b = ops.isect_tiles_bucketed(_t(m2t), _t(r), _t(d), 16, 4, 4)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    # empty
+    e = ops.isect_tiles_bucketed(_t(np.zeros((1, 4, 2), np.float32)), _t(np.zeros((1, 4, 2), np.int32)), _t(np.ones((1, 4), np.float32)), 16, 3, 2)
+    assert e[1].numel() == 0 and (e[3] == 0).all()
+
+
 def _raster_case(gs, m2, con, col, op, W, H, off, fl, bg=None, absgrad=False, seed=0, strict_frac=0.995):
     """Runs fwd+bwd on the GPU and in the oracle (f64) and applies the module's tolerance contract."""
     D = col.shape[-1]
