@@ -13,7 +13,8 @@ all-reduced over NCCL (view-axis data parallelism, weak scaling).  The optimizer
 
 Printed line (rank 0): metric = rendered views/s (fwd+bwd), ms_per_step = train-step ms,
 value = device-resident timing, e2e = same step with the per-step host->device copy of the camera and
-the target image from pinned memory and the device->host read of the loss inside the timed region.
+the target image from pinned memory (double-buffered on a copy stream) and the device->host read of the
+loss inside the timed region.
 roofline = dominant kernel (compositing backward) algorithmic bytes / CUDA-event time vs the measured
 HBM peak; cpu_baseline = the CPU oracle port timed on this box's host cores.
 """
@@ -261,11 +262,26 @@ def main():
     grad_names = ("means", "quats", "scales", "opacities", "sh")
     flat_grads = torch.zeros(N * 59, device=dev) if world > 1 else None
 
-    def step(e2e: bool):
+    # e2e input pipeline: every step's camera + target image are copied from pinned host memory inside
+    # the timed region, double-buffered on a side stream so that the copy of step i+1 overlaps the compute
+    # of step i (what a DataLoader with pin_memory + non_blocking does); step i waits for ITS copy.
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_in = [(torch.empty_like(vm_dev), torch.empty_like(K_dev), torch.empty_like(target_dev)) for _ in range(2)]
+    copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def issue_copy(slot: int):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])  # the previous user of this slot has finished
+            dev_in[slot][0].copy_(vm_host, non_blocking=True)
+            dev_in[slot][1].copy_(K_host, non_blocking=True)
+            dev_in[slot][2].copy_(target_host, non_blocking=True)
+            copy_done[slot].record(copy_stream)
+
+    def step(e2e: bool, slot: int = 0):
         if e2e:
-            vm = vm_host.to(dev, non_blocking=True)
-            K = K_host.to(dev, non_blocking=True)
-            tgt = target_host.to(dev, non_blocking=True)
+            torch.cuda.current_stream().wait_event(copy_done[slot])
+            vm, K, tgt = dev_in[slot]
         else:
             vm, K, tgt = vm_dev, K_dev, target_dev
         for p in params.values():
@@ -285,6 +301,7 @@ def main():
                 o += g.numel()
             dist.all_reduce(flat_grads)
         if e2e:
+            consumed[slot].record()
             loss_host.copy_(loss.detach(), non_blocking=True)
         return meta
 
@@ -294,8 +311,17 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            step(e2e)
+        if e2e:
+            for c in consumed:
+                c.record()
+            issue_copy(0)  # the first copy is inside the timed region too
+            for i in range(steps):
+                if i + 1 < steps:
+                    issue_copy((i + 1) & 1)
+                step(True, i & 1)
+        else:
+            for _ in range(steps):
+                step(False)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -305,9 +331,12 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
+    for c in consumed:
+        c.record()
+    for i in range(max(args.warmup, 3)):
         meta = step(False)
-        step(True)
+        issue_copy(i & 1)
+        step(True, i & 1)
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -386,9 +415,10 @@ def main():
                 "value": n_gpus * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
             },
-            # ours per step: project_sh fwd, isect count, cub scan (x?), emit, cub sort (several), offsets, pack,
-            # raster fwd, raster bwd, project_sh bwd -- counted as C-ABI kernel launches of our own kernels
-            "gpu_launches": args.steps * 2 * 8,
+            # our own kernels per step: project_sh_fwd, isect_count, isect_emit, isect_offsets, pack_records,
+            # tile_order, raster_fwd, raster_bwd, project_sh_bwd (= 9; cub scan / radix-sort launches made by the
+            # library are not counted); timed region = `steps` device-resident + `steps` e2e steps
+            "gpu_launches": args.steps * 2 * 9,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "ref_cuda": ref_cuda,
         }
         print(json.dumps(line))

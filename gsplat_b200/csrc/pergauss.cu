@@ -302,13 +302,14 @@ template<int DEG>
 __global__ void __launch_bounds__(kThreads) sh_bwd_kernel(
     int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, const float *__restrict__ means,
     const float *__restrict__ viewmats, const float *__restrict__ coeffs, const uint8_t *__restrict__ masks,
-    const float *__restrict__ v_colors, float *__restrict__ v_coeffs, float *__restrict__ v_means
+    const float *__restrict__ v_colors, float *__restrict__ v_coeffs, float *__restrict__ v_means,
+    float *__restrict__ v_dirsum
 )
 {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if(idx >= N * D)
-        return;
-    const int64_t n = idx / D, d = idx % D;
+    const int64_t idx  = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = idx < N * D; // out-of-range threads stay for the warp reduction of v_dirsum
+    const int64_t n = in_range ? idx / D : 0, d = in_range ? idx % D : 0;
+    const unsigned lane = threadIdx.x & 31;
     constexpr int NB = (DEG + 1) * (DEG + 1);
     float acc[NB];
 #pragma unroll
@@ -319,8 +320,10 @@ __global__ void __launch_bounds__(kThreads) sh_bwd_kernel(
     {
         const int64_t b = img / C;
         const int64_t o = img * N + n;
-        if(masks && !masks[o])
-            continue;
+        const bool on   = in_range && !(masks && !masks[o]);
+        float vd[3]     = {0.f, 0.f, 0.f};
+        if(on)
+        {
         const float *mean = means + (b * N + n) * 3;
         float dir[3];
         sh_view_dir(mean, viewmats + img * 16, dir);
@@ -339,14 +342,30 @@ __global__ void __launch_bounds__(kThreads) sh_bwd_kernel(
             vu[1] += g * Y[k].y;
             vu[2] += g * Y[k].z;
         }
-        if(v_means != nullptr && DEG >= 1)
+        if(DEG >= 1)
         {
             const float dot = vu[0] * u[0] + vu[1] * u[1] + vu[2] * u[2];
 #pragma unroll
             for(int j = 0; j < 3; ++j)
-                atomicAdd(v_means + (b * N + n) * 3 + j, (vu[j] - dot * u[j]) * inorm);
+                vd[j] = (vu[j] - dot * u[j]) * inorm;
+            if(v_means != nullptr)
+            {
+#pragma unroll
+                for(int j = 0; j < 3; ++j)
+                    atomicAdd(v_means + (b * N + n) * 3 + j, vd[j]);
+            }
+        }
+        }
+        if(v_dirsum != nullptr && DEG >= 1)
+        { // per-image sum of the view-direction gradient (for the pose gradient): warp reduce, one atomic per warp
+            Butterfly<3, 16>::run(vd, lane);
+            const int slot = butterfly_slot<3>(lane);
+            if(slot >= 0 && vd[0] != 0.f)
+                atomicAdd(v_dirsum + img * 3 + slot, vd[0]);
         }
     }
+    if(!in_range)
+        return;
     float *vcf = v_coeffs + n * K * D;
 #pragma unroll
     for(int k = 0; k < NB; ++k)
@@ -896,7 +915,7 @@ extern "C" int gsb200_sh_fwd(
 extern "C" int gsb200_sh_bwd(
     int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, int degrees_to_use, const float *means,
     const float *viewmats, const float *coeffs, const uint8_t *masks, const float *v_colors, float *v_coeffs,
-    float *v_means, void *stream
+    float *v_means, float *v_dirsum, void *stream
 )
 {
     if(B < 0 || C < 0 || N < 0 || K <= 0 || D <= 0 || degrees_to_use < 0 || degrees_to_use > 4
@@ -905,11 +924,13 @@ extern "C" int gsb200_sh_bwd(
     cudaStream_t st = (cudaStream_t)stream;
     if(v_means && B * N > 0)
         GSB_CUDA_TRY(cudaMemsetAsync(v_means, 0, sizeof(float) * 3 * (size_t)(B * N), st));
+    if(v_dirsum && B * C > 0)
+        GSB_CUDA_TRY(cudaMemsetAsync(v_dirsum, 0, sizeof(float) * 3 * (size_t)(B * C), st));
     if(N == 0)
         return GSB200_OK;
     if(!means || !viewmats || !coeffs || !v_colors || !v_coeffs)
         return GSB200_E_INVALID;
-#define CALL(d) sh_bwd_kernel<d><<<grid_for(N * D, kThreads), kThreads, 0, st>>>(B, C, N, K, D, means, viewmats, coeffs, masks, v_colors, v_coeffs, v_means)
+#define CALL(d) sh_bwd_kernel<d><<<grid_for(N * D, kThreads), kThreads, 0, st>>>(B, C, N, K, D, means, viewmats, coeffs, masks, v_colors, v_coeffs, v_means, v_dirsum)
     GSB_DEG_SWITCH(degrees_to_use, CALL)
 #undef CALL
     return check_launch();

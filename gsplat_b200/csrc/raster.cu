@@ -208,6 +208,11 @@ struct Ring
     {
         return reinterpret_cast<uint64_t *>(base + (size_t)kStages * RecLayout<CDIM>::kStageBytes) + s;
     }
+    __device__ __forceinline__ int32_t *ids(int s) const
+    {
+        return reinterpret_cast<int32_t *>(base + (size_t)kStages * RecLayout<CDIM>::kStageBytes + kStages * sizeof(uint64_t))
+             + s * kBatch;
+    }
     // one thread: arm the barrier and launch the three bulk copies of records [first, first+count)
     __device__ __forceinline__ void issue(
         int stage, const float4 *gcull, const float4 *ggeom, const float4 *gcolor, int64_t first, int count
@@ -226,7 +231,8 @@ struct Ring
 template<int CDIM>
 constexpr size_t ring_smem_bytes()
 {
-    return (size_t)kStages * RecLayout<CDIM>::kStageBytes + kStages * sizeof(uint64_t);
+    // stages | full barriers | per-stage gaussian ids (backward only)
+    return (size_t)kStages * RecLayout<CDIM>::kStageBytes + kStages * sizeof(uint64_t) + (size_t)kStages * kBatch * sizeof(int32_t);
 }
 
 // Can the gaussian reach alpha >= 1/255 anywhere in the 8x4 pixel block centred at (cx, cy)?  Conservative:
@@ -430,7 +436,7 @@ struct GradDst
 };
 
 template<int CDIM, bool ABS>
-__global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
+__global__ void __launch_bounds__(kWarps * 32, (CDIM <= 4 ? 5 : 1)) raster_bwd_kernel(
     const uint32_t I, const int64_t n_isects, const float4 *__restrict__ gcull, const float4 *__restrict__ ggeom,
     const float4 *__restrict__ gcolor, const int32_t *__restrict__ order, const int32_t *__restrict__ flatten_ids,
     const float *__restrict__ backgrounds,
@@ -445,7 +451,6 @@ __global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Ring<CDIM> ring;
     ring.carve(smem_raw);
-    __shared__ int32_t s_ids[kStages][kBatch];
     __shared__ int32_t s_tile_bin;
 
     const TileGeom tg      = decode_tile(order, tw, th);
@@ -558,7 +563,7 @@ __global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
         const int count       = batch_count(b);
         // gaussian ids of this batch (coalesced; needed for the scatter)
         if((int)tid < count)
-            s_ids[stage][tid] = flatten_ids[first + tid];
+            ring.ids(stage)[tid] = flatten_ids[first + tid];
         __syncthreads();
         // the whole batch lies behind this warp's deepest contributor -> nothing to do for the warp
         if(first <= warp_bin_final)
@@ -568,7 +573,7 @@ __global__ void __launch_bounds__(kWarps * 32) raster_bwd_kernel(
             const float4 *saxis   = ring.axis(stage);
             const float4 *sgeom   = ring.geom(stage);
             const float4 *scol    = ring.color(stage);
-            const int32_t *sid    = s_ids[stage];
+            const int32_t *sid    = ring.ids(stage);
             const int lim         = bin_final - first;      // local index of this pixel's last contributor
             const int warp_lim    = warp_bin_final - first; // ... of the warp's
             for(int c1 = count; c1 > 0; c1 -= 32)

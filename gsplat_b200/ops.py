@@ -275,26 +275,30 @@ class _SphericalHarmonics(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_colors):
         means, viewmats, coeffs, m8 = ctx.saved_tensors
-        if ctx.needs_input_grad[2]:
-            raise NotImplementedError(
-                "spherical_harmonics: gradient w.r.t. viewmats (pose optimisation through the SH view "
-                "direction) is not built; reference: csrc/SphericalHarmonicsViewDirectionCUDA.cu"
-            )
         batch = tuple(means.shape[:-2])
         B, N, C = _prod(batch), means.shape[-2], viewmats.shape[-3]
         K, D = coeffs.shape[-2:]
         v_colors = v_colors.contiguous()
         v_coeffs = torch.empty_like(coeffs)
         v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
+        need_vm = ctx.needs_input_grad[2]
+        v_dirsum = torch.empty(batch + (C, 3), device=means.device, dtype=torch.float32) if need_vm else None
         with _Ctx(means.device) as st:
             check(
                 lib().gsb200_sh_bwd(
                     B, C, N, K, D, ctx.deg, ptr(means), ptr(viewmats), ptr(coeffs), ptr(m8), ptr(v_colors), ptr(v_coeffs),
-                    ptr(v_means), st,
+                    ptr(v_means), ptr(v_dirsum), st,
                 ),
                 "spherical_harmonics_bwd",
             )
-        return None, v_means, None, v_coeffs, None
+        v_viewmats = None
+        if need_vm:
+            # dir = mean + R^T t  =>  dL/dR[i][j] = t[i] S[j],  dL/dt[i] = sum_j R[i][j] S[j],  S = sum_n dL/ddir
+            R, t = viewmats[..., :3, :3], viewmats[..., :3, 3]
+            v_viewmats = torch.zeros_like(viewmats)
+            v_viewmats[..., :3, :3] = t[..., :, None] * v_dirsum[..., None, :]
+            v_viewmats[..., :3, 3] = torch.einsum("...ij,...j->...i", R, v_dirsum)
+        return None, v_means, v_viewmats, v_coeffs, None
 
 
 def spherical_harmonics(

@@ -86,11 +86,13 @@ extern "C"
         int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, int degrees_to_use, const float *means,
         const float *viewmats, const float *coeffs, const uint8_t *masks, float *colors, void *stream
     );
-    /* v_coeffs [N,K,D] fully written (zeros for unused bands / masked rows); v_means [B,N,3] or NULL. */
+    /* v_coeffs [N,K,D] fully written (zeros for unused bands / masked rows); v_means [B,N,3] or NULL;
+     * v_dirsum [B,C,3] or NULL: per-image sum of the view-direction gradient, from which the caller forms
+     * v_viewmats (dir = mean + R^T t; compute_v_viewmats of the reference schema). */
     int gsb200_sh_bwd(
         int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, int degrees_to_use, const float *means,
         const float *viewmats, const float *coeffs, const uint8_t *masks, const float *v_colors, float *v_coeffs,
-        float *v_means, void *stream
+        float *v_means, float *v_dirsum, void *stream
     );
 
     /* ---- fused projection + conic + SH->RGB : the orchestrator's default training path

@@ -165,6 +165,20 @@ def test_sh(gs, deg):
     _close(_n(v_cf), g[f"v_coeffs{deg}"], 1e-4, 1e-5, "v_coeffs vs reference golden")
     if deg > 0:
         _close(_n(v_m), g[f"v_means{deg}"], 1e-3, 1e-4 * np.abs(g[f"v_means{deg}"]).max(), "v_means vs reference golden")
+    if deg > 0:
+        # pose gradient through the view direction (dir = mean + R^T t): one camera at a time,
+        # dL/dR = t S^T, dL/dt = R S with S = sum_n dL/ddir_n = sum_n v_means_n
+        for c in range(vm.shape[0]):
+            vmc = vm[c : c + 1].clone().requires_grad_(True)
+            m1 = means.detach().clone().requires_grad_(True)
+            col_c = gs.spherical_harmonics(deg, m1, vmc, cf.detach())
+            g_vm, g_m = torch.autograd.grad((col_c * v_col[c : c + 1]).sum(), (vmc, m1))
+            S = g_m.sum(0)
+            R, t = vmc.detach()[0, :3, :3], vmc.detach()[0, :3, 3]
+            expect = torch.zeros(4, 4, device=DEV)
+            expect[:3, :3] = t[:, None] * S[None, :]
+            expect[:3, 3] = R @ S
+            torch.testing.assert_close(g_vm[0], expect, rtol=2e-3, atol=2e-4 * float(expect.abs().max()))
     # masks: masked rows are zero and get zero gradient
     mask = np.zeros(oc.shape[:-1], bool)
     mask[:, ::3] = True
