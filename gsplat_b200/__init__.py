@@ -6,6 +6,8 @@ rasterize_to_pixels, quat_scale_to_covar_preci.  Importing the package does not 
 operator does (and needs gsplat_b200/libgsplat_b200.so, built by ``python -m gsplat_b200.build``).
 """
 from .ops import (  # noqa: F401
+    compute_relocation,
+    mcmc_perturb_positions,
     fully_fused_projection,
     fused_project_sh,
     isect_offset_encode,
@@ -34,5 +36,7 @@ __all__ = [
     "isect_offset_encode",
     "rasterize_to_pixels",
     "quat_scale_to_covar_preci",
+    "compute_relocation",
+    "mcmc_perturb_positions",
     "has_3dgs",
 ]

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "gsb200_segsort_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "gsb200_segsort_keys": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "gsb200_isect_bucket_finalize": (c_int, [c_i64, c_u32, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gsb200_relocation": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_vp, c_vp, c_vp]),
+    "gsb200_mcmc_perturb_positions": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, c_vp]),
     "gsb200_raster_records_bytes": (c_sz, [c_i64, c_int, c_i64]),
     "gsb200_raster_fwd": (
         c_int,

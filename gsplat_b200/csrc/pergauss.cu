@@ -791,6 +791,62 @@ __global__ void __launch_bounds__(kThreads) isect_offsets_kernel(
         for(int64_t k = id + 1; k < total_tiles; ++k)
             offsets[k] = (int32_t)n_isects;
 }
+// ------------------------------------------------------------------ MCMC strategy ops ("next" row)
+// Relocation, Eq. 9 of "3D Gaussian Splatting as Markov Chain Monte Carlo" (reference:
+// csrc/RelocationCUDA.cu:36-80): new opacity 1 - (1 - o)^(1/n) clamped to [min_opacity, 1 - eps]; new scale
+// = o / sum_{i=1..n} sum_{k<i} C(i-1,k) (-1)^k / sqrt(k+1) o_new^(k+1) times the old scale.
+__global__ void __launch_bounds__(kThreads) relocation_kernel(
+    int64_t N, const float *__restrict__ opacities, const float *__restrict__ scales, const int32_t *__restrict__ ratios,
+    const float *__restrict__ binoms, int n_max, float min_opacity, float *__restrict__ new_opacities,
+    float *__restrict__ new_scales
+)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= N)
+        return;
+    const int n   = ratios[i];
+    const float o = opacities[i];
+    float o_new   = 1.0f - powf(1.0f - o, 1.0f / (float)n);
+    o_new         = fminf(fmaxf(o_new, min_opacity), 1.0f - 1.1920929e-07f);
+    new_opacities[i] = o_new;
+    float denom = 0.f;
+    for(int r = 1; r <= n; ++r)
+    {
+        float p = o_new; // o_new^(k+1)
+        float sign = 1.f;
+        for(int k = 0; k < r; ++k)
+        {
+            denom += binoms[(r - 1) * n_max + k] * (sign / sqrtf((float)(k + 1))) * p;
+            p *= o_new;
+            sign = -sign;
+        }
+    }
+    const float coeff = o / denom;
+#pragma unroll
+    for(int k = 0; k < 3; ++k)
+        new_scales[i * 3 + k] = coeff * scales[i * 3 + k];
+}
+
+// positions += Sigma * (noise * sigmoid(-k (sigmoid(opacity_logit) - t)) * noise_scale), in place
+// (reference: csrc/MCMCPerturbCUDA.cu:28-60).
+__global__ void __launch_bounds__(kThreads) mcmc_perturb_kernel(
+    int64_t N, float *__restrict__ positions, const float *__restrict__ quats, const float *__restrict__ scales_log,
+    const float *__restrict__ opacities_logit, const float *__restrict__ noise, float noise_scale, float t, float k
+)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= N)
+        return;
+    const float q[4] = {quats[i * 4], quats[i * 4 + 1], quats[i * 4 + 2], quats[i * 4 + 3]};
+    const float s[3] = {expf(scales_log[i * 3]), expf(scales_log[i * 3 + 1]), expf(scales_log[i * 3 + 2])};
+    const M3 cov     = quat_scale_to_sym<false>(q, s);
+    const float dens = 1.f / (1.f + expf(-opacities_logit[i]));
+    const float w    = (1.f / (1.f + expf(k * (dens - t)))) * noise_scale;
+    const float nz[3] = {noise[i * 3] * w, noise[i * 3 + 1] * w, noise[i * 3 + 2] * w};
+#pragma unroll
+    for(int r = 0; r < 3; ++r)
+        positions[i * 3 + r] += cov.m[r * 3 + 0] * nz[0] + cov.m[r * 3 + 1] * nz[1] + cov.m[r * 3 + 2] * nz[2];
+}
 } // namespace gsb
 
 // =====================================================================================================
@@ -1162,6 +1218,41 @@ extern "C" int gsb200_isect_bucket_finalize(
         return GSB200_E_INVALID;
     isect_bucket_finalize_kernel<<<grid_for(total_tiles * 32, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         total_tiles, n_tiles, bits_for_count(n_tiles), offsets, keys_sorted, isect_ids, flatten_ids
+    );
+    return check_launch();
+}
+
+// ---- MCMC strategy ops
+extern "C" int gsb200_relocation(
+    int64_t N, const float *opacities, const float *scales, const int32_t *ratios, const float *binoms, int n_max,
+    float min_opacity, float *new_opacities, float *new_scales, void *stream
+)
+{
+    if(N < 0 || n_max <= 0)
+        return GSB200_E_INVALID;
+    if(N == 0)
+        return GSB200_OK;
+    if(!opacities || !scales || !ratios || !binoms || !new_opacities || !new_scales)
+        return GSB200_E_INVALID;
+    relocation_kernel<<<grid_for(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        N, opacities, scales, ratios, binoms, n_max, min_opacity, new_opacities, new_scales
+    );
+    return check_launch();
+}
+
+extern "C" int gsb200_mcmc_perturb_positions(
+    int64_t N, float *positions, const float *quats, const float *scales_log, const float *opacities_logit,
+    const float *noise, float noise_scale, float t, float k, void *stream
+)
+{
+    if(N < 0)
+        return GSB200_E_INVALID;
+    if(N == 0)
+        return GSB200_OK;
+    if(!positions || !quats || !scales_log || !opacities_logit || !noise)
+        return GSB200_E_INVALID;
+    mcmc_perturb_kernel<<<grid_for(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        N, positions, quats, scales_log, opacities_logit, noise, noise_scale, t, k
     );
     return check_launch();
 }

@@ -726,3 +726,57 @@ def rasterize_to_pixels(
     if pad:
         render_colors = render_colors[..., :D]
     return render_colors, render_alphas
+
+
+# --------------------------------------------------------------------------------------------
+# MCMC strategy ops ("next" row)
+
+
+@torch.no_grad()
+def compute_relocation(
+    opacities: Tensor, scales: Tensor, ratios: Tensor, binoms: Tensor, min_opacity: float = 0.005
+) -> Tuple[Tensor, Tensor]:
+    """Eq. 9 of "3D Gaussian Splatting as Markov Chain Monte Carlo": opacities / scales of Gaussians that are
+    split into ``ratios`` copies.  Mirrors gsplat.relocation.compute_relocation
+    (/root/reference/gsplat/relocation.py:25-80): ``ratios`` is clamped to [1, n_max] in place."""
+    dev = require_cuda(opacities, scales, ratios, binoms)
+    N = opacities.shape[0]
+    n_max = binoms.shape[0]
+    assert scales.shape == (N, 3), scales.shape
+    assert ratios.shape == (N,), ratios.shape
+    opacities, scales, binoms = f32c(opacities, "opacities"), f32c(scales, "scales"), f32c(binoms, "binoms")
+    ratios.clamp_(min=1, max=n_max)
+    r32 = ratios.int().contiguous()
+    new_opacities, new_scales = torch.empty_like(opacities), torch.empty_like(scales)
+    with _Ctx(dev) as st:
+        check(
+            lib().gsb200_relocation(
+                N, ptr(opacities), ptr(scales), ptr(r32), ptr(binoms), n_max, float(min_opacity), ptr(new_opacities),
+                ptr(new_scales), st,
+            ),
+            "relocation",
+        )
+    return new_opacities, new_scales
+
+
+@torch.no_grad()
+def mcmc_perturb_positions(
+    positions: Tensor, quats: Tensor, scales_log: Tensor, opacities_logit: Tensor, noise: Tensor, noise_scale: float,
+    t: float = 0.005, k: float = 100.0,
+) -> None:
+    """In place: positions += Sigma(quats, exp(scales_log)) @ (noise * sigmoid(-k (sigmoid(opacities_logit) - t))
+    * noise_scale)   (/root/reference/gsplat/cuda/csrc/MCMCPerturbCUDA.cu:28-60)."""
+    dev = require_cuda(positions, quats, scales_log, opacities_logit, noise)
+    if not positions.is_contiguous() or positions.dtype != torch.float32:
+        raise ValueError("positions must be a contiguous float32 tensor (updated in place)")
+    N = positions.shape[0]
+    quats, scales_log = f32c(quats, "quats"), f32c(scales_log, "scales")
+    opacities_logit, noise = f32c(opacities_logit, "opacities"), f32c(noise, "noise")
+    with _Ctx(dev) as st:
+        check(
+            lib().gsb200_mcmc_perturb_positions(
+                N, ptr(positions), ptr(quats), ptr(scales_log), ptr(opacities_logit), ptr(noise), float(noise_scale),
+                float(t), float(k), st,
+            ),
+            "mcmc_perturb_positions",
+        )

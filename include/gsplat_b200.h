@@ -205,6 +205,18 @@ extern "C"
         void *stream
     );
 
+    /* ---- MCMC strategy ops ("next" row): relocation (ext.cpp `relocation`, gsplat/relocation.py:64,
+     * csrc/RelocationCUDA.cu:36-80) and in-place position perturbation (csrc/MCMCPerturbCUDA.cu:28-60,
+     * gsplat/strategy/ops.py).  ratios int32 [N] already clamped to [1, n_max]; binoms [n_max, n_max]. */
+    int gsb200_relocation(
+        int64_t N, const float *opacities, const float *scales, const int32_t *ratios, const float *binoms, int n_max,
+        float min_opacity, float *new_opacities, float *new_scales, void *stream
+    );
+    int gsb200_mcmc_perturb_positions(
+        int64_t N, float *positions, const float *quats, const float *scales_log, const float *opacities_logit,
+        const float *noise, float noise_scale, float t, float k, void *stream
+    );
+
 #ifdef __cplusplus
 }
 #endif

@@ -367,3 +367,37 @@ def rasterization_fwd_bwd(
         v_opacities=g["v_opacities"].sum(0).astype(dt), v_sh=v_coeffs, raster=g,
     )
     return fwd, grads
+
+
+# --------------------------------------------------------------------------
+# MCMC strategy ops ("next" row): plain numpy restatements
+def compute_relocation(opacities, scales, ratios, binoms, min_opacity=0.005):
+    """Eq. 9 of the 3DGS-MCMC paper.  Reference: csrc/RelocationCUDA.cu:36-80 (kernel) and the reference's own
+    Python restatement tests/test_relocation.py:42-76.  ratios already clamped to [1, n_max]."""
+    dt = opacities.dtype
+    eps = np.finfo(dt).eps
+    N = opacities.shape[0]
+    new_o = np.empty_like(opacities)
+    new_s = np.empty_like(scales)
+    for i in range(N):
+        n = int(ratios[i])
+        o = dt.type(1.0) - (dt.type(1.0) - opacities[i]) ** dt.type(1.0 / n)
+        o = min(max(o, dt.type(min_opacity)), dt.type(1.0 - eps))
+        new_o[i] = o
+        denom = 0.0
+        for r in range(1, n + 1):
+            for k in range(r):
+                denom += float(binoms[r - 1, k]) * ((-1.0) ** k) * (float(o) ** (k + 1)) / math.sqrt(k + 1)
+        new_s[i] = scales[i] * dt.type(float(opacities[i]) / denom)
+    return new_o, new_s
+
+
+def mcmc_perturb_positions(positions, quats, scales_log, opacities_logit, noise, noise_scale, t=0.005, k=100.0):
+    """positions + Sigma @ (noise * sigmoid(-k (sigmoid(o) - t)) * noise_scale).  Reference:
+    csrc/MCMCPerturbCUDA.cu:28-60; PyTorch fallback gsplat/strategy/ops.py:494-512."""
+    dt = positions.dtype
+    cov, _ = quat_scale_to_covar_preci(quats.astype(dt), np.exp(scales_log.astype(dt)), True, False, False)
+    dens = 1.0 / (1.0 + np.exp(-opacities_logit.astype(dt)))
+    w = (1.0 / (1.0 + np.exp(k * (dens - t)))) * noise_scale
+    nz = noise.astype(dt) * w[:, None]
+    return positions + np.einsum("nij,nj->ni", cov, nz)

@@ -284,6 +284,46 @@ def make_accumulate(rng):
     )
 
 
+# ---------------------------------------------------------------- MCMC strategy ops ("next" row)
+def make_mcmc(rng):
+    """relocation: the reference's own Python restatement in its test-suite
+    (/root/reference/tests/test_relocation.py:42-76 _reference_relocation, loaded by path);
+    perturbation: the reference's PyTorch fallback (gsplat/strategy/ops.py:494-512) with an explicit noise."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_test_relocation", "/root/reference/tests/test_relocation.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    N, n_max = 257, 51
+    op = (rng.random(N) * 0.98 + 0.01).astype(np.float32)
+    op[:8] = [1e-4, 0.9999, 0.5, 0.003, 0.999999, 0.25, 0.75, 0.01]
+    sc = (rng.random((N, 3)) * 0.5 + 0.01).astype(np.float32)
+    ratios = rng.randint(1, n_max + 1, N).astype(np.int32)
+    ratios[:4] = [1, n_max, 2, 3]
+    binoms = mod._binomial_table(n_max, torch.device("cpu"))
+    out = {}
+    for tag, mo in (("", 0.005), ("_mo0", 0.0)):
+        no, ns = mod._reference_relocation(
+            torch.tensor(op, dtype=f64), torch.tensor(sc, dtype=f64), torch.tensor(ratios), binoms.to(f64), mo
+        )
+        out["new_opacities" + tag], out["new_scales" + tag] = no, ns
+    # perturbation
+    M = 300
+    pos = rng.standard_normal((M, 3)).astype(np.float32)
+    quats = rng.standard_normal((M, 4)).astype(np.float32)
+    slog = (rng.standard_normal((M, 3)) * 0.5 - 3).astype(np.float32)
+    ologit = (rng.standard_normal(M) * 3).astype(np.float32)
+    noise = rng.standard_normal((M, 3)).astype(np.float32)
+    noise_scale, t, k = 5e5 * 1.6e-4, 0.005, 100.0
+    covars, _ = _quat_scale_to_covar_preci(torch.tensor(quats, dtype=f64), torch.exp(torch.tensor(slog, dtype=f64)), True, False, triu=False)
+    opac = torch.sigmoid(torch.tensor(ologit, dtype=f64))
+    nz = torch.tensor(noise, dtype=f64) * torch.sigmoid(-k * (opac - t)).unsqueeze(-1) * noise_scale
+    new_pos = torch.tensor(pos, dtype=f64) + torch.einsum("bij,bj->bi", covars, nz)
+    save("ref_mcmc.npz", opacities=op, scales=sc, ratios=ratios, binoms=binoms, n_max=np.int64(n_max), positions=pos,
+         quats=quats, scales_log=slog, opacities_logit=ologit, noise=noise, noise_scale=np.float64(noise_scale),
+         t=np.float64(t), k=np.float64(k), new_positions=new_pos, **out)
+
+
 if __name__ == "__main__":
     rng = np.random.RandomState(20260922)
     means_all, viewmats, Ks, W, H = make_garden()
@@ -292,3 +332,4 @@ if __name__ == "__main__":
     make_sh(rng, viewmats)
     make_isect(rng)
     make_accumulate(rng)
+    make_mcmc(np.random.RandomState(7))

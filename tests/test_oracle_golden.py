@@ -261,3 +261,16 @@ def test_full_pipeline_small_runs_and_is_consistent():
     same_list = np.array_equal(f32["flatten_ids"], f64["flatten_ids"])
     if same_list:
         _close(f32["render_colors"][ok], f64["render_colors"][ok], 1e-3, 1e-4, "pipeline colors")
+
+
+# ---- MCMC strategy ops vs the reference's own Python restatements
+def test_mcmc_ops(golden_dir):
+    g = _load(golden_dir, "ref_mcmc.npz")
+    f8 = lambda k: g[k].astype(np.float64)  # noqa: E731
+    for tag, mo in (("", 0.005), ("_mo0", 0.0)):
+        no, ns = gso.compute_relocation(f8("opacities"), f8("scales"), g["ratios"], f8("binoms"), mo)
+        _close(no, g["new_opacities" + tag], 1e-12, 1e-14, "new_opacities")
+        _close(ns, g["new_scales" + tag], 1e-9, 1e-12, "new_scales")
+    newp = gso.mcmc_perturb_positions(f8("positions"), f8("quats"), f8("scales_log"), f8("opacities_logit"), f8("noise"),
+                                      float(g["noise_scale"]), float(g["t"]), float(g["k"]))
+    _close(newp, g["new_positions"], 1e-10, 1e-10, "new_positions")
