@@ -235,6 +235,7 @@ def main():
     import torch.distributed as dist
 
     import gsplat_b200
+    from gsplat_b200 import distributed as D
     from gsplat_b200 import ops
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists)"
@@ -260,7 +261,6 @@ def main():
     h2d_bytes = vm_host.numel() * 4 + K_host.numel() * 4 + target_host.numel() * 4
     d2h_bytes = 4
     grad_names = ("means", "quats", "scales", "opacities", "sh")
-    flat_grads = torch.zeros(N * 59, device=dev) if world > 1 else None
 
     # e2e input pipeline: every step's camera + target image are copied from pinned host memory inside
     # the timed region, double-buffered on a side stream so that the copy of step i+1 overlaps the compute
@@ -293,13 +293,9 @@ def main():
         loss = (rc - tgt).abs().mean()
         loss.backward()
         if world > 1:
-            # one bucketed all-reduce of the 59 floats / Gaussian
-            o = 0
-            for k in grad_names:
-                g = params[k].grad.reshape(-1)
-                flat_grads[o : o + g.numel()].copy_(g)
-                o += g.numel()
-            dist.all_reduce(flat_grads)
+            # the 59 floats / Gaussian in ONE coalesced NCCL launch, reduced in place in
+            # the gradient tensors (no staging copy)
+            D.all_reduce_gaussian_grads([params[k] for k in grad_names], coalesced=True)
         if e2e:
             consumed[slot].record()
             loss_host.copy_(loss.detach(), non_blocking=True)

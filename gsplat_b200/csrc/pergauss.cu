@@ -666,8 +666,8 @@ __global__ void __launch_bounds__(kThreads) isect_count_kernel(
 __global__ void __launch_bounds__(kThreads) isect_emit_kernel(
     int64_t total, int64_t N, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
     const float *__restrict__ depths, const float *__restrict__ conics, const float *__restrict__ opacities,
-    const int64_t *__restrict__ cum_tiles, uint32_t tile_size, uint32_t tw, uint32_t th, uint32_t tile_n_bits,
-    int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids
+    const int64_t *__restrict__ cum_tiles, const int64_t *__restrict__ image_ids, uint32_t tile_size, uint32_t tw,
+    uint32_t th, uint32_t tile_n_bits, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids
 )
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(kThreads) isect_emit_kernel(
     if(accu)
         cn[0] = conics[i * 3], cn[1] = conics[i * 3 + 1], cn[2] = conics[i * 3 + 2], op = opacities[i];
     int64_t cur         = (i == 0) ? 0 : cum_tiles[i - 1];
-    const int64_t hi    = (i / N) << (32 + tile_n_bits);
+    const int64_t hi    = (image_ids ? image_ids[i] : (i / N)) << (32 + tile_n_bits); // packed rows carry their image id
     const int64_t dbits = (int64_t)__float_as_uint(depths[i]);
     tiles_of_gaussian(m.x, m.y, r.x, r.y, accu ? cn : nullptr, accu ? &op : nullptr, tile_size, tw, th, [&](int64_t tile) {
         isect_ids[cur]   = hi | (tile << 32) | dbits;
@@ -1091,13 +1091,14 @@ extern "C" int gsb200_isect_count(
 
 extern "C" int gsb200_isect_emit(
     int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *depths, const float *conics,
-    const float *opacities, const int64_t *cum_tiles, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
-    int64_t *isect_ids, int32_t *flatten_ids, void *stream
+    const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids, uint32_t tile_size,
+    uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids, int32_t *flatten_ids, void *stream
 )
 {
     if(I < 0 || N < 0 || tile_size == 0)
         return GSB200_E_INVALID;
-    const int64_t total = I * N;
+    // packed layout: N rows in total (image_ids given), I only sizes the key; dense: I * N rows
+    const int64_t total = image_ids ? N : I * N;
     if(total == 0)
         return GSB200_OK;
     if(!means2d || !radii || !depths || !cum_tiles || !isect_ids || !flatten_ids)
@@ -1106,8 +1107,8 @@ extern "C" int gsb200_isect_emit(
     if(bits_for_count(I) + tile_bits > 32)
         return GSB200_E_KEYBITS;
     isect_emit_kernel<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        total, N, means2d, radii, depths, conics, opacities, cum_tiles, tile_size, tile_width, tile_height, tile_bits,
-        isect_ids, flatten_ids
+        total, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, tile_size, tile_width, tile_height,
+        tile_bits, isect_ids, flatten_ids
     );
     return check_launch();
 }

@@ -60,11 +60,36 @@ class GradBucket:
 
 def all_reduce_gaussian_grads(
     params: Sequence[Tensor], bucket: Optional[GradBucket] = None, average: bool = False, group=None,
-    async_op: bool = False,
+    async_op: bool = False, coalesced: bool = False,
 ):
     """Sum (or average) the ``.grad`` of the replicated Gaussian parameters over all ranks with one
     all-reduce.  Returns the bucket (and the work handle when ``async_op``); call ``bucket.unpack()``
-    after ``work.wait()`` in the async case."""
+    after ``work.wait()`` in the async case.
+
+    ``coalesced=True``: no staging buffer -- the gradient tensors themselves are reduced in place inside
+    one coalesced launch (``torch.distributed._coalescing_manager``: a single NCCL group call on NVLink);
+    parameters without a gradient get a zero gradient first so that every rank issues the same calls."""
+    if coalesced:
+        grads = []
+        for p in params:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            elif not p.grad.is_contiguous():
+                p.grad = p.grad.contiguous()
+            grads.append(p.grad)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            if str(dist.get_backend(group)).lower() == "nccl":
+                with dist._coalescing_manager(group=group, device=grads[0].device, async_ops=False):
+                    for g in grads:
+                        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+            else:  # gloo (CPU tests) has no coalescing: same calls, one by one
+                for g in grads:
+                    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                inv = 1.0 / dist.get_world_size(group)
+                for g in grads:
+                    g.mul_(inv)
+        return None
     if bucket is None:
         bucket = GradBucket(params)
     flat = bucket.pack()

@@ -232,18 +232,38 @@ def fully_fused_projection(
     """Projects Gaussians to 2D (EWA).  Returns (radii int32 [..., C, N, 2], means2d [..., C, N, 2],
     depths [..., C, N], conics [..., C, N, 3], compensations [..., C, N] | None).  ``radii == 0`` marks
     culled entries; their float outputs are zero."""
-    if packed:
-        raise NotImplementedError("fully_fused_projection(packed=True) is a 'next' row (SURVEY.md section 8f.1)")
     if sparse_grad:
-        raise AssertionError("sparse_grad is only supported when packed is True")
+        if not packed:
+            raise AssertionError("sparse_grad is only supported when packed is True")
+        raise NotImplementedError("sparse_grad (COO gradients) is a 'next' row (SURVEY.md section 8f.1)")
     if covars is None and (quats is None or scales is None):
         raise ValueError("either covars or (quats, scales) must be given")
     if covars is not None:
         quats = scales = None
     cam = _camera_model_id(camera_model)
-    return _FullyFusedProjection.apply(
+    out = _FullyFusedProjection.apply(
         means, covars, quats, scales, opacities, viewmats, Ks, int(width), int(height), float(eps2d), float(near_plane),
         float(far_plane), float(radius_clip), bool(calc_compensations), cam,
+    )
+    if not packed:
+        return out
+    # packed=True: the reference's COO layout (batch_ids, camera_ids, gaussian_ids, indptr, radii, means2d,
+    # depths, conics, compensations), rows in ascending (b, c, n) order.  The compacting two-pass kernel
+    # (csrc/ProjectionEWA3DGSPacked.cu) is a "next" row; here the dense kernel runs and the visible rows are
+    # gathered, which gives the same values, gradients and ordering (not the memory saving).
+    radii, means2d, depths, conics, comps = out
+    C, N = viewmats.shape[-3], means.shape[-2]
+    sel = (radii > 0).all(dim=-1).reshape(-1)
+    rows = torch.nonzero(sel, as_tuple=False).squeeze(-1)
+    gaussian_ids = (rows % N).to(torch.int32)
+    camera_ids = ((rows // N) % C).to(torch.int32)
+    batch_ids = (rows // (N * C)).to(torch.int32)
+    per_image = sel.reshape(-1, N).sum(dim=1)
+    indptr = torch.zeros(per_image.numel() + 1, device=sel.device, dtype=torch.int32)
+    indptr[1:] = torch.cumsum(per_image, 0).to(torch.int32)
+    return (
+        batch_ids, camera_ids, gaussian_ids, indptr, radii.reshape(-1, 2)[rows], means2d.reshape(-1, 2)[rows],
+        depths.reshape(-1)[rows], conics.reshape(-1, 3)[rows], None if comps is None else comps.reshape(-1)[rows],
     )
 
 
@@ -314,10 +334,26 @@ def spherical_harmonics(
 ) -> Tensor:
     """Evaluates SH colours for view directions ``mean - camera_position`` (camera position recovered as
     ``-R^T t``).  Returns [..., C, N, D]; masked-off rows are 0."""
-    if batch_ids is not None or camera_ids is not None or gaussian_ids is not None:
-        raise NotImplementedError("packed spherical_harmonics is a 'next' row (SURVEY.md section 8f.1)")
     if viewmats_rs is not None:
         raise NotImplementedError("rolling-shutter view matrices are out of scope")
+    if batch_ids is not None or camera_ids is not None or gaussian_ids is not None:
+        # packed mode: coeffs [nnz, K, D] pre-gathered, one (batch, camera, gaussian) triple per row.  The view
+        # direction mean + R^T t is formed per row (torch, differentiable) and evaluated by the dense kernel
+        # with an identity view matrix, one "gaussian" per row.
+        if batch_ids is None or camera_ids is None or gaussian_ids is None:
+            raise ValueError("batch_ids, camera_ids and gaussian_ids must be given together")
+        nb = means.dim() - 2
+        N, C = means.shape[-2], viewmats.shape[-3]
+        m = means.reshape(-1, N, 3)[batch_ids.long(), gaussian_ids.long()]  # [nnz, 3]
+        vm = viewmats.reshape(-1, C, 4, 4)[batch_ids.long(), camera_ids.long()]  # [nnz, 4, 4]
+        dirs = m + torch.einsum("nij,ni->nj", vm[:, :3, :3], vm[:, :3, 3])
+        if coeffs.dim() != 3 or coeffs.shape[0] != dirs.shape[0]:
+            raise ValueError(f"packed coeffs must be [nnz, K, D]; got {tuple(coeffs.shape)} for nnz={dirs.shape[0]}")
+        if not (0 <= degrees_to_use <= 4) or (degrees_to_use + 1) ** 2 > coeffs.shape[-2]:
+            raise ValueError(f"degrees_to_use={degrees_to_use} needs K >= {(degrees_to_use + 1) ** 2}")
+        eye = torch.eye(4, device=dirs.device, dtype=dirs.dtype)[None]
+        out = _SphericalHarmonics.apply(int(degrees_to_use), dirs, eye, coeffs, None if masks is None else masks[None])
+        return out[0]
     if coeffs.dim() != 3 or coeffs.shape[0] != means.shape[-2]:
         raise ValueError(f"coeffs must be [N, K, D]; got {tuple(coeffs.shape)} for N={means.shape[-2]}")
     if not (0 <= degrees_to_use <= 4) or (degrees_to_use + 1) ** 2 > coeffs.shape[-2]:
@@ -448,16 +484,26 @@ def isect_tiles(
     """Maps projected Gaussians to the tiles they touch.  With ``conics`` and ``opacities`` the
     conservative ellipse test (AccuTile / SNUGBOX) is used, otherwise the radius AABB.
     Returns (tiles_per_gauss int32 [..., N], isect_ids int64 [n_isects], flatten_ids int32 [n_isects])."""
-    if packed:
-        raise NotImplementedError("isect_tiles(packed=True) is a 'next' row (SURVEY.md section 8f.1)")
     dev = require_cuda(means2d, radii, depths)
     means2d, depths = f32c(means2d, "means2d"), f32c(depths, "depths")
     conics, opacities = f32c(conics, "conics"), f32c(opacities, "opacities")
     if radii.dtype != torch.int32:
         raise TypeError("radii must be int32")
     radii = radii.contiguous()
-    image_dims = tuple(means2d.shape[:-2])
-    I, N = _prod(image_dims), means2d.shape[-2]
+    if packed:
+        if n_images is None or image_ids is None:
+            raise ValueError("n_images and image_ids are required when means2d is packed ([nnz, 2]).")
+        if segmented:
+            raise ValueError("segmented sort is not supported for packed inputs")
+        if means2d.dim() != 2:
+            raise ValueError(f"packed means2d must be [nnz, 2], got {tuple(means2d.shape)}")
+        image_dims, I, N = (), int(n_images), means2d.shape[0]
+        img_ids = image_ids.to(torch.int64).contiguous()
+        I_count = 1  # pass 1 sees one flat list of nnz rows
+    else:
+        image_dims = tuple(means2d.shape[:-2])
+        I, N = _prod(image_dims), means2d.shape[-2]
+        img_ids, I_count = None, I
     L = lib()
     n_tiles = tile_width * tile_height
     image_bits, tile_bits = _cabi.bits_for_count(I), _cabi.bits_for_count(n_tiles)
@@ -466,7 +512,7 @@ def isect_tiles(
             f"intersect_tile: (image, tile) id packing needs {image_bits + tile_bits} bits but only 32 are "
             f"available (I={I}, n_tiles={n_tiles})."
         )
-    total = I * N
+    total = I_count * N
     tiles_per_gauss = torch.empty(image_dims + (N,), device=dev, dtype=torch.int32)
     if total == 0:
         return (tiles_per_gauss, torch.empty(0, device=dev, dtype=torch.int64), torch.empty(0, device=dev, dtype=torch.int32))
@@ -476,7 +522,7 @@ def isect_tiles(
         ws = _scratch_buffer(dev, "scan", L.gsb200_isect_scan_workspace_bytes(total))
         check(
             L.gsb200_isect_count(
-                I, N, ptr(means2d), ptr(radii), ptr(conics) if accu else None, ptr(opacities) if accu else None,
+                I_count, N, ptr(means2d), ptr(radii), ptr(conics) if accu else None, ptr(opacities) if accu else None,
                 tile_size, tile_width, tile_height, ptr(tiles_per_gauss), ptr(cum), ptr(ws), ws.numel(), st,
             ),
             "intersect_tile (count)",
@@ -489,8 +535,8 @@ def isect_tiles(
         check(
             L.gsb200_isect_emit(
                 I, N, ptr(means2d), ptr(radii), ptr(depths), ptr(conics) if accu else None,
-                ptr(opacities) if accu else None, ptr(cum), tile_size, tile_width, tile_height, ptr(isect_ids),
-                ptr(flatten_ids), st,
+                ptr(opacities) if accu else None, ptr(cum), ptr(img_ids), tile_size, tile_width, tile_height,
+                ptr(isect_ids), ptr(flatten_ids), st,
             ),
             "intersect_tile (emit)",
         )

@@ -128,11 +128,13 @@ extern "C"
         const float *opacities, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
         int32_t *tiles_per_gauss, int64_t *cum_tiles, void *workspace, size_t workspace_bytes, void *stream
     );
-    /* Pass 2: unsorted isect_ids int64 [n_isects], flatten_ids int32 [n_isects]. */
+    /* Pass 2: unsorted isect_ids int64 [n_isects], flatten_ids int32 [n_isects].
+     * Packed layout (reference packed=True): pass image_ids int64 [N] (the image of each of the N rows);
+     * pass 1 is then called with I = 1. */
     int gsb200_isect_emit(
         int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *depths, const float *conics,
-        const float *opacities, const int64_t *cum_tiles, uint32_t tile_size, uint32_t tile_width,
-        uint32_t tile_height, int64_t *isect_ids, int32_t *flatten_ids, void *stream
+        const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids, uint32_t tile_size,
+        uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids, int32_t *flatten_ids, void *stream
     );
     /* Stable radix sort of (isect_ids, flatten_ids) on key bits [0, end_bit)
      * (cub::DeviceRadixSort::SortPairs, csrc/IntersectTile.cu:1078-1121). */

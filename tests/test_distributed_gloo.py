@@ -47,6 +47,11 @@ def _worker(rank, world, port, out):
     work.wait()
     bucket.unpack(bucket._scale)
     assert torch.allclose(r[0].grad, torch.full((4,), 3.0))
+    # coalesced in-place variant (gloo runs the calls one by one; NCCL fuses them into one launch)
+    c = [torch.ones(5, requires_grad=True), torch.ones(2, 3, requires_grad=True)]
+    (c[0] * float(rank + 1)).sum().backward()  # c[1] has no gradient on any rank
+    D.all_reduce_gaussian_grads(c, coalesced=True)
+    assert torch.allclose(c[0].grad, torch.full((5,), 3.0)) and torch.equal(c[1].grad, torch.zeros(2, 3))
     dist.barrier()
     dist.destroy_process_group()
     out.put(rank)

@@ -549,3 +549,50 @@ def test_mcmc_ops(gs):
     gs.mcmc_perturb_positions(pos, _t(g["quats"]), _t(g["scales_log"]), _t(g["opacities_logit"]), _t(g["noise"]),
                               float(g["noise_scale"]), float(g["t"]), float(g["k"]))
     _close(_n(pos), g["new_positions"], 1e-4, 1e-5, "perturbed positions")
+
+
+def test_packed_operator_variants(gs):
+    """packed=True forms of the per-op surface (COO rows) against the dense ops."""
+    sc = scene.make_scene(n_max=30000, sh_degree=2)
+    W, H, C = 320, 180, 2
+    Ks = scene.rescale_K(sc["Ks"], sc["width"], sc["height"], W, H)[:C]
+    means, quats, scales, opac = (_t(sc[k], True) for k in ("means", "quats", "scales", "opacities"))
+    vm, K = _t(sc["viewmats"][:C]), _t(Ks)
+    radii, m2, dep, con, _ = gs.fully_fused_projection(means, None, quats, scales, vm, K, W, H, opacities=opac)
+    b_ids, c_ids, g_ids, indptr, p_radii, p_m2, p_dep, p_con, p_comp = gs.fully_fused_projection(
+        means, None, quats, scales, vm, K, W, H, opacities=opac, packed=True
+    )
+    sel = (radii > 0).all(-1)
+    nnz = int(sel.sum())
+    assert p_m2.shape == (nnz, 2) and p_comp is None and indptr.tolist() == [0, int(sel[0].sum()), nnz]
+    assert torch.equal(p_m2, m2[sel]) and torch.equal(p_con, con[sel]) and torch.equal(p_radii, radii[sel])
+    assert torch.equal(g_ids.long(), torch.nonzero(sel)[:, 1]) and torch.equal(c_ids.long(), torch.nonzero(sel)[:, 0])
+    g1 = torch.autograd.grad(p_m2.sum() + p_con.sum(), means, retain_graph=True)[0]
+    g2 = torch.autograd.grad(m2[sel].sum() + con[sel].sum(), means)[0]
+    assert torch.equal(g1, g2)
+    # isect on packed rows == isect on the dense layout (same keys; flatten ids index the packed rows)
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    op_cn = opac.detach()[None].expand(C, -1).contiguous()
+    d_tpg, d_ids, d_fl = gs.isect_tiles(m2, radii, dep, 16, tw, th, conics=con, opacities=op_cn)
+    image_ids = c_ids.long()
+    p_tpg, p_ids, p_fl = gs.isect_tiles(
+        p_m2.detach(), p_radii, p_dep.detach(), 16, tw, th, packed=True, n_images=C, image_ids=image_ids, gaussian_ids=g_ids,
+        conics=p_con.detach(), opacities=op_cn[sel],
+    )
+    assert torch.equal(p_ids, d_ids)
+    rows = torch.nonzero(sel.reshape(-1)).squeeze(-1)
+    assert torch.equal(rows[p_fl.long()], d_fl.long())
+    assert torch.equal(p_tpg, d_tpg[sel])
+    # packed SH == dense SH on the visible rows
+    sh = _t(np.ascontiguousarray(sc["sh"][:, :9]), True)
+    dense = gs.spherical_harmonics(2, means, vm, sh, masks=sel)
+    packed = gs.spherical_harmonics(2, means, vm, sh[g_ids.long()], batch_ids=b_ids, camera_ids=c_ids, gaussian_ids=g_ids)
+    torch.testing.assert_close(packed, dense[sel], rtol=1e-5, atol=1e-6)
+    # and the packed rows render the same image through rasterize_to_pixels(packed=True)
+    off = gs.isect_offset_encode(p_ids, C, tw, th)
+    col = torch.clamp_min(packed + 0.5, 0.0)
+    rc_p, ra_p = gs.rasterize_to_pixels(p_m2, p_con, col, op_cn[sel], W, H, 16, off, p_fl, packed=True)
+    dcol = torch.clamp_min(dense + 0.5, 0.0) * sel[..., None]
+    rc_d, ra_d = gs.rasterize_to_pixels(m2, con, dcol, op_cn, W, H, 16, gs.isect_offset_encode(d_ids, C, tw, th), d_fl)
+    torch.testing.assert_close(rc_p, rc_d, rtol=1e-5, atol=1e-6)
+    assert torch.equal(ra_p, ra_d)
