@@ -11,6 +11,7 @@ Launch: one process per GPU (torchrun / ``cli`` below, the reference's spawner r
 """
 from __future__ import annotations
 
+import math
 import os
 from typing import Callable, Dict, Iterable, List, Optional, Sequence
 
@@ -119,6 +120,115 @@ def render_views_dp(
         viewmats.index_select(0, idx), Ks.index_select(0, idx), width, height, **kwargs,
     )
     return rc, ra, meta, ids
+
+
+# ------------------------------------------------------------------------------------------------
+# Reference-semantics ``distributed=True`` (gaussian-sharded rendering): every rank owns a shard of the
+# Gaussians and a set of cameras.  Seam A: cameras are all-gathered so that each rank projects ITS Gaussians
+# onto ALL cameras; Seam B: the projected Gaussians are exchanged all-to-all so that each rank ends up with
+# ALL Gaussians projected onto ITS cameras, and composites those.  Both seams are differentiable (the
+# backward of an all-gather is a reduce-scatter-like gather of gradients, of an all-to-all the reverse
+# all-to-all).  Reference: /root/reference/gsplat/cuda/csrc/DistributedCollectives.cpp:299-453,
+# csrc/Rendering.cpp:852-874,1217-1262; Python helpers /root/reference/gsplat/distributed.py:25-272.
+
+
+def all_gather_ints(value: int, device, group=None) -> List[int]:
+    """One integer from every rank (non-differentiable bookkeeping: counts of gaussians / cameras)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return [int(value)]
+    mine = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    out = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return [int(t.item()) for t in out]
+
+
+def all_gather_rows(tensors: Sequence[Tensor], counts: Sequence[int], group=None) -> List[Tensor]:
+    """Differentiable all-gather of several row-aligned tensors [n_r, ...] (n_r = counts[rank]) in ONE
+    collective: columns are concatenated, rows padded to max(counts), gathered, trimmed.  Returns the
+    tensors with sum(counts) rows, rank-major."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return list(tensors)
+    import torch.distributed.nn.functional as distF
+
+    n = tensors[0].shape[0]
+    widths = [t[0].numel() if n else int(t.numel() // max(n, 1)) for t in tensors]
+    flat = torch.cat([t.reshape(n, -1) for t in tensors], dim=-1)
+    cap = max(counts)
+    if n < cap:
+        flat = torch.cat([flat, flat.new_zeros((cap - n, flat.shape[1]))], dim=0)
+    if flat.requires_grad:
+        parts = distF.all_gather(flat, group=group)
+    else:
+        parts = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(parts, flat.contiguous(), group=group)
+    full = torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+    outs = []
+    for chunk, t in zip(torch.split(full, widths, dim=-1), tensors):
+        outs.append(chunk.reshape((-1,) + tuple(t.shape[1:])))
+    return outs
+
+
+def all_to_all_rows(
+    tensors: Sequence[Tensor], send_counts: Sequence[int], recv_counts: Sequence[int], group=None
+) -> List[Tensor]:
+    """Differentiable all-to-all of several row-aligned tensors in ONE collective: rows
+    [sum(send_counts[:j]), +send_counts[j]) go to rank j; returns tensors with sum(recv_counts) rows,
+    source-rank-major.  Integer tensors are exchanged exactly (no gradient)."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return list(tensors)
+    import torch.distributed.nn.functional as distF
+
+    n = tensors[0].shape[0]
+    assert sum(send_counts) == n, (send_counts, n)
+    outs: List[Optional[Tensor]] = [None] * len(tensors)
+    for is_float in (True, False):
+        idx = [i for i, t in enumerate(tensors) if t.is_floating_point() == is_float]
+        if not idx:
+            continue
+        group_t = [tensors[i] for i in idx]
+        widths = [int(t.numel() // max(n, 1)) if n else int(math.prod(t.shape[1:])) for t in group_t]
+        flat = torch.cat([t.reshape(n, -1) for t in group_t], dim=-1).contiguous()
+        send = list(flat.split(list(send_counts), dim=0))
+        uneven_ok = str(dist.get_backend(group)).lower() == "nccl"
+        if not uneven_ok:
+            # gloo (CPU tests) only exchanges equally sized chunks: pad every chunk to the global maximum
+            cap_t = torch.tensor([max(list(send_counts) + list(recv_counts))], dtype=torch.int64, device=flat.device)
+            dist.all_reduce(cap_t, op=dist.ReduceOp.MAX, group=group)
+            cap = int(cap_t.item())
+            send = [torch.cat([x, x.new_zeros((cap - x.shape[0], x.shape[1]))], dim=0) if x.shape[0] < cap else x for x in send]
+            recv = [flat.new_empty((cap, flat.shape[1])) for _ in recv_counts]
+        else:
+            recv = [flat.new_empty((c, flat.shape[1])) for c in recv_counts]
+        if is_float and flat.requires_grad:
+            recv = list(distF.all_to_all(recv, send, group=group))
+        elif uneven_ok:
+            dist.all_to_all(recv, [x.contiguous() for x in send], group=group)
+        else:
+            # gloo has no all_to_all: everyone gathers everyone's padded chunks and keeps its own column
+            stacked = torch.stack(send, dim=0).contiguous()  # [world, cap, w]
+            gathered = [torch.empty_like(stacked) for _ in range(world)]
+            dist.all_gather(gathered, stacked, group=group)
+            me = dist.get_rank(group)
+            recv = [g[me] for g in gathered]
+        if not uneven_ok:
+            recv = [r[:c] for r, c in zip(recv, recv_counts)]
+        full = torch.cat(recv, dim=0)
+        for i, chunk, t in zip(idx, torch.split(full, widths, dim=-1), group_t):
+            outs[i] = chunk.reshape((-1,) + tuple(t.shape[1:]))
+    return outs  # type: ignore[return-value]
+
+
+def camera_major_to_local(t: Tensor, C_local: int, N_world: Sequence[int]) -> Tensor:
+    """[sum_i C_local * N_i, ...] received rank-major (rank i contributes its N_i gaussians for each of our
+    C_local cameras) -> [C_local, sum_i N_i, ...]."""
+    parts, o = [], 0
+    for n_i in N_world:
+        parts.append(t[o : o + C_local * n_i].reshape((C_local, n_i) + tuple(t.shape[1:])))
+        o += C_local * n_i
+    return torch.cat(parts, dim=1)
 
 
 def cli(fn: Callable, args, verbose: bool = False) -> None:

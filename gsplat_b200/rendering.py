@@ -114,14 +114,17 @@ def rasterization(
         raise ValueError(f"unknown rasterize_mode {rasterize_mode!r}")
     if sparse_grad:
         _unsupported("sparse_grad", "sparse COO gradients are a 'next' row (SURVEY.md section 8f.1)")
+    world_size, world_rank = 1, 0
     if distributed:
+        # reference: rendering.py:178-197 -- needs an initialised default group; NCCL in the reference (the CPU
+        # tests of the host logic here run it over gloo)
         if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
             raise ValueError("distributed=True requires an initialized default torch.distributed process group.")
-        if torch.distributed.get_world_size() > 1:
-            _unsupported(
-                "distributed=True (world_size > 1)",
-                "gaussian-sharded rendering is a 'next' row; gsplat_b200.distributed offers view-parallel DP",
-            )
+        world_size, world_rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        if len(tuple(means.shape[:-2])) != 0:
+            raise ValueError("distributed=True does not support batch dimensions")
+        if world_size > 1 and colors is not None and sh_degree is None and colors.dim() == 3:
+            raise ValueError("distributed=True: per-camera colors [C, N, D] cannot be sharded; pass [N, D] or SH")
     if tile_size is None:
         tile_size = 16
     if tile_size != 16:
@@ -171,6 +174,18 @@ def rasterization(
 
     antialiased = rasterize_mode == "antialiased"
 
+    # ---- Seam A (distributed=True): every rank projects ITS gaussians onto ALL cameras
+    C_world, N_world = [C], [N]
+    if distributed and world_size > 1:
+        from . import distributed as gdist
+
+        N_world = gdist.all_gather_ints(N, means.device)
+        C_world = gdist.all_gather_ints(C, means.device)
+        viewmats, Ks = gdist.all_gather_rows([viewmats, Ks], C_world)
+        C = sum(C_world)
+        if backgrounds is not None and tuple(backgrounds.shape[:-1]) != (C_world[world_rank],):
+            raise ValueError("backgrounds must be [C_local, D] under distributed=True")
+
     # ---- projection (+ SH): fused single pass when it applies
     fused = (
         has_color and sh_degree is not None and covars is None and nb == 0 and colors.shape[-1] == 3
@@ -201,6 +216,26 @@ def rasterization(
     opac = torch.broadcast_to(opacities[..., None, :], batch_dims + (C, N))
     if compensations is not None:
         opac = opac * compensations
+
+    # ---- Seam B (distributed=True): all-to-all so that each rank holds ALL gaussians projected onto ITS cameras
+    if distributed and world_size > 1:
+        C_local = C_world[world_rank]
+        send = [c * N for c in C_world]          # rows (camera-major) going to each camera owner
+        recv = [C_local * n for n in N_world]    # rows arriving from each gaussian owner
+        fields = [means2d.reshape(C * N, 2), depths.reshape(C * N), conics.reshape(C * N, 3), opac.reshape(C * N)]
+        if feat is not None:
+            if feat.dim() == 2:  # [N, D] shared by all cameras
+                feat = torch.broadcast_to(feat[None], (C, N, feat.shape[-1]))
+            fields.append(feat.reshape(C * N, feat.shape[-1]))
+        fields.append(radii.reshape(C * N, 2))
+        got = gdist.all_to_all_rows(fields, send, recv)
+        loc = [gdist.camera_major_to_local(t, C_local, N_world) for t in got]
+        means2d, depths, conics, opac = loc[0], loc[1], loc[2], loc[3]
+        if feat is not None:
+            feat = loc[4]
+        radii = loc[-1].contiguous()
+        C, N = C_local, sum(N_world)
+        I = C
 
     # ---- tile intersection (AccuTile) + offsets
     tile_width = math.ceil(width / float(tile_size))

@@ -52,6 +52,30 @@ def _worker(rank, world, port, out):
     (c[0] * float(rank + 1)).sum().backward()  # c[1] has no gradient on any rank
     D.all_reduce_gaussian_grads(c, coalesced=True)
     assert torch.allclose(c[0].grad, torch.full((5,), 3.0)) and torch.equal(c[1].grad, torch.zeros(2, 3))
+    # ---- reference-semantics seams: variable-count, differentiable row collectives
+    n_mine = 3 + rank  # rank 0 owns 3 rows, rank 1 owns 4
+    counts = D.all_gather_ints(n_mine, "cpu")
+    assert counts == [3, 4]
+    a = (torch.arange(n_mine * 2, dtype=torch.float32).reshape(n_mine, 2) + 100 * rank).requires_grad_(True)
+    b = torch.arange(n_mine, dtype=torch.float32) + 10 * rank
+    ga, gb = D.all_gather_rows([a, b], counts)
+    assert ga.shape == (7, 2) and gb.shape == (7,)
+    assert torch.equal(gb, torch.tensor([0.0, 1, 2, 10, 11, 12, 13]))
+    (ga * (rank + 1)).sum().backward()  # every rank's gradient flows back to the owner: 1 + 2 = 3
+    assert torch.allclose(a.grad, torch.full_like(a, 3.0))
+    # all-to-all: rank r sends (r + 1 + j) rows to rank j
+    send = [rank + 1 + j for j in range(world)]
+    recv = [j + 1 + rank for j in range(world)]
+    x = (torch.arange(sum(send), dtype=torch.float32)[:, None] + 1000 * rank).requires_grad_(True)
+    ids = torch.arange(sum(send), dtype=torch.int32) + 1000 * rank
+    rx, rid = D.all_to_all_rows([x, ids], send, recv)
+    assert rx.shape == (sum(recv), 1) and rid.dtype == torch.int32 and torch.equal(rx[:, 0].long(), rid.long())
+    rx.sum().backward()
+    assert torch.allclose(x.grad, torch.ones_like(x))
+    # camera-major -> local layout
+    t = torch.arange(2 * 3 + 2 * 4).float()
+    loc = D.camera_major_to_local(t, 2, [3, 4])
+    assert loc.shape == (2, 7) and loc[1, 3:].tolist() == [10.0, 11.0, 12.0, 13.0]
     dist.barrier()
     dist.destroy_process_group()
     out.put(rank)
