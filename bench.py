@@ -341,6 +341,68 @@ def main():
     ms_e2e = timed(True, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- N > 1 diagnostics (outside the timed regions): where a DP step spends its time on every rank, and the
+    # same job (world views / step over the same Gaussians, every gradient summed over all views) laid out the
+    # reference's way -- Gaussians sharded across ranks, projected rows exchanged by all-to-all, no all-reduce.
+    dp_info = None
+    if world > 1:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        comp, comm = [], []
+        for _ in range(5):
+            dist.barrier()
+            torch.cuda.synchronize()
+            ev[0].record()
+            for p in params.values():
+                p.grad = None
+            rc, _, _ = gsplat_b200.rasterization(
+                params["means"], params["quats"], params["scales"], params["opacities"], params["sh"], vm_dev, K_dev, W_IMG,
+                H_IMG, sh_degree=SH_DEGREE, packed=False,
+            )
+            (rc - target_dev).abs().mean().backward()
+            ev[1].record()
+            D.all_reduce_gaussian_grads([params[k] for k in grad_names], coalesced=True)
+            ev[2].record()
+            torch.cuda.synchronize()
+            comp.append(ev[0].elapsed_time(ev[1]))
+            comm.append(ev[1].elapsed_time(ev[2]))
+        mine = torch.tensor([sorted(comp)[2], sorted(comm)[2]], device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        bounds = [int(round(i * N / world)) for i in range(world + 1)]
+        shard = {k: params[k].detach()[bounds[rank] : bounds[rank + 1]].clone().requires_grad_(True) for k in params}
+
+        def sharded_step():
+            for p in shard.values():
+                p.grad = None
+            rc, _, _ = gsplat_b200.rasterization(
+                shard["means"], shard["quats"], shard["scales"], shard["opacities"], shard["sh"], vm_dev, K_dev, W_IMG, H_IMG,
+                sh_degree=SH_DEGREE, packed=False, distributed=True,
+            )
+            (rc - target_dev).abs().mean().backward()
+
+        for _ in range(3):
+            sharded_step()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(args.steps):
+            sharded_step()
+        ev[1].record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms_sh = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev)
+        dist.all_reduce(ms_sh, op=dist.ReduceOp.MAX)
+        dp_info = {
+            "per_rank_compute_ms": [round(float(t[0]), 3) for t in allr],
+            "per_rank_allreduce_ms": [round(float(t[1]), 3) for t in allr],
+            "allreduce_bytes_per_rank": int(sum(params[k].numel() for k in grad_names) * 4),
+            "gaussian_sharded": {
+                "what": "same job with rasterization(distributed=True): Gaussians sharded, all-to-all of projected rows, no all-reduce",
+                "value": n_gpus * args.steps / (float(ms_sh.item()) * 1e-3), "unit": UNIT,
+                "ms_per_step": float(ms_sh.item()) / args.steps,
+            },
+        }
+
     # ---- roofline of the dominant kernels, timed alone with CUDA events on the launching stream
     S = int(meta["flatten_ids"].numel())
     P, T = W_IMG * H_IMG, meta["tile_width"] * meta["tile_height"]
@@ -411,11 +473,11 @@ def main():
                 "value": n_gpus * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
             },
-            # our own kernels per step: project_sh_fwd, isect_count, isect_emit, isect_offsets, pack_records,
-            # tile_order, raster_fwd, raster_bwd, project_sh_bwd (= 9; cub scan / radix-sort launches made by the
-            # library are not counted); timed region = `steps` device-resident + `steps` e2e steps
-            "gpu_launches": args.steps * 2 * 9,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "ref_cuda": ref_cuda,
+            # our own kernels per step: project_sh_fwd, depth_key, isect_count, isect_emit, isect_offsets,
+            # pack_records, tile_order, raster_fwd, raster_bwd, project_sh_bwd (= 10; cub scan / radix-sort launches
+            # made by the library are not counted); timed region = `steps` device-resident + `steps` e2e steps
+            "gpu_launches": args.steps * 2 * 10,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "ref_cuda": ref_cuda, "dp": dp_info,
         }
         print(json.dumps(line))
     if world > 1:

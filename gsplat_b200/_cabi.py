@@ -56,18 +56,14 @@ _SIGNATURES = {
         [c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_f32, c_vp, c_vp, c_vp, c_vp,
          c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     ),
+    "gsb200_isect_depth_order_workspace_bytes": (c_sz, [c_i64, c_i64]),
+    "gsb200_isect_depth_order": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "gsb200_isect_scan_workspace_bytes": (c_sz, [c_i64]),
-    "gsb200_isect_count": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_vp, c_vp, c_vp, c_sz, c_vp]),
-    "gsb200_isect_emit": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_vp, c_vp, c_vp]),
-    "gsb200_sort_workspace_bytes": (c_sz, [c_i64, c_int]),
-    "gsb200_sort_pairs": (c_int, [c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "gsb200_isect_count": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "gsb200_isect_emit": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_vp, c_vp, c_vp]),
+    "gsb200_sort_workspace_bytes": (c_sz, [c_i64, c_int, c_int]),
+    "gsb200_sort_pairs": (c_int, [c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "gsb200_isect_offsets": (c_int, [c_i64, c_vp, c_i64, c_u32, c_u32, c_vp, c_vp]),
-    "gsb200_isect_bucket_scan_workspace_bytes": (c_sz, [c_i64]),
-    "gsb200_isect_bucket_count": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
-    "gsb200_isect_bucket_emit": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_vp, c_vp, c_vp, c_vp]),
-    "gsb200_segsort_workspace_bytes": (c_sz, [c_i64, c_i64]),
-    "gsb200_segsort_keys": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
-    "gsb200_isect_bucket_finalize": (c_int, [c_i64, c_u32, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gsb200_relocation": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_vp, c_vp, c_vp]),
     "gsb200_mcmc_perturb_positions": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, c_vp]),
     "gsb200_raster_records_bytes": (c_sz, [c_i64, c_int, c_i64]),

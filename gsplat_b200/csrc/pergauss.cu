@@ -641,16 +641,20 @@ __device__ __forceinline__ int tiles_of_gaussian(
     return count;
 }
 
+// `order` (optional): thread j handles row order[j] (the depth order of gsb200_isect_depth_order) and also
+// writes its count to counts_in_order[j], the array the scan runs over.
 __global__ void __launch_bounds__(kThreads) isect_count_kernel(
     int64_t total, const float *__restrict__ means2d, const int32_t *__restrict__ radii, const float *__restrict__ conics,
-    const float *__restrict__ opacities, uint32_t tile_size, uint32_t tw, uint32_t th, int32_t *__restrict__ tiles_per_gauss
+    const float *__restrict__ opacities, const int32_t *__restrict__ order, uint32_t tile_size, uint32_t tw, uint32_t th,
+    int32_t *__restrict__ tiles_per_gauss, int32_t *__restrict__ counts_in_order
 )
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= total)
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(j >= total)
         return;
-    const int2 r = reinterpret_cast<const int2 *>(radii)[i];
-    int cnt      = 0;
+    const int64_t i = order ? (int64_t)order[j] : j;
+    const int2 r    = reinterpret_cast<const int2 *>(radii)[i];
+    int cnt         = 0;
     if(r.x > 0 && r.y > 0)
     {
         const float2 m = reinterpret_cast<const float2 *>(means2d)[i];
@@ -661,19 +665,23 @@ __global__ void __launch_bounds__(kThreads) isect_count_kernel(
         cnt = tiles_of_gaussian(m.x, m.y, r.x, r.y, accu ? cn : nullptr, accu ? &op : nullptr, tile_size, tw, th, [](int64_t) {});
     }
     tiles_per_gauss[i] = cnt;
+    if(order)
+        counts_in_order[j] = cnt;
 }
 
 __global__ void __launch_bounds__(kThreads) isect_emit_kernel(
     int64_t total, int64_t N, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
     const float *__restrict__ depths, const float *__restrict__ conics, const float *__restrict__ opacities,
-    const int64_t *__restrict__ cum_tiles, const int64_t *__restrict__ image_ids, uint32_t tile_size, uint32_t tw,
-    uint32_t th, uint32_t tile_n_bits, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids
+    const int64_t *__restrict__ cum_tiles, const int64_t *__restrict__ image_ids, const int32_t *__restrict__ order,
+    uint32_t tile_size, uint32_t tw, uint32_t th, uint32_t tile_n_bits, int64_t *__restrict__ isect_ids,
+    int32_t *__restrict__ flatten_ids
 )
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= total)
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(j >= total)
         return;
-    const int2 r = reinterpret_cast<const int2 *>(radii)[i];
+    const int64_t i = order ? (int64_t)order[j] : j;
+    const int2 r    = reinterpret_cast<const int2 *>(radii)[i];
     if(r.x <= 0 || r.y <= 0)
         return;
     const float2 m = reinterpret_cast<const float2 *>(means2d)[i];
@@ -681,7 +689,7 @@ __global__ void __launch_bounds__(kThreads) isect_emit_kernel(
     const bool accu = conics != nullptr && opacities != nullptr;
     if(accu)
         cn[0] = conics[i * 3], cn[1] = conics[i * 3 + 1], cn[2] = conics[i * 3 + 2], op = opacities[i];
-    int64_t cur         = (i == 0) ? 0 : cum_tiles[i - 1];
+    int64_t cur         = (j == 0) ? 0 : cum_tiles[j - 1];
     const int64_t hi    = (image_ids ? image_ids[i] : (i / N)) << (32 + tile_n_bits); // packed rows carry their image id
     const int64_t dbits = (int64_t)__float_as_uint(depths[i]);
     tiles_of_gaussian(m.x, m.y, r.x, r.y, accu ? cn : nullptr, accu ? &op : nullptr, tile_size, tw, th, [&](int64_t tile) {
@@ -689,81 +697,6 @@ __global__ void __launch_bounds__(kThreads) isect_emit_kernel(
         flatten_ids[cur] = (int32_t)i;
         ++cur;
     });
-}
-
-// ---- tile-bucketed variant (no global sort): the count pass also histograms the tiles, the emit pass
-// drops each (depth, gaussian) key straight into its tile's segment; a per-tile segmented sort finishes.
-__global__ void __launch_bounds__(kThreads) isect_bucket_count_kernel(
-    int64_t total, int64_t N, int64_t n_tiles, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
-    const float *__restrict__ conics, const float *__restrict__ opacities, uint32_t tile_size, uint32_t tw, uint32_t th,
-    int32_t *__restrict__ tiles_per_gauss, int32_t *__restrict__ tile_counts
-)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= total)
-        return;
-    const int2 r = reinterpret_cast<const int2 *>(radii)[i];
-    int cnt      = 0;
-    if(r.x > 0 && r.y > 0)
-    {
-        const float2 m = reinterpret_cast<const float2 *>(means2d)[i];
-        float cn[3] = {0.f, 0.f, 0.f}, op = 0.f;
-        const bool accu = conics != nullptr && opacities != nullptr;
-        if(accu)
-            cn[0] = conics[i * 3], cn[1] = conics[i * 3 + 1], cn[2] = conics[i * 3 + 2], op = opacities[i];
-        int32_t *tc = tile_counts + (i / N) * n_tiles;
-        cnt = tiles_of_gaussian(m.x, m.y, r.x, r.y, accu ? cn : nullptr, accu ? &op : nullptr, tile_size, tw, th,
-                                [&](int64_t tile) { atomicAdd(tc + tile, 1); });
-    }
-    tiles_per_gauss[i] = cnt;
-}
-
-__global__ void __launch_bounds__(kThreads) isect_bucket_emit_kernel(
-    int64_t total, int64_t N, int64_t n_tiles, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
-    const float *__restrict__ depths, const float *__restrict__ conics, const float *__restrict__ opacities,
-    uint32_t tile_size, uint32_t tw, uint32_t th, const int32_t *__restrict__ offsets, int32_t *__restrict__ cursor,
-    uint64_t *__restrict__ keys
-)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= total)
-        return;
-    const int2 r = reinterpret_cast<const int2 *>(radii)[i];
-    if(r.x <= 0 || r.y <= 0)
-        return;
-    const float2 m = reinterpret_cast<const float2 *>(means2d)[i];
-    float cn[3] = {0.f, 0.f, 0.f}, op = 0.f;
-    const bool accu = conics != nullptr && opacities != nullptr;
-    if(accu)
-        cn[0] = conics[i * 3], cn[1] = conics[i * 3 + 1], cn[2] = conics[i * 3 + 2], op = opacities[i];
-    const int64_t base = (i / N) * n_tiles;
-    // depth in the high word, gaussian index in the low word: unique keys, so the per-tile order
-    // (depth, then emit order) does not depend on which thread won which slot
-    const uint64_t key = ((uint64_t)__float_as_uint(depths[i]) << 32) | (uint64_t)(uint32_t)i;
-    tiles_of_gaussian(m.x, m.y, r.x, r.y, accu ? cn : nullptr, accu ? &op : nullptr, tile_size, tw, th, [&](int64_t tile) {
-        const int32_t pos = offsets[base + tile] + atomicAdd(cursor + base + tile, 1);
-        keys[pos]         = key;
-    });
-}
-
-// one warp per tile: sorted per-tile keys -> reference-format isect_ids / flatten_ids
-__global__ void __launch_bounds__(kThreads) isect_bucket_finalize_kernel(
-    int64_t total_tiles, int64_t n_tiles, uint32_t tile_n_bits, const int32_t *__restrict__ offsets,
-    const uint64_t *__restrict__ keys, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids
-)
-{
-    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if(t >= total_tiles)
-        return;
-    const unsigned lane = threadIdx.x & 31;
-    const int64_t hi    = (((t / n_tiles) << tile_n_bits) | (t % n_tiles)) << 32;
-    const int32_t b = offsets[t], e = offsets[t + 1];
-    for(int32_t s = b + (int32_t)lane; s < e; s += 32)
-    {
-        const uint64_t k = keys[s];
-        isect_ids[s]     = hi | (int64_t)(k >> 32);
-        flatten_ids[s]   = (int32_t)(uint32_t)k;
-    }
 }
 
 // offsets[(image, tile)] = first sorted index of that tile's run.  One thread per sorted
@@ -1057,13 +990,13 @@ extern "C" size_t gsb200_isect_scan_workspace_bytes(int64_t n_elements)
     if(n_elements <= 0)
         return 0;
     cub::DeviceScan::InclusiveSum((void *)nullptr, bytes, (const int32_t *)nullptr, (int64_t *)nullptr, n_elements);
-    return bytes + 256;
+    return ((bytes + 255) & ~(size_t)255) + sizeof(int32_t) * (size_t)n_elements + 256; // + counts in depth order
 }
 
 extern "C" int gsb200_isect_count(
     int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *conics, const float *opacities,
-    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int32_t *tiles_per_gauss, int64_t *cum_tiles,
-    void *workspace, size_t workspace_bytes, void *stream
+    const int32_t *order, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int32_t *tiles_per_gauss,
+    int64_t *cum_tiles, void *workspace, size_t workspace_bytes, void *stream
 )
 {
     if(I < 0 || N < 0 || tile_size == 0)
@@ -1071,27 +1004,29 @@ extern "C" int gsb200_isect_count(
     const int64_t total = I * N;
     if(total == 0)
         return GSB200_OK;
-    if(!means2d || !radii || !tiles_per_gauss || !cum_tiles || !workspace)
+    if(!means2d || !radii || !tiles_per_gauss || !cum_tiles || !workspace || total > 0x7fffffffLL)
         return GSB200_E_INVALID;
     if(bits_for_count(I) + bits_for_count((int64_t)tile_width * tile_height) > 32)
         return GSB200_E_KEYBITS;
     cudaStream_t st = (cudaStream_t)stream;
+    size_t need     = 0;
+    cub::DeviceScan::InclusiveSum((void *)nullptr, need, tiles_per_gauss, cum_tiles, total, st);
+    const size_t scan_bytes = (need + 255) & ~(size_t)255;
+    if(scan_bytes + (order ? sizeof(int32_t) * (size_t)total : 0) > workspace_bytes)
+        return GSB200_E_WORKSPACE;
+    int32_t *counts_in_order = order ? reinterpret_cast<int32_t *>(static_cast<char *>(workspace) + scan_bytes) : nullptr;
     isect_count_kernel<<<grid_for(total, kThreads), kThreads, 0, st>>>(
-        total, means2d, radii, conics, opacities, tile_size, tile_width, tile_height, tiles_per_gauss
+        total, means2d, radii, conics, opacities, order, tile_size, tile_width, tile_height, tiles_per_gauss, counts_in_order
     );
     if(int rc = check_launch())
         return rc;
-    size_t need = 0;
-    cub::DeviceScan::InclusiveSum((void *)nullptr, need, tiles_per_gauss, cum_tiles, total, st);
-    if(need > workspace_bytes)
-        return GSB200_E_WORKSPACE;
-    GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(workspace, need, tiles_per_gauss, cum_tiles, total, st));
+    GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(workspace, need, order ? counts_in_order : tiles_per_gauss, cum_tiles, total, st));
     return GSB200_OK;
 }
 
 extern "C" int gsb200_isect_emit(
     int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *depths, const float *conics,
-    const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids, uint32_t tile_size,
+    const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids, const int32_t *order, uint32_t tile_size,
     uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids, int32_t *flatten_ids, void *stream
 )
 {
@@ -1107,7 +1042,7 @@ extern "C" int gsb200_isect_emit(
     if(bits_for_count(I) + tile_bits > 32)
         return GSB200_E_KEYBITS;
     isect_emit_kernel<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        total, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, tile_size, tile_width, tile_height,
+        total, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
         tile_bits, isect_ids, flatten_ids
     );
     return check_launch();
@@ -1136,89 +1071,6 @@ extern "C" int gsb200_isect_offsets(
         return GSB200_E_INVALID;
     isect_offsets_kernel<<<grid_for(n_isects, kThreads), kThreads, 0, st>>>(
         n_isects, isect_ids, total, n_tiles, bits_for_count(n_tiles), offsets
-    );
-    return check_launch();
-}
-
-// ---- tile-bucketed intersection (used by rasterization(); same outputs as count/emit/sort/offsets)
-extern "C" size_t gsb200_isect_bucket_scan_workspace_bytes(int64_t total_tiles)
-{
-    size_t bytes = 0;
-    if(total_tiles <= 0)
-        return 0;
-    cub::DeviceScan::ExclusiveSum((void *)nullptr, bytes, (const int32_t *)nullptr, (int32_t *)nullptr, total_tiles + 1);
-    return bytes + 256;
-}
-
-extern "C" int gsb200_isect_bucket_count(
-    int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *conics, const float *opacities,
-    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int32_t *tiles_per_gauss, int32_t *tile_counts,
-    int32_t *offsets, void *workspace, size_t workspace_bytes, void *stream
-)
-{
-    if(I < 0 || N < 0 || tile_size == 0)
-        return GSB200_E_INVALID;
-    const int64_t n_tiles = (int64_t)tile_width * tile_height, total_tiles = I * n_tiles, total = I * N;
-    if(total_tiles == 0)
-        return GSB200_OK;
-    if(!tile_counts || !offsets || !workspace || (total > 0 && (!means2d || !radii || !tiles_per_gauss)))
-        return GSB200_E_INVALID;
-    if(bits_for_count(I) + bits_for_count(n_tiles) > 32)
-        return GSB200_E_KEYBITS;
-    cudaStream_t st = (cudaStream_t)stream;
-    // tile_counts has total_tiles + 1 entries (the last stays 0 so that the exclusive scan ends with the total)
-    GSB_CUDA_TRY(cudaMemsetAsync(tile_counts, 0, sizeof(int32_t) * (size_t)(total_tiles + 1), st));
-    if(total > 0)
-    {
-        isect_bucket_count_kernel<<<grid_for(total, kThreads), kThreads, 0, st>>>(
-            total, N, n_tiles, means2d, radii, conics, opacities, tile_size, tile_width, tile_height, tiles_per_gauss,
-            tile_counts
-        );
-        if(int rc = check_launch())
-            return rc;
-    }
-    size_t need = 0;
-    cub::DeviceScan::ExclusiveSum((void *)nullptr, need, tile_counts, offsets, total_tiles + 1, st);
-    if(need > workspace_bytes)
-        return GSB200_E_WORKSPACE;
-    GSB_CUDA_TRY(cub::DeviceScan::ExclusiveSum(workspace, need, tile_counts, offsets, total_tiles + 1, st));
-    return GSB200_OK;
-}
-
-extern "C" int gsb200_isect_bucket_emit(
-    int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *depths, const float *conics,
-    const float *opacities, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, const int32_t *offsets,
-    int32_t *cursor, uint64_t *keys, void *stream
-)
-{
-    if(I < 0 || N < 0 || tile_size == 0)
-        return GSB200_E_INVALID;
-    const int64_t n_tiles = (int64_t)tile_width * tile_height, total = I * N;
-    if(total == 0 || n_tiles == 0)
-        return GSB200_OK;
-    if(!means2d || !radii || !depths || !offsets || !cursor || !keys)
-        return GSB200_E_INVALID;
-    cudaStream_t st = (cudaStream_t)stream;
-    GSB_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)(I * n_tiles), st));
-    isect_bucket_emit_kernel<<<grid_for(total, kThreads), kThreads, 0, st>>>(
-        total, N, n_tiles, means2d, radii, depths, conics, opacities, tile_size, tile_width, tile_height, offsets, cursor,
-        keys
-    );
-    return check_launch();
-}
-
-extern "C" int gsb200_isect_bucket_finalize(
-    int64_t I, uint32_t tile_width, uint32_t tile_height, const int32_t *offsets, const uint64_t *keys_sorted,
-    int64_t *isect_ids, int32_t *flatten_ids, void *stream
-)
-{
-    const int64_t n_tiles = (int64_t)tile_width * tile_height, total_tiles = I * n_tiles;
-    if(total_tiles <= 0)
-        return GSB200_OK;
-    if(!offsets || !keys_sorted || !isect_ids || !flatten_ids)
-        return GSB200_E_INVALID;
-    isect_bucket_finalize_kernel<<<grid_for(total_tiles * 32, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        total_tiles, n_tiles, bits_for_count(n_tiles), offsets, keys_sorted, isect_ids, flatten_ids
     );
     return check_launch();
 }

@@ -1,10 +1,10 @@
 // sort.cu -- (isect_id, flatten_id) radix sort and library-level helpers.
 //
-// The sort is cub::DeviceRadixSort::SortPairs on key bits [0, 32 + tile_bits + image_bits), the same
-// library call the reference makes (csrc/IntersectTile.cu:1078-1121); the onesweep kernels it
-// instantiates are compiled here for sm_100a.  Stable, so equal (tile, depth) keys keep emit order.
+// The sorts are cub::DeviceRadixSort::SortPairs (the library call the reference makes,
+// csrc/IntersectTile.cu:1078-1121; its onesweep kernels are compiled here for sm_100a), used twice:
+// once over the N projected rows on (image, depth) and once over the S intersections on the (image, tile)
+// bits only -- see gsb200_isect_depth_order below.
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_segmented_sort.cuh>
 
 #include "common.cuh"
 
@@ -34,24 +34,25 @@ extern "C" const char *gsb200_last_cuda_error(void) { return cudaGetErrorString(
 
 extern "C" uint32_t gsb200_bits_for_count(int64_t count) { return gsb::bits_for_count(count); }
 
-extern "C" size_t gsb200_sort_workspace_bytes(int64_t n_isects, int end_bit)
+extern "C" size_t gsb200_sort_workspace_bytes(int64_t n_isects, int begin_bit, int end_bit)
 {
     if(n_isects <= 0)
         return 0;
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(
         (void *)nullptr, bytes, (const int64_t *)nullptr, (int64_t *)nullptr, (const int32_t *)nullptr, (int32_t *)nullptr,
-        n_isects, 0, end_bit
+        n_isects, begin_bit, end_bit
     );
     return bytes + 256;
 }
 
+// Stable LSD radix sort of the (key, value) pairs on key bits [begin_bit, end_bit).
 extern "C" int gsb200_sort_pairs(
-    int64_t n_isects, int end_bit, const int64_t *keys_in, const int32_t *vals_in, int64_t *keys_out, int32_t *vals_out,
-    void *workspace, size_t workspace_bytes, void *stream
+    int64_t n_isects, int begin_bit, int end_bit, const int64_t *keys_in, const int32_t *vals_in, int64_t *keys_out,
+    int32_t *vals_out, void *workspace, size_t workspace_bytes, void *stream
 )
 {
-    if(n_isects < 0 || end_bit < 0 || end_bit > 64)
+    if(n_isects < 0 || begin_bit < 0 || end_bit < begin_bit || end_bit > 64)
         return GSB200_E_INVALID;
     if(n_isects == 0)
         return GSB200_OK;
@@ -59,44 +60,90 @@ extern "C" int gsb200_sort_pairs(
         return GSB200_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     size_t need     = 0;
-    cub::DeviceRadixSort::SortPairs((void *)nullptr, need, keys_in, keys_out, vals_in, vals_out, n_isects, 0, end_bit, st);
+    cub::DeviceRadixSort::SortPairs((void *)nullptr, need, keys_in, keys_out, vals_in, vals_out, n_isects, begin_bit, end_bit, st);
     if(need > workspace_bytes)
         return GSB200_E_WORKSPACE;
-    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(workspace, need, keys_in, keys_out, vals_in, vals_out, n_isects, 0, end_bit, st));
+    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(workspace, need, keys_in, keys_out, vals_in, vals_out, n_isects, begin_bit, end_bit, st));
     return GSB200_OK;
 }
 
-// Per-tile sort of the bucketed (depth << 32 | gaussian) keys: cub::DeviceSegmentedSort, segments =
-// tiles (offsets has n_segments + 1 entries).  Ascending 64-bit keys == (depth bits, emit order), i.e.
-// exactly the order the stable global radix sort of the reference produces inside a tile.
-extern "C" size_t gsb200_segsort_workspace_bytes(int64_t n_items, int64_t n_segments)
+// ---- depth order of the projected gaussians (pre-pass of the tile intersection)
+// The reference sorts all S intersections on (image, tile, depth) = 45+ key bits.  Sorting the rows ONCE by
+// (image, depth) and emitting the intersections in that order leaves only the (image, tile) bits for the
+// S-sized sort: both sorts are stable, so inside a tile the result is (depth, then row index) -- exactly the
+// order the reference's single stable sort produces (csrc/Intersect.cpp:283-326).
+namespace gsb
 {
-    if(n_items <= 0 || n_segments <= 0)
-        return 0;
-    size_t bytes = 0;
-    cub::DeviceSegmentedSort::SortKeys(
-        (void *)nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)n_items, (int)n_segments,
-        (const int32_t *)nullptr, (const int32_t *)nullptr
-    );
-    return bytes + 256;
+__global__ void __launch_bounds__(256) depth_key_kernel(
+    int64_t total, int64_t N, const int32_t *__restrict__ radii, const float *__restrict__ depths,
+    const int64_t *__restrict__ image_ids, uint64_t *__restrict__ keys, int32_t *__restrict__ rows
+)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= total)
+        return;
+    const int2 r = reinterpret_cast<const int2 *>(radii)[i];
+    uint64_t k   = ~0ull; // culled rows go last
+    if(r.x > 0 && r.y > 0)
+        k = ((uint64_t)(image_ids ? image_ids[i] : i / N) << 32) | (uint64_t)__float_as_uint(depths[i]);
+    keys[i] = k;
+    rows[i] = (int32_t)i;
 }
 
-extern "C" int gsb200_segsort_keys(
-    int64_t n_items, int64_t n_segments, const int32_t *offsets, const uint64_t *keys_in, uint64_t *keys_out,
+struct DepthOrderLayout
+{
+    size_t keys_in, keys_out, rows_in, cub, total;
+};
+static DepthOrderLayout depth_order_layout(int64_t total, int end_bit)
+{
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    DepthOrderLayout L;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(
+        (void *)nullptr, cub_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const int32_t *)nullptr, (int32_t *)nullptr,
+        total, 0, end_bit
+    );
+    L.keys_in  = 0;
+    L.keys_out = L.keys_in + al(sizeof(uint64_t) * (size_t)total);
+    L.rows_in  = L.keys_out + al(sizeof(uint64_t) * (size_t)total);
+    L.cub      = L.rows_in + al(sizeof(int32_t) * (size_t)total);
+    L.total    = L.cub + al(cub_bytes) + 256;
+    return L;
+}
+} // namespace gsb
+
+extern "C" size_t gsb200_isect_depth_order_workspace_bytes(int64_t I, int64_t total_rows)
+{
+    if(total_rows <= 0 || I <= 0)
+        return 0;
+    return gsb::depth_order_layout(total_rows, 32 + (int)gsb::bits_for_count(I)).total;
+}
+
+extern "C" int gsb200_isect_depth_order(
+    int64_t I, int64_t N, const int32_t *radii, const float *depths, const int64_t *image_ids, int32_t *order,
     void *workspace, size_t workspace_bytes, void *stream
 )
 {
-    if(n_items < 0 || n_segments < 0 || n_items > 0x7fffffffLL || n_segments > 0x7fffffffLL)
+    if(I < 0 || N < 0)
         return GSB200_E_INVALID;
-    if(n_items == 0 || n_segments == 0)
+    const int64_t total = image_ids ? N : I * N; // packed: N rows in total
+    if(total == 0)
         return GSB200_OK;
-    if(!offsets || !keys_in || !keys_out || !workspace)
+    if(!radii || !depths || !order || !workspace || total > 0x7fffffffLL)
         return GSB200_E_INVALID;
-    cudaStream_t st = (cudaStream_t)stream;
-    size_t need     = 0;
-    cub::DeviceSegmentedSort::SortKeys((void *)nullptr, need, keys_in, keys_out, (int)n_items, (int)n_segments, offsets, offsets + 1, st);
-    if(need > workspace_bytes)
+    const int end_bit = 32 + (int)gsb::bits_for_count(I);
+    const auto L      = gsb::depth_order_layout(total, end_bit);
+    if(L.total > workspace_bytes)
         return GSB200_E_WORKSPACE;
-    GSB_CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(workspace, need, keys_in, keys_out, (int)n_items, (int)n_segments, offsets, offsets + 1, st));
+    char *ws         = static_cast<char *>(workspace);
+    uint64_t *k_in   = reinterpret_cast<uint64_t *>(ws + L.keys_in), *k_out = reinterpret_cast<uint64_t *>(ws + L.keys_out);
+    int32_t *rows_in = reinterpret_cast<int32_t *>(ws + L.rows_in);
+    cudaStream_t st  = (cudaStream_t)stream;
+    gsb::depth_key_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, N, radii, depths, image_ids, k_in, rows_in);
+    if(int rc = gsb::check_launch())
+        return rc;
+    size_t cub_bytes = L.total - L.cub;
+    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, k_in, k_out, rows_in, order, total, 0, end_bit, st));
     return GSB200_OK;
 }
+

@@ -519,11 +519,20 @@ def isect_tiles(
     accu = conics is not None and opacities is not None
     cum = torch.empty(total, device=dev, dtype=torch.int64)
     with _Ctx(dev) as st:
+        order = None
+        if sort:
+            # pass 0: rows in (image, depth) order, so that the S-sized sort below only has the (image, tile) bits left
+            order = torch.empty(total, device=dev, dtype=torch.int32)
+            ws = _scratch_buffer(dev, "dorder", L.gsb200_isect_depth_order_workspace_bytes(I, total))
+            check(
+                L.gsb200_isect_depth_order(I, N, ptr(radii), ptr(depths), ptr(img_ids), ptr(order), ptr(ws), ws.numel(), st),
+                "intersect_tile (depth order)",
+            )
         ws = _scratch_buffer(dev, "scan", L.gsb200_isect_scan_workspace_bytes(total))
         check(
             L.gsb200_isect_count(
                 I_count, N, ptr(means2d), ptr(radii), ptr(conics) if accu else None, ptr(opacities) if accu else None,
-                tile_size, tile_width, tile_height, ptr(tiles_per_gauss), ptr(cum), ptr(ws), ws.numel(), st,
+                ptr(order), tile_size, tile_width, tile_height, ptr(tiles_per_gauss), ptr(cum), ptr(ws), ws.numel(), st,
             ),
             "intersect_tile (count)",
         )
@@ -535,95 +544,24 @@ def isect_tiles(
         check(
             L.gsb200_isect_emit(
                 I, N, ptr(means2d), ptr(radii), ptr(depths), ptr(conics) if accu else None,
-                ptr(opacities) if accu else None, ptr(cum), ptr(img_ids), tile_size, tile_width, tile_height,
+                ptr(opacities) if accu else None, ptr(cum), ptr(img_ids), ptr(order), tile_size, tile_width, tile_height,
                 ptr(isect_ids), ptr(flatten_ids), st,
             ),
             "intersect_tile (emit)",
         )
         if sort:
-            end_bit = 32 + tile_bits + image_bits
+            begin_bit, end_bit = 32, 32 + tile_bits + image_bits
             keys_out, vals_out = torch.empty_like(isect_ids), torch.empty_like(flatten_ids)
-            ws = _scratch_buffer(dev, "sort", L.gsb200_sort_workspace_bytes(n_isects, end_bit))
+            ws = _scratch_buffer(dev, "sort", L.gsb200_sort_workspace_bytes(n_isects, begin_bit, end_bit))
             check(
                 L.gsb200_sort_pairs(
-                    n_isects, end_bit, ptr(isect_ids), ptr(flatten_ids), ptr(keys_out), ptr(vals_out), ptr(ws), ws.numel(), st
+                    n_isects, begin_bit, end_bit, ptr(isect_ids), ptr(flatten_ids), ptr(keys_out), ptr(vals_out), ptr(ws),
+                    ws.numel(), st,
                 ),
                 "intersect_tile (sort)",
             )
             isect_ids, flatten_ids = keys_out, vals_out
     return tiles_per_gauss, isect_ids, flatten_ids
-
-
-@torch.no_grad()
-def isect_tiles_bucketed(
-    means2d: Tensor,  # [..., N, 2]
-    radii: Tensor,  # [..., N, 2]
-    depths: Tensor,  # [..., N]
-    tile_size: int,
-    tile_width: int,
-    tile_height: int,
-    conics: Optional[Tensor] = None,
-    opacities: Optional[Tensor] = None,
-) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """isect_tiles(sort=True) + isect_offset_encode in one go, without the global radix sort:
-    per-tile histogram in the count pass, exclusive scan (= the offsets), keys dropped straight into their
-    tile's segment, one segmented sort over the tiles.  Returns (tiles_per_gauss, isect_ids, flatten_ids,
-    isect_offsets [..., tile_height, tile_width]) -- bit-identical to the two reference-shaped ops."""
-    dev = require_cuda(means2d, radii, depths)
-    means2d, depths = f32c(means2d, "means2d"), f32c(depths, "depths")
-    conics, opacities = f32c(conics, "conics"), f32c(opacities, "opacities")
-    if radii.dtype != torch.int32:
-        raise TypeError("radii must be int32")
-    radii = radii.contiguous()
-    image_dims = tuple(means2d.shape[:-2])
-    I, N = _prod(image_dims), means2d.shape[-2]
-    L = lib()
-    n_tiles = tile_width * tile_height
-    image_bits, tile_bits = _cabi.bits_for_count(I), _cabi.bits_for_count(n_tiles)
-    if image_bits + tile_bits > 32:
-        raise RuntimeError(
-            f"intersect_tile: (image, tile) id packing needs {image_bits + tile_bits} bits but only 32 are "
-            f"available (I={I}, n_tiles={n_tiles})."
-        )
-    TT = I * n_tiles
-    accu = conics is not None and opacities is not None
-    tiles_per_gauss = torch.empty(image_dims + (N,), device=dev, dtype=torch.int32)
-    tile_counts = torch.empty(TT + 1, device=dev, dtype=torch.int32)
-    offsets = torch.empty(TT + 1, device=dev, dtype=torch.int32)
-    with _Ctx(dev) as st:
-        ws = _scratch_buffer(dev, "bscan", L.gsb200_isect_bucket_scan_workspace_bytes(TT))
-        check(
-            L.gsb200_isect_bucket_count(
-                I, N, ptr(means2d), ptr(radii), ptr(conics) if accu else None, ptr(opacities) if accu else None,
-                tile_size, tile_width, tile_height, ptr(tiles_per_gauss), ptr(tile_counts), ptr(offsets), ptr(ws),
-                ws.numel(), st,
-            ),
-            "isect_bucket_count",
-        )
-        n_isects = int(offsets[-1].item())  # the one host sync of the forward
-        isect_ids = torch.empty(n_isects, device=dev, dtype=torch.int64)
-        flatten_ids = torch.empty(n_isects, device=dev, dtype=torch.int32)
-        if n_isects > 0:
-            keys = torch.empty(n_isects, device=dev, dtype=torch.int64)
-            keys_sorted = torch.empty(n_isects, device=dev, dtype=torch.int64)
-            check(
-                L.gsb200_isect_bucket_emit(
-                    I, N, ptr(means2d), ptr(radii), ptr(depths), ptr(conics) if accu else None,
-                    ptr(opacities) if accu else None, tile_size, tile_width, tile_height, ptr(offsets), ptr(tile_counts),
-                    ptr(keys), st,
-                ),
-                "isect_bucket_emit",
-            )
-            ws = _scratch_buffer(dev, "segsort", L.gsb200_segsort_workspace_bytes(n_isects, TT))
-            check(
-                L.gsb200_segsort_keys(n_isects, TT, ptr(offsets), ptr(keys), ptr(keys_sorted), ptr(ws), ws.numel(), st),
-                "segsort_keys",
-            )
-            check(
-                L.gsb200_isect_bucket_finalize(I, tile_width, tile_height, ptr(offsets), ptr(keys_sorted), ptr(isect_ids), ptr(flatten_ids), st),
-                "isect_bucket_finalize",
-            )
-    return tiles_per_gauss, isect_ids, flatten_ids, offsets[:TT].view(image_dims + (tile_height, tile_width))
 
 
 @torch.no_grad()

@@ -23,13 +23,10 @@ from .ops import (
     fused_project_sh,
     isect_offset_encode,
     isect_tiles,
-    isect_tiles_bucketed,
     rasterize_to_pixels,
     spherical_harmonics,
 )
 
-# tile-bucketed intersection (per-tile segmented sort) instead of the global radix sort; identical outputs
-_USE_BUCKETED_ISECT = os.environ.get("GSB200_BUCKETED_ISECT", "0") == "1"  # measured slower than the radix path (r01: 0.82 vs 0.33 ms): off
 
 _COLOR_MODES = {"RGB", "RGB-d", "RGB-Ed", "RGB+D", "RGB+ED"}
 _HIT_DISTANCE_MODES = {"d", "Ed", "RGB-d", "RGB-Ed"}
@@ -240,16 +237,12 @@ def rasterization(
     # ---- tile intersection (AccuTile) + offsets
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
-    if _USE_BUCKETED_ISECT:
-        tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = isect_tiles_bucketed(
-            means2d, radii, depths, tile_size, tile_width, tile_height, conics=conics, opacities=opac
-        )
-    else:  # reference-shaped op sequence: count, emit, global radix sort, offsets
-        tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(
-            means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, segmented=segmented, packed=False,
-            n_images=I, conics=conics, opacities=opac,
-        )
-        isect_offsets = isect_offset_encode(isect_ids, I, tile_width, tile_height)
+    # reference-shaped op sequence: (depth order,) count, emit, radix sort on the (image, tile) bits, offsets
+    tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(
+        means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, segmented=segmented, packed=False,
+        n_images=I, conics=conics, opacities=opac,
+    )
+    isect_offsets = isect_offset_encode(isect_ids, I, tile_width, tile_height)
     isect_offsets = isect_offsets.reshape(batch_dims + (C, tile_height, tile_width))
 
     camera_ids = gaussian_ids = batch_ids = None

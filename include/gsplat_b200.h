@@ -119,64 +119,44 @@ extern "C"
     );
 
     /* ---- intersect_tile : ext.cpp:1022-1026, _wrapper.py:1196-1266, host csrc/Intersect.cpp:170-329 ----
-     * Pass 1: tiles_per_gauss int32 [I*N] and its inclusive scan cum_tiles int64 [I*N] (device).
-     * conics + opacities given -> AccuTile/SNUGBOX ellipse test, else AABB from radii.
-     * The caller reads cum_tiles[I*N-1] (= n_isects) to size the pass-2 outputs. */
+     * Pass 0 (sorted output only): order int32 [rows] = the projected rows in ascending (image, depth bits,
+     * row) order, culled rows (radii <= 0) last.  Emitting the intersections in this order leaves only the
+     * (image, tile) key bits for the S-sized sort -- same final order as the reference's one stable sort on
+     * (image, tile, depth).  rows = I*N, or N when image_ids (packed layout) is given. */
+    size_t gsb200_isect_depth_order_workspace_bytes(int64_t I, int64_t total_rows);
+    int gsb200_isect_depth_order(
+        int64_t I, int64_t N, const int32_t *radii, const float *depths, const int64_t *image_ids, int32_t *order,
+        void *workspace, size_t workspace_bytes, void *stream
+    );
+    /* Pass 1: tiles_per_gauss int32 [I*N] (row order) and the inclusive scan cum_tiles int64 [I*N] of the
+     * counts taken in `order` (NULL = row order).  conics + opacities given -> AccuTile/SNUGBOX ellipse test,
+     * else AABB from radii.  The caller reads cum_tiles[I*N-1] (= n_isects) to size the pass-2 outputs. */
     size_t gsb200_isect_scan_workspace_bytes(int64_t n_elements);
     int gsb200_isect_count(
         int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *conics,
-        const float *opacities, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+        const float *opacities, const int32_t *order, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
         int32_t *tiles_per_gauss, int64_t *cum_tiles, void *workspace, size_t workspace_bytes, void *stream
     );
-    /* Pass 2: unsorted isect_ids int64 [n_isects], flatten_ids int32 [n_isects].
-     * Packed layout (reference packed=True): pass image_ids int64 [N] (the image of each of the N rows);
-     * pass 1 is then called with I = 1. */
+    /* Pass 2: isect_ids int64 [n_isects], flatten_ids int32 [n_isects], emitted in `order` (NULL = row order,
+     * the reference's unsorted output).  Packed layout (reference packed=True): pass image_ids int64 [N]
+     * (the image of each of the N rows); pass 1 is then called with I = 1. */
     int gsb200_isect_emit(
         int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *depths, const float *conics,
-        const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids, uint32_t tile_size,
-        uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids, int32_t *flatten_ids, void *stream
+        const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids, const int32_t *order,
+        uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids, int32_t *flatten_ids,
+        void *stream
     );
-    /* Stable radix sort of (isect_ids, flatten_ids) on key bits [0, end_bit)
-     * (cub::DeviceRadixSort::SortPairs, csrc/IntersectTile.cu:1078-1121). */
-    size_t gsb200_sort_workspace_bytes(int64_t n_isects, int end_bit);
+    /* Stable radix sort of (isect_ids, flatten_ids) on key bits [begin_bit, end_bit)
+     * (cub::DeviceRadixSort::SortPairs, csrc/IntersectTile.cu:1078-1121); begin_bit = 32 after pass 0. */
+    size_t gsb200_sort_workspace_bytes(int64_t n_isects, int begin_bit, int end_bit);
     int gsb200_sort_pairs(
-        int64_t n_isects, int end_bit, const int64_t *keys_in, const int32_t *vals_in, int64_t *keys_out,
-        int32_t *vals_out, void *workspace, size_t workspace_bytes, void *stream
+        int64_t n_isects, int begin_bit, int end_bit, const int64_t *keys_in, const int32_t *vals_in,
+        int64_t *keys_out, int32_t *vals_out, void *workspace, size_t workspace_bytes, void *stream
     );
     /* ---- intersect_offset : ext.cpp:1027, _wrapper.py:1328-1347 ---- offsets int32 [I, th, tw]. */
     int gsb200_isect_offsets(
         int64_t n_isects, const int64_t *isect_ids, int64_t I, uint32_t tile_width, uint32_t tile_height,
         int32_t *offsets, void *stream
-    );
-
-    /* ---- tile-bucketed intersection: same four outputs as intersect_tile(sort=True) + intersect_offset
-     * (ext.cpp:1022-1027) without the global radix sort.  Used by rasterization().
-     *   1. bucket_count : tiles_per_gauss [I*N] + per-tile histogram tile_counts [I*T+1] + its exclusive scan
-     *                     offsets [I*T+1] (offsets[I*T] = n_isects; the first I*T entries ARE isect_offsets)
-     *   2. bucket_emit  : keys[n_isects] = depth_bits << 32 | flatten_id, dropped into the tile's segment
-     *                     (cursor [I*T] scratch)
-     *   3. segsort_keys : cub::DeviceSegmentedSort over the tile segments
-     *   4. bucket_finalize: isect_ids / flatten_ids in the reference's format and order. */
-    size_t gsb200_isect_bucket_scan_workspace_bytes(int64_t total_tiles);
-    int gsb200_isect_bucket_count(
-        int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *conics,
-        const float *opacities, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
-        int32_t *tiles_per_gauss, int32_t *tile_counts, int32_t *offsets, void *workspace, size_t workspace_bytes,
-        void *stream
-    );
-    int gsb200_isect_bucket_emit(
-        int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *depths, const float *conics,
-        const float *opacities, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
-        const int32_t *offsets, int32_t *cursor, uint64_t *keys, void *stream
-    );
-    size_t gsb200_segsort_workspace_bytes(int64_t n_items, int64_t n_segments);
-    int gsb200_segsort_keys(
-        int64_t n_items, int64_t n_segments, const int32_t *offsets, const uint64_t *keys_in, uint64_t *keys_out,
-        void *workspace, size_t workspace_bytes, void *stream
-    );
-    int gsb200_isect_bucket_finalize(
-        int64_t I, uint32_t tile_width, uint32_t tile_height, const int32_t *offsets, const uint64_t *keys_sorted,
-        int64_t *isect_ids, int32_t *flatten_ids, void *stream
     );
 
     /* ---- rasterize_to_pixels_3dgs / _bwd : ext.cpp:1079-1089, _wrapper.py:1497-1562, 2010-2117 ----

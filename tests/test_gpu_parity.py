@@ -232,8 +232,16 @@ def test_isect_accutile_exact_on_scene(gs):
     assert offn[0] == 0 and (np.diff(offn) >= 0).all() and offn[-1] <= len(ids)
 
 
-def test_isect_bucketed_equals_sorted_path(gs):
-    from gsplat_b200 import ops
+def test_isect_sorted_equals_stable_sort_of_unsorted(gs):
+    """The two-level sort (rows by depth, then intersections by (image, tile) bits only) must give exactly what
+    one stable sort of the reference's unsorted emission gives (csrc/Intersect.cpp:283-326)."""
+
+    def check(m2, radii, dep, tw, th, **kw):
+        a = gs.isect_tiles(_t(m2), _t(radii), _t(dep), 16, tw, th, **kw)
+        u = gs.isect_tiles(_t(m2), _t(radii), _t(dep), 16, tw, th, sort=False, **kw)
+        ids, perm = torch.sort(u[1], stable=True)
+        assert torch.equal(a[0], u[0]) and torch.equal(a[1], ids) and torch.equal(a[2], u[2][perm])
+        return a
 
     sc = scene.make_scene(n_max=80000)
     W, H = 800, 450
@@ -243,21 +251,29 @@ def test_isect_bucketed_equals_sorted_path(gs):
     tw, th = math.ceil(W / 16), math.ceil(H / 16)
     for accu in (True, False):
         kw = dict(conics=_t(con), opacities=_t(op)) if accu else {}
-        a = gs.isect_tiles(_t(m2), _t(radii), _t(dep), 16, tw, th, **kw)
-        off = gs.isect_offset_encode(a[1], 3, tw, th)
-        b = ops.isect_tiles_bucketed(_t(m2), _t(radii), _t(dep), 16, tw, th, **kw)
-        assert a[1].numel() > 10000
-        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(off, b[3])
+        assert check(m2, radii, dep, tw, th, **kw)[1].numel() > 10000
     # ties in depth inside a tile keep emit (gaussian index) order
     m2t = np.tile(np.array([[20.0, 20.0]], np.float32), (1, 64, 1))
-    r = np.full((1, 64, 2), 10, np.int32)
-    d = np.full((1, 64), 1.5, np.float32)
-    a = gs.isect_tiles(_t(m2t), _t(r), _t(d), 16, 4, 4)
-    b = ops.isect_tiles_bucketed(_t(m2t), _t(r), _t(d), 16, 4, 4)
-    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    a = check(m2t, np.full((1, 64, 2), 10, np.int32), np.full((1, 64), 1.5, np.float32), 4, 4)
+    assert (np.diff(_n(a[2]).reshape(-1, 64), axis=1) > 0).all()
+    # crowded tiles with heavy depth ties (depths quantised to 1/64), two images, some culled rows
+    rng = np.random.RandomState(3)
+    for n in (7000, 40000):
+        m2c = (rng.rand(2, n, 2) * 64).astype(np.float32)
+        rc = rng.randint(0, 80, size=(2, n, 2)).astype(np.int32)
+        rc[:, ::7] = 0
+        dc = (np.round(rng.rand(2, n) * 64) / 64 + 0.5).astype(np.float32)
+        check(m2c, rc, dc, 4, 4)
+    # packed rows with image ids
+    nnz = 5000
+    img = np.sort(rng.randint(0, 3, size=nnz)).astype(np.int64)
+    m2p = (rng.rand(nnz, 2) * 64).astype(np.float32)
+    rp = rng.randint(0, 30, size=(nnz, 2)).astype(np.int32)
+    dp = (np.round(rng.rand(nnz) * 16) / 16 + 0.5).astype(np.float32)
+    check(m2p, rp, dp, 4, 4, packed=True, n_images=3, image_ids=_t(img), gaussian_ids=_t(np.arange(nnz, dtype=np.int64)))
     # empty
-    e = ops.isect_tiles_bucketed(_t(np.zeros((1, 4, 2), np.float32)), _t(np.zeros((1, 4, 2), np.int32)), _t(np.ones((1, 4), np.float32)), 16, 3, 2)
-    assert e[1].numel() == 0 and (e[3] == 0).all()
+    e = gs.isect_tiles(_t(np.zeros((1, 4, 2), np.float32)), _t(np.zeros((1, 4, 2), np.int32)), _t(np.ones((1, 4), np.float32)), 16, 3, 2)
+    assert e[1].numel() == 0
 
 
 def _raster_case(gs, m2, con, col, op, W, H, off, fl, bg=None, absgrad=False, seed=0, strict_frac=0.995):

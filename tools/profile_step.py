@@ -72,7 +72,6 @@ if args.breakdown:
         ms_i, ir = t(lambda: ops.isect_tiles(m2, radii, dep, 16, tw, th, conics=con, opacities=op))
         ms_in, _ = t(lambda: ops.isect_tiles(m2, radii, dep, 16, tw, th, conics=con, opacities=op, sort=False))
         tpg, ids, fl = ir
-        ms_ib, _ = t(lambda: ops.isect_tiles_bucketed(m2, radii, dep, 16, tw, th, conics=con, opacities=op))
         ms_o, off = t(lambda: ops.isect_offset_encode(ids, 1, tw, th))
         ms_r, _ = t(lambda: ops.rasterize_to_pixels(m2, con, col, op, W, H, 16, off, fl))
     m2g, cong, colg, opg = (x.detach().clone().requires_grad_(True) for x in (m2, con, col, op))
@@ -90,5 +89,5 @@ if args.breakdown:
                                       g[2].data_ptr(), g[2].stride(-2), None, ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), stream())
     ms_pb, _ = t(pb)
     ms_step, _ = t(step, 10)
-    print(f"BREAKDOWN ms: project_sh_fwd {ms_p:.3f} | isect(count+scan+sync+emit+sort) {ms_i:.3f} (unsorted {ms_in:.3f}; bucketed incl. offsets {ms_ib:.3f}) | offsets {ms_o:.3f} | "
+    print(f"BREAKDOWN ms: project_sh_fwd {ms_p:.3f} | isect(order+count+scan+sync+emit+sort) {ms_i:.3f} (unsorted {ms_in:.3f}) | offsets {ms_o:.3f} | "
           f"raster_fwd(pack+raster) {ms_r:.3f} | raster_bwd(+memset) {ms_rb:.3f} | project_sh_bwd {ms_pb:.3f} | full step {ms_step:.3f}")
