@@ -43,7 +43,7 @@ def workload_config(n_gpus: int) -> dict:
         "workload": "BASELINE configs[2]: synthetic 1M Gaussians (test_garden crop tiled 3x3 = 1006065), "
         "1 view 1920x1080 per GPU, SH3, packed=False, near=0.01 far=1e10 eps2d=0.3",
         "step": "rasterization fwd + L1 loss + bwd to means/quats/scales/opacities/SH"
-        + (" + NCCL all-reduce of Gaussian grads" if n_gpus > 1 else ""),
+        + (" + all-reduce (SUM) of the Gaussian grads over NVLink" if n_gpus > 1 else ""),
         "views_per_step": n_gpus,
         "parallelism": f"view-axis DP x{n_gpus} (replicated Gaussians)" if n_gpus > 1 else "single GPU",
         "l2": "inputs (236 MB of Gaussian parameters + 25 MB target) exceed the 126 MB L2; no explicit flush",
@@ -262,6 +262,27 @@ def main():
     d2h_bytes = 4
     grad_names = ("means", "quats", "scales", "opacities", "sh")
 
+    # N > 1: the gradient all-reduce is our own kernel over NVSwitch peer memory (csrc/nvls.cu): the fused backward
+    # writes the gradients straight into a symmetric buffer, one launch reduces it in place on every rank.
+    # NCCL (coalesced, in place) is the fallback when the system has no symmetric / multicast memory.
+    arena, allreduce_kind = None, "none"
+    if world > 1:
+        allreduce_kind = "nccl (coalesced, in place)"
+        if os.environ.get("GSB200_ALLREDUCE", "own") != "nccl":
+            try:
+                arena = D.NvlsGradArena({k: params[k] for k in grad_names})
+                ops.set_gradient_allocator(arena.allocator)
+                allreduce_kind = f"own kernel over symmetric memory ({arena.algo}, {arena.blocks} blocks)"
+            except Exception as e:  # noqa: BLE001
+                if rank == 0:
+                    print(f"[bench] symmetric-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+
+    def all_reduce_grads():
+        if arena is not None:
+            arena.all_reduce()
+        else:
+            D.all_reduce_gaussian_grads([params[k] for k in grad_names], coalesced=True)
+
     # e2e input pipeline: every step's camera + target image are copied from pinned host memory inside
     # the timed region, double-buffered on a side stream so that the copy of step i+1 overlaps the compute
     # of step i (what a DataLoader with pin_memory + non_blocking does); step i waits for ITS copy.
@@ -293,9 +314,7 @@ def main():
         loss = (rc - tgt).abs().mean()
         loss.backward()
         if world > 1:
-            # the 59 floats / Gaussian in ONE coalesced NCCL launch, reduced in place in
-            # the gradient tensors (no staging copy)
-            D.all_reduce_gaussian_grads([params[k] for k in grad_names], coalesced=True)
+            all_reduce_grads()  # the 59 floats / Gaussian, one launch, in place
         if e2e:
             consumed[slot].record()
             loss_host.copy_(loss.detach(), non_blocking=True)
@@ -346,8 +365,8 @@ def main():
     # reference's way -- Gaussians sharded across ranks, projected rows exchanged by all-to-all, no all-reduce.
     dp_info = None
     if world > 1:
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        comp, comm = [], []
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        comp, comm, nccl = [], [], []
         for _ in range(5):
             dist.barrier()
             torch.cuda.synchronize()
@@ -360,14 +379,18 @@ def main():
             )
             (rc - target_dev).abs().mean().backward()
             ev[1].record()
-            D.all_reduce_gaussian_grads([params[k] for k in grad_names], coalesced=True)
+            all_reduce_grads()
             ev[2].record()
+            D.all_reduce_gaussian_grads([params[k] for k in grad_names], coalesced=True)  # NCCL on the same payload
+            ev[3].record()
             torch.cuda.synchronize()
             comp.append(ev[0].elapsed_time(ev[1]))
             comm.append(ev[1].elapsed_time(ev[2]))
-        mine = torch.tensor([sorted(comp)[2], sorted(comm)[2]], device=dev)
+            nccl.append(ev[2].elapsed_time(ev[3]))
+        mine = torch.tensor([sorted(comp)[2], sorted(comm)[2], sorted(nccl)[2]], device=dev)
         allr = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
+        ops.set_gradient_allocator(None)
         bounds = [int(round(i * N / world)) for i in range(world + 1)]
         shard = {k: params[k].detach()[bounds[rank] : bounds[rank + 1]].clone().requires_grad_(True) for k in params}
 
@@ -395,6 +418,8 @@ def main():
         dp_info = {
             "per_rank_compute_ms": [round(float(t[0]), 3) for t in allr],
             "per_rank_allreduce_ms": [round(float(t[1]), 3) for t in allr],
+            "per_rank_nccl_allreduce_ms": [round(float(t[2]), 3) for t in allr],
+            "allreduce": allreduce_kind,
             "allreduce_bytes_per_rank": int(sum(params[k].numel() for k in grad_names) * 4),
             "gaussian_sharded": {
                 "what": "same job with rasterization(distributed=True): Gaussians sharded, all-to-all of projected rows, no all-reduce",
@@ -468,7 +493,7 @@ def main():
             "metric": METRIC, "value": n_gpus * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(n_gpus),
+            "config": dict(workload_config(n_gpus), **({"allreduce": allreduce_kind} if n_gpus > 1 else {})),
             "e2e": {
                 "value": n_gpus * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
@@ -476,7 +501,7 @@ def main():
             # our own kernels per step: project_sh_fwd, depth_key, isect_count, isect_emit, isect_offsets,
             # pack_records, tile_order, raster_fwd, raster_bwd, project_sh_bwd (= 10; cub scan / radix-sort launches
             # made by the library are not counted); timed region = `steps` device-resident + `steps` e2e steps
-            "gpu_launches": args.steps * 2 * 10,
+            "gpu_launches": args.steps * 2 * (10 + (1 if arena is not None else 0)),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "ref_cuda": ref_cuda, "dp": dp_info,
         }
         print(json.dumps(line))

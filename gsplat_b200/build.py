@@ -24,6 +24,7 @@ UNITS = {
     "raster.cu": [],
     "pergauss.cu": ["-fmad=false"],
     "sort.cu": [],
+    "nvls.cu": [],
 }
 HEADERS = ["common.cuh", "gaussmath.cuh", os.path.join("..", "..", "include", "gsplat_b200.h")]
 

@@ -106,6 +106,84 @@ def all_reduce_gaussian_grads(
     return bucket
 
 
+class NvlsGradArena:
+    """The gradients of the replicated Gaussian parameters in ONE symmetric fp32 buffer (same layout on every
+    rank, bound to an NVSwitch multicast address) plus the in-place all-reduce over it done by our own kernel
+    (csrc/nvls.cu: in-switch ``multimem.ld_reduce`` + ``multimem.st``; include/gsplat_b200.h
+    gsb200_nvls_allreduce_f32).  Allocation / handle exchange is torch's symmetric-memory plumbing.
+
+        arena = NvlsGradArena({"means": means, "quats": quats, "scales": scales, "opacities": opac, "sh": sh})
+        ops.set_gradient_allocator(arena.allocator)      # the fused backward writes into the arena directly
+        loss.backward(); arena.all_reduce()              # p.grad are views of the arena afterwards
+
+    Raises RuntimeError when the GPUs have no multicast support (fall back to all_reduce_gaussian_grads)."""
+
+    ALIGN = 64  # floats (256 B) between segment starts
+
+    def __init__(self, named_params: Dict[str, Tensor], group=None, blocks: Optional[int] = None, algo: Optional[str] = None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from ._cabi import lib
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.params = dict(named_params)
+        self.blocks = int(os.environ.get("GSB200_NVLS_BLOCKS", "64")) if blocks is None else int(blocks)
+        dev = next(iter(self.params.values())).device
+        self.offsets, o = {}, 0
+        for k, p in self.params.items():
+            if p.dtype != torch.float32:
+                raise TypeError("NvlsGradArena holds float32 gradients")
+            self.offsets[k] = o
+            o += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = max(o, self.ALIGN)
+        need_pad = self.blocks * self.world * 4
+        if symm_mem.get_signal_pad_size() < need_pad:
+            symm_mem.set_signal_pad_size(need_pad)
+        self.flat = symm_mem.empty(self.numel, dtype=torch.float32, device=dev)
+        self.hdl = symm_mem.rendezvous(self.flat, self.group.group_name)
+        # world == 2: plain peer loads / stores move 1x the payload per direction, the multicast scheme 1.5x
+        self.algo = algo or os.environ.get("GSB200_ALLREDUCE_ALGO") or ("p2p" if self.world == 2 else "nvls")
+        if self.algo not in ("p2p", "nvls"):
+            raise ValueError(f"unknown all-reduce algorithm {self.algo!r}")
+        if self.algo == "nvls" and int(self.hdl.multicast_ptr) == 0:
+            raise RuntimeError("NvlsGradArena: no NVLS multicast support on this system")
+        if int(self.hdl.signal_pad_size) < need_pad:
+            raise RuntimeError("NvlsGradArena: signal pad too small for the requested number of blocks")
+        self.flat.zero_()
+        self.views = {k: self.flat[self.offsets[k] : self.offsets[k] + p.numel()].view(p.shape) for k, p in self.params.items()}
+        self._lib = lib()
+
+    def allocator(self, name: str, like: Tensor) -> Optional[Tensor]:
+        v = self.views.get(name)
+        # a FRESH tensor object over the arena segment: autograd adopts a gradient as .grad without copying only
+        # when nothing else references that tensor object
+        return v.detach() if v is not None and v.shape == like.shape else None
+
+    def all_reduce(self) -> None:
+        """Sums the .grad of all registered parameters over the ranks, in place in the arena."""
+        from ._cabi import check
+
+        for k, p in self.params.items():
+            v = self.views[k]
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)  # produced elsewhere (e.g. opacities): staged
+            p.grad = v
+        st = torch.cuda.current_stream().cuda_stream
+        pads, pad_bytes = int(self.hdl.signal_pad_ptrs_dev), int(self.hdl.signal_pad_size)
+        if self.algo == "nvls":
+            rc = self._lib.gsb200_nvls_allreduce_f32(
+                int(self.hdl.multicast_ptr), self.numel, self.rank, self.world, pads, pad_bytes, self.blocks, st
+            )
+        else:
+            rc = self._lib.gsb200_p2p_allreduce_f32(
+                int(self.hdl.buffer_ptrs_dev), self.numel, self.rank, self.world, pads, pad_bytes, self.blocks, st
+            )
+        check(rc, f"{self.algo}_allreduce")
+
+
 def render_views_dp(
     rasterize: Callable[..., tuple], gaussians: Dict[str, Tensor], viewmats: Tensor, Ks: Tensor, width: int, height: int,
     **kwargs,

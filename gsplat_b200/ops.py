@@ -365,6 +365,28 @@ def spherical_harmonics(
 # fused projection + conic + SH -> RGB (the rasterization() default path)
 
 
+# Where the fused backward puts the parameter gradients.  The view-parallel trainer registers the segments of its
+# symmetric (NVLS multicast) gradient buffer here, so that the backward kernel writes straight into the memory
+# the all-reduce kernel works on (gsplat_b200.distributed.NvlsGradArena) -- no staging copy.
+_grad_allocator = None
+
+
+def set_gradient_allocator(fn) -> None:
+    """fn(name, like) -> Tensor | None with name in {"means", "quats", "scales", "sh"}; None = default."""
+    global _grad_allocator
+    _grad_allocator = fn
+
+
+def _alloc_grad(name: str, like: Tensor) -> Tensor:
+    if _grad_allocator is not None:
+        t = _grad_allocator(name, like)
+        if t is not None:
+            if t.shape != like.shape or t.dtype != like.dtype or t.device != like.device or not t.is_contiguous():
+                raise RuntimeError(f"gradient allocator returned a mismatching tensor for {name!r}")
+            return t
+    return torch.empty_like(like)
+
+
 class _ProjectSH(torch.autograd.Function):
     @staticmethod
     def forward(
@@ -415,8 +437,8 @@ class _ProjectSH(torch.autograd.Function):
         v_conics, s_c = _rows(v_conics, 3, "v_conics")
         v_colors, s_col = _rows(v_colors, 3, "v_colors")
         v_comps = None if (v_comps is None or comps is None) else v_comps.contiguous()
-        v_means, v_quats, v_scales = torch.empty_like(means), torch.empty_like(quats), torch.empty_like(scales)
-        v_sh = torch.empty_like(sh_coeffs)
+        v_means, v_quats, v_scales = _alloc_grad("means", means), _alloc_grad("quats", quats), _alloc_grad("scales", scales)
+        v_sh = _alloc_grad("sh", sh_coeffs)
         with _Ctx(dev) as st:
             check(
                 lib().gsb200_project_sh_bwd(

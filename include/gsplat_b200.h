@@ -199,6 +199,25 @@ extern "C"
         const float *noise, float noise_scale, float t, float k, void *stream
     );
 
+    /* ---- view-parallel gradient all-reduce (replaces the NCCL all-reduce of
+     * gsplat_b200/distributed.py on NVSwitch systems) over NVLS multicast memory, in place.
+     * Every rank calls this on its stream with the SAME n_floats (multiple of 4) and `blocks`:
+     *   multicast_ptr   : multicast (all-GPU) address of the symmetric gradient buffer, 16-byte aligned
+     *   signal_pads_dev : device array of `world` pointers, entry r = rank r's signal pad (zero-initialised,
+     *                     peer-mapped; at least blocks * world * 4 bytes) -- used for the two rank barriers
+     * On return (stream order) every rank's buffer holds the element-wise sum over the ranks. */
+    int gsb200_nvls_allreduce_f32(
+        void *multicast_ptr, int64_t n_floats, int rank, int world, void *const *signal_pads_dev,
+        int64_t signal_pad_bytes, int blocks, void *stream
+    );
+    /* Same contract without the switch reduction (plain peer loads / stores over NVLink): buffers_dev = device
+     * array of `world` pointers, entry r = rank r's symmetric buffer.  Moves less than the multicast scheme
+     * only for world == 2. */
+    int gsb200_p2p_allreduce_f32(
+        void *const *buffers_dev, int64_t n_floats, int rank, int world, void *const *signal_pads_dev,
+        int64_t signal_pad_bytes, int blocks, void *stream
+    );
+
 #ifdef __cplusplus
 }
 #endif

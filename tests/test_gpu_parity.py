@@ -633,8 +633,7 @@ def test_distributed_single_rank_is_identity(gs):
     assert torch.equal(a, b) and torch.equal(aa, ba)
 
 
-def test_distributed_two_ranks_sharded():
-    """Launches tests/dist_sharded_check.py on 2 GPUs (skipped on a 1-GPU box)."""
+def _torchrun2(script, port):
     import subprocess
     import sys as _sys
 
@@ -643,8 +642,19 @@ def test_distributed_two_ranks_sharded():
     root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
     r = subprocess.run(
         [_sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-         "--master-port", "29588", os.path.join(root, "tests", "dist_sharded_check.py")],
+         "--master-port", str(port), os.path.join(root, "tests", script)],
         capture_output=True, text=True, timeout=600,
     )
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    assert r.stdout.count("sharded check ok") == 3
+    return r.stdout
+
+
+def test_distributed_two_ranks_sharded():
+    """Launches tests/dist_sharded_check.py on 2 GPUs (skipped on a 1-GPU box)."""
+    assert _torchrun2("dist_sharded_check.py", 29588).count("sharded check ok") == 3
+
+
+def test_nvls_allreduce_two_ranks():
+    """Own all-reduce kernels (multimem + peer-to-peer) vs NCCL, bit-exact at 2 ranks (skipped on a 1-GPU box)."""
+    out = _torchrun2("dist_nvls_check.py", 29590)
+    assert out.count("nvls check ok") == 7
