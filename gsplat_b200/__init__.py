@@ -6,6 +6,7 @@ rasterize_to_pixels, quat_scale_to_covar_preci.  Importing the package does not 
 operator does (and needs gsplat_b200/libgsplat_b200.so, built by ``python -m gsplat_b200.build``).
 """
 from .ops import (  # noqa: F401
+    adam,
     compute_relocation,
     mcmc_perturb_positions,
     fully_fused_projection,
@@ -16,6 +17,7 @@ from .ops import (  # noqa: F401
     rasterize_to_pixels,
     spherical_harmonics,
 )
+from .optimizers import SelectiveAdam  # noqa: F401
 from .rendering import rasterization  # noqa: F401
 
 __version__ = "0.1.0"
@@ -38,5 +40,7 @@ __all__ = [
     "quat_scale_to_covar_preci",
     "compute_relocation",
     "mcmc_perturb_positions",
+    "adam",
+    "SelectiveAdam",
     "has_3dgs",
 ]

@@ -206,6 +206,98 @@ __device__ __forceinline__ PerspJ persp_jacobian(const float *pc, const Cam &c, 
     return o;
 }
 
+// ---- orthographic / fisheye camera models (reference CameraModelType ids: 0 pinhole, 1 ortho, 2 fisheye;
+// include/Utils.cuh:498-526 ortho_proj, :692-731 fisheye_proj).  Dense 2x3 Jacobian, row-major.
+constexpr int kCamPinhole = 0, kCamOrtho = 1, kCamFisheye = 2;
+constexpr float kFisheyeEps = 0.0000001f;
+
+template<int CAM>
+__device__ __forceinline__ void dense_jacobian(const float *pc, const Cam &c, float *J, float &m2x, float &m2y)
+{
+    const float x = pc[0], y = pc[1], z = pc[2];
+    if constexpr(CAM == kCamOrtho)
+    {
+        J[0] = c.fx, J[1] = 0.f, J[2] = 0.f;
+        J[3] = 0.f, J[4] = c.fy, J[5] = 0.f;
+        m2x = c.fx * x + c.cx;
+        m2y = c.fy * y + c.cy;
+    }
+    else
+    {
+        const float xy_len = sqrtf(x * x + y * y) + kFisheyeEps;
+        const float theta  = atan2f(xy_len, z + kFisheyeEps);
+        m2x                = x * c.fx * theta / xy_len + c.cx;
+        m2y                = y * c.fy * theta / xy_len + c.cy;
+        const float x2 = x * x + kFisheyeEps, y2 = y * y, xy = x * y;
+        const float x2y2 = x2 + y2;
+        const float inv  = 1.f / (x2y2 + z * z);
+        const float b    = atan2f(xy_len, z) / xy_len / x2y2;
+        const float a    = z * inv / x2y2;
+        J[0] = c.fx * (x2 * a + y2 * b);
+        J[1] = c.fx * xy * (a - b);
+        J[2] = -c.fx * x * inv;
+        J[3] = c.fy * xy * (a - b);
+        J[4] = c.fy * (y2 * a + x2 * b);
+        J[5] = -c.fy * y * inv;
+    }
+}
+
+// Forward-mode dual number over (x, y, z): the fisheye Jacobian's own derivative is obtained by pushing
+// duals through the very expression dense_jacobian evaluates (the reference ships a hand-expanded closed
+// form, Utils.cuh:733-846; the CPU oracle restates that one, so the two derivations check each other).
+struct D3
+{
+    float v, dx, dy, dz;
+};
+__device__ __forceinline__ D3 d3(float v, float dx, float dy, float dz) { return D3{v, dx, dy, dz}; }
+__device__ __forceinline__ D3 operator+(const D3 &a, const D3 &b) { return d3(a.v + b.v, a.dx + b.dx, a.dy + b.dy, a.dz + b.dz); }
+__device__ __forceinline__ D3 operator-(const D3 &a, const D3 &b) { return d3(a.v - b.v, a.dx - b.dx, a.dy - b.dy, a.dz - b.dz); }
+__device__ __forceinline__ D3 operator+(const D3 &a, float s) { return d3(a.v + s, a.dx, a.dy, a.dz); }
+__device__ __forceinline__ D3 operator*(const D3 &a, const D3 &b)
+{
+    return d3(a.v * b.v, a.dx * b.v + a.v * b.dx, a.dy * b.v + a.v * b.dy, a.dz * b.v + a.v * b.dz);
+}
+__device__ __forceinline__ D3 operator*(float s, const D3 &a) { return d3(s * a.v, s * a.dx, s * a.dy, s * a.dz); }
+__device__ __forceinline__ D3 operator/(const D3 &a, const D3 &b)
+{
+    const float ib = 1.f / b.v, q = a.v * ib;
+    return d3(q, (a.dx - q * b.dx) * ib, (a.dy - q * b.dy) * ib, (a.dz - q * b.dz) * ib);
+}
+__device__ __forceinline__ D3 d3_sqrt(const D3 &a)
+{
+    const float r = sqrtf(a.v), h = r > 0.f ? 0.5f / r : 0.f; // on the optical axis the length has no gradient
+    return d3(r, h * a.dx, h * a.dy, h * a.dz);
+}
+__device__ __forceinline__ D3 d3_atan2(const D3 &p, const D3 &q)
+{
+    const float w = 1.f / (p.v * p.v + q.v * q.v);
+    return d3(atan2f(p.v, q.v), (q.v * p.dx - p.v * q.dx) * w, (q.v * p.dy - p.v * q.dy) * w, (q.v * p.dz - p.v * q.dz) * w);
+}
+
+// v_pc contribution of v_J through the fisheye Jacobian:  sum_k  dJ[k]/d{x,y,z} * v_J[k]
+__device__ __forceinline__ void fisheye_jacobian_vjp(const float *pc, const Cam &c, const float *v_J, float *v_pc)
+{
+    const D3 x = d3(pc[0], 1.f, 0.f, 0.f), y = d3(pc[1], 0.f, 1.f, 0.f), z = d3(pc[2], 0.f, 0.f, 1.f);
+    const D3 len  = d3_sqrt(x * x + y * y) + kFisheyeEps;
+    const D3 x2   = x * x + kFisheyeEps, y2 = y * y, xy = x * y;
+    const D3 x2y2 = x2 + y2;
+    const D3 r2   = x2y2 + z * z;
+    const D3 one  = d3(1.f, 0.f, 0.f, 0.f);
+    const D3 inv  = one / r2;
+    const D3 b    = d3_atan2(len, z) / len / x2y2;
+    const D3 a    = z * inv / x2y2;
+    const D3 amb  = a - b;
+    const D3 Jd[6] = {c.fx * (x2 * a + y2 * b), c.fx * (xy * amb), (-c.fx) * (x * inv),
+                      c.fy * (xy * amb), c.fy * (y2 * a + x2 * b), (-c.fy) * (y * inv)};
+#pragma unroll
+    for(int k = 0; k < 6; ++k)
+    {
+        v_pc[0] += Jd[k].dx * v_J[k];
+        v_pc[1] += Jd[k].dy * v_J[k];
+        v_pc[2] += Jd[k].dz * v_J[k];
+    }
+}
+
 struct Proj
 {
     int rx, ry; // 0,0 when culled
@@ -214,6 +306,7 @@ struct Proj
 
 // Forward projection of one (camera, gaussian).  cov = world covariance.
 // Reference: csrc/ProjectionEWA3DGSFused.cu:38-219.
+template<int CAM = kCamPinhole>
 __device__ __forceinline__ Proj project_one(
     const float *mean, const M3 &cov, const float *opacity, const Cam &cam, uint32_t W, uint32_t H, float eps2d,
     float near_plane, float far_plane, float radius_clip, bool comp_scales_opacity
@@ -229,20 +322,38 @@ __device__ __forceinline__ Proj project_one(
     if(pc[2] < near_plane || pc[2] > far_plane)
         return o;
     const M3 covc = mul_bt(mul(cam.R, cov), cam.R);
-    const PerspJ pj = persp_jacobian(pc, cam, W, H);
-    float T2[6];
-#pragma unroll
-    for(int j = 0; j < 3; ++j)
+    float c00, c01, c10, c11, m2x, m2y;
+    if constexpr(CAM == kCamPinhole)
     {
-        T2[j]     = pj.J00 * covc.m[0 * 3 + j] + pj.J02 * covc.m[2 * 3 + j];
-        T2[3 + j] = pj.J11 * covc.m[1 * 3 + j] + pj.J12 * covc.m[2 * 3 + j];
+        const PerspJ pj = persp_jacobian(pc, cam, W, H);
+        float T2[6];
+#pragma unroll
+        for(int j = 0; j < 3; ++j)
+        {
+            T2[j]     = pj.J00 * covc.m[0 * 3 + j] + pj.J02 * covc.m[2 * 3 + j];
+            T2[3 + j] = pj.J11 * covc.m[1 * 3 + j] + pj.J12 * covc.m[2 * 3 + j];
+        }
+        c00 = T2[0] * pj.J00 + T2[2] * pj.J02;
+        c01 = T2[1] * pj.J11 + T2[2] * pj.J12;
+        c10 = T2[3] * pj.J00 + T2[5] * pj.J02;
+        c11 = T2[4] * pj.J11 + T2[5] * pj.J12;
+        m2x = cam.fx * pc[0] * pj.rz + cam.cx;
+        m2y = cam.fy * pc[1] * pj.rz + cam.cy;
     }
-    float c00       = T2[0] * pj.J00 + T2[2] * pj.J02;
-    const float c01 = T2[1] * pj.J11 + T2[2] * pj.J12;
-    const float c10 = T2[3] * pj.J00 + T2[5] * pj.J02;
-    float c11       = T2[4] * pj.J11 + T2[5] * pj.J12;
-    const float m2x = cam.fx * pc[0] * pj.rz + cam.cx;
-    const float m2y = cam.fy * pc[1] * pj.rz + cam.cy;
+    else
+    {
+        float J[6], T2[6];
+        dense_jacobian<CAM>(pc, cam, J, m2x, m2y);
+#pragma unroll
+        for(int i = 0; i < 2; ++i)
+#pragma unroll
+            for(int j = 0; j < 3; ++j)
+                T2[i * 3 + j] = J[i * 3 + 0] * covc.m[0 * 3 + j] + J[i * 3 + 1] * covc.m[1 * 3 + j] + J[i * 3 + 2] * covc.m[2 * 3 + j];
+        c00 = T2[0] * J[0] + T2[1] * J[1] + T2[2] * J[2];
+        c01 = T2[0] * J[3] + T2[1] * J[4] + T2[2] * J[5];
+        c10 = T2[3] * J[0] + T2[4] * J[1] + T2[5] * J[2];
+        c11 = T2[3] * J[3] + T2[4] * J[4] + T2[5] * J[5];
+    }
 
     const float det_orig = c00 * c11 - c01 * c10;
     c00 += eps2d;
@@ -288,6 +399,7 @@ struct ProjGrad
 };
 
 // VJP of project_one for a visible gaussian.  Reference: csrc/ProjectionEWA3DGSFused.cu:376-638.
+template<int CAM = kCamPinhole>
 __device__ __forceinline__ ProjGrad project_one_vjp(
     const float *mean, const M3 &cov, const Cam &cam, uint32_t W, uint32_t H, float eps2d, const float *conic,
     float vm2x, float vm2y, float v_depth, const float *v_conic, bool has_comp, float comp, float v_comp
@@ -321,8 +433,19 @@ __device__ __forceinline__ ProjGrad project_one_vjp(
     for(int i = 0; i < 3; ++i)
         pc[i] = cam.R.m[i * 3 + 0] * mean[0] + cam.R.m[i * 3 + 1] * mean[1] + cam.R.m[i * 3 + 2] * mean[2] + cam.t[i];
     const M3 covc   = mul_bt(mul(cam.R, cov), cam.R);
-    const PerspJ pj = persp_jacobian(pc, cam, W, H);
-    const float J[6] = {pj.J00, 0.f, pj.J02, 0.f, pj.J11, pj.J12};
+    PerspJ pj;
+    float J[6];
+    if constexpr(CAM == kCamPinhole)
+    {
+        pj   = persp_jacobian(pc, cam, W, H);
+        J[0] = pj.J00, J[1] = 0.f, J[2] = pj.J02;
+        J[3] = 0.f, J[4] = pj.J11, J[5] = pj.J12;
+    }
+    else
+    {
+        float m2x_unused, m2y_unused;
+        dense_jacobian<CAM>(pc, cam, J, m2x_unused, m2y_unused);
+    }
     float JtG[6];
 #pragma unroll
     for(int i = 0; i < 3; ++i)
@@ -350,21 +473,32 @@ __device__ __forceinline__ ProjGrad project_one_vjp(
             v_J[i * 3 + j]
                 = (GJ[i * 3 + 0] * covc.m[j * 3 + 0] + GJ[i * 3 + 1] * covc.m[j * 3 + 1] + GJ[i * 3 + 2] * covc.m[j * 3 + 2])
                 + (GtJ[i * 3 + 0] * covc.m[0 * 3 + j] + GtJ[i * 3 + 1] * covc.m[1 * 3 + j] + GtJ[i * 3 + 2] * covc.m[2 * 3 + j]);
-    const float x = pc[0], y = pc[1];
-    const float rz = pj.rz, rz2 = pj.rz2, rz3 = rz2 * rz;
-    const float fx = cam.fx, fy = cam.fy;
-    g.v_pc[0] = fx * rz * vm2x;
-    g.v_pc[1] = fy * rz * vm2y;
-    g.v_pc[2] = -(fx * x * vm2x + fy * y * vm2y) * rz2;
-    if(pj.x_in)
-        g.v_pc[0] += -fx * rz2 * v_J[2];
+    if constexpr(CAM == kCamPinhole)
+    {
+        const float x = pc[0], y = pc[1];
+        const float rz = pj.rz, rz2 = pj.rz2, rz3 = rz2 * rz;
+        const float fx = cam.fx, fy = cam.fy;
+        g.v_pc[0] = fx * rz * vm2x;
+        g.v_pc[1] = fy * rz * vm2y;
+        g.v_pc[2] = -(fx * x * vm2x + fy * y * vm2y) * rz2;
+        if(pj.x_in)
+            g.v_pc[0] += -fx * rz2 * v_J[2];
+        else
+            g.v_pc[2] += -fx * rz3 * v_J[2] * pj.tx;
+        if(pj.y_in)
+            g.v_pc[1] += -fy * rz2 * v_J[5];
+        else
+            g.v_pc[2] += -fy * rz3 * v_J[5] * pj.ty;
+        g.v_pc[2] += -fx * rz2 * v_J[0] - fy * rz2 * v_J[4] + 2.f * fx * pj.tx * rz3 * v_J[2] + 2.f * fy * pj.ty * rz3 * v_J[5];
+    }
     else
-        g.v_pc[2] += -fx * rz3 * v_J[2] * pj.tx;
-    if(pj.y_in)
-        g.v_pc[1] += -fy * rz2 * v_J[5];
-    else
-        g.v_pc[2] += -fy * rz3 * v_J[5] * pj.ty;
-    g.v_pc[2] += -fx * rz2 * v_J[0] - fy * rz2 * v_J[4] + 2.f * fx * pj.tx * rz3 * v_J[2] + 2.f * fy * pj.ty * rz3 * v_J[5];
+    {
+#pragma unroll
+        for(int j = 0; j < 3; ++j)
+            g.v_pc[j] = J[0 * 3 + j] * vm2x + J[1 * 3 + j] * vm2y;
+        if constexpr(CAM == kCamFisheye)
+            fisheye_jacobian_vjp(pc, cam, v_J, g.v_pc);
+    }
     g.v_pc[2] += v_depth;
 #pragma unroll
     for(int j = 0; j < 3; ++j)

@@ -103,6 +103,7 @@ __device__ __forceinline__ M3 load_cov6(const float *c6)
     return S;
 }
 
+template<int CAM>
 __global__ void __launch_bounds__(kThreads) projection_fwd_kernel(
     int64_t B, int64_t C, int64_t N, const float *__restrict__ means, const float *__restrict__ covars,
     const float *__restrict__ quats, const float *__restrict__ scales, const float *__restrict__ opacities,
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kThreads) projection_fwd_kernel(
     float op = 0.f;
     if(opacities)
         op = opacities[bn];
-    const Proj p = project_one(
+    const Proj p = project_one<CAM>(
         mean, cov, opacities ? &op : nullptr, cam, W, H, eps2d, near_plane, far_plane, radius_clip, compensations != nullptr
     );
     reinterpret_cast<int2 *>(radii)[idx]    = make_int2(p.rx, p.ry);
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(kThreads) projection_fwd_kernel(
 
 // One thread per (b, n), looping over the C cameras: the per-gaussian sums stay in registers and
 // every output row is written exactly once (deterministic, no zero-init, no atomics).
+template<int CAM>
 __global__ void __launch_bounds__(kThreads) projection_bwd_kernel(
     int64_t B, int64_t C, int64_t N, const float *__restrict__ means, const float *__restrict__ covars,
     const float *__restrict__ quats, const float *__restrict__ scales, const float *__restrict__ viewmats,
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(kThreads) projection_bwd_kernel(
             const float conic[3] = {conics[idx * 3], conics[idx * 3 + 1], conics[idx * 3 + 2]};
             const float vc[3]    = {v_conics[idx * s_c], v_conics[idx * s_c + 1], v_conics[idx * s_c + 2]};
             const bool has_comp  = v_compensations != nullptr;
-            const ProjGrad g     = project_one_vjp(
+            const ProjGrad g     = project_one_vjp<CAM>(
                 mean, cov, cam, W, H, eps2d, conic, v_means2d[idx * s_m2], v_means2d[idx * s_m2 + 1], v_depths[idx * s_d],
                 vc, has_comp, has_comp ? compensations[idx] : 0.f, has_comp ? v_compensations[idx] : 0.f
             );
@@ -780,6 +782,26 @@ __global__ void __launch_bounds__(kThreads) mcmc_perturb_kernel(
     for(int r = 0; r < 3; ++r)
         positions[i * 3 + r] += cov.m[r * 3 + 0] * nz[0] + cov.m[r * 3 + 1] * nz[1] + cov.m[r * 3 + 2] * nz[2];
 }
+
+// Selective Adam step (no bias correction), in place; rows whose `valid` flag is 0 are left untouched
+// (reference: csrc/AdamCUDA.cu:34-70, gsplat/optimizers/selective_adam.py).  One thread per element.
+__global__ void __launch_bounds__(kThreads) adam_kernel(
+    int64_t total, int64_t D, float *__restrict__ param, const float *__restrict__ grad, float *__restrict__ exp_avg,
+    float *__restrict__ exp_avg_sq, const uint8_t *__restrict__ valid, float lr, float b1, float b2, float eps
+)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= total)
+        return;
+    if(valid != nullptr && !valid[i / D])
+        return;
+    const float g = grad[i];
+    const float m = b1 * exp_avg[i] + (1.0f - b1) * g;
+    const float v = b2 * exp_avg_sq[i] + (1.0f - b2) * g * g;
+    param[i] += -lr * m / (sqrtf(v) + eps);
+    exp_avg[i]    = m;
+    exp_avg_sq[i] = v;
+}
 } // namespace gsb
 
 // =====================================================================================================
@@ -822,7 +844,7 @@ extern "C" int gsb200_projection_fwd(
 {
     if(B < 0 || C < 0 || N < 0)
         return GSB200_E_INVALID;
-    if(camera_model != 0)
+    if(camera_model < 0 || camera_model > 2) // ftheta / lidar are other pipelines (3DGUT), not built
         return GSB200_E_UNSUPPORTED;
     const int64_t total = B * C * N;
     if(total == 0)
@@ -831,10 +853,18 @@ extern "C" int gsb200_projection_fwd(
         return GSB200_E_INVALID;
     if(!covars && (!quats || !scales))
         return GSB200_E_INVALID;
-    projection_fwd_kernel<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        B, C, N, means, covars, quats, scales, opacities, viewmats, Ks, image_width, image_height, eps2d, near_plane,
-        far_plane, radius_clip, radii, means2d, depths, conics, compensations
-    );
+#define GSB_LAUNCH(CAM)                                                                                                \
+    projection_fwd_kernel<CAM><<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(                        \
+        B, C, N, means, covars, quats, scales, opacities, viewmats, Ks, image_width, image_height, eps2d, near_plane,   \
+        far_plane, radius_clip, radii, means2d, depths, conics, compensations                                           \
+    )
+    if(camera_model == kCamPinhole)
+        GSB_LAUNCH(kCamPinhole);
+    else if(camera_model == kCamOrtho)
+        GSB_LAUNCH(kCamOrtho);
+    else
+        GSB_LAUNCH(kCamFisheye);
+#undef GSB_LAUNCH
     return check_launch();
 }
 
@@ -849,7 +879,7 @@ extern "C" int gsb200_projection_bwd(
 {
     if(B < 0 || C < 0 || N < 0)
         return GSB200_E_INVALID;
-    if(camera_model != 0)
+    if(camera_model < 0 || camera_model > 2)
         return GSB200_E_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if(v_viewmats && B * C > 0)
@@ -862,11 +892,19 @@ extern "C" int gsb200_projection_bwd(
         return GSB200_E_INVALID;
     if(v_compensations && !compensations)
         return GSB200_E_INVALID;
-    projection_bwd_kernel<<<grid_for(B * N, kThreads), kThreads, 0, st>>>(
-        B, C, N, means, covars, quats, scales, viewmats, Ks, image_width, image_height, eps2d, radii, conics,
-        compensations, v_means2d, v_means2d_stride, v_depths, v_depths_stride, v_conics, v_conics_stride,
-        v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats
-    );
+#define GSB_LAUNCH(CAM)                                                                                                \
+    projection_bwd_kernel<CAM><<<grid_for(B * N, kThreads), kThreads, 0, st>>>(                                          \
+        B, C, N, means, covars, quats, scales, viewmats, Ks, image_width, image_height, eps2d, radii, conics,           \
+        compensations, v_means2d, v_means2d_stride, v_depths, v_depths_stride, v_conics, v_conics_stride,               \
+        v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats                                               \
+    )
+    if(camera_model == kCamPinhole)
+        GSB_LAUNCH(kCamPinhole);
+    else if(camera_model == kCamOrtho)
+        GSB_LAUNCH(kCamOrtho);
+    else
+        GSB_LAUNCH(kCamFisheye);
+#undef GSB_LAUNCH
     return check_launch();
 }
 
@@ -1106,6 +1144,23 @@ extern "C" int gsb200_mcmc_perturb_positions(
         return GSB200_E_INVALID;
     mcmc_perturb_kernel<<<grid_for(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         N, positions, quats, scales_log, opacities_logit, noise, noise_scale, t, k
+    );
+    return check_launch();
+}
+
+extern "C" int gsb200_adam(
+    int64_t N, int64_t D, float *param, const float *param_grad, float *exp_avg, float *exp_avg_sq, const uint8_t *valid,
+    float lr, float b1, float b2, float eps, void *stream
+)
+{
+    if(N < 0 || D < 0)
+        return GSB200_E_INVALID;
+    if(N * D == 0)
+        return GSB200_OK;
+    if(!param || !param_grad || !exp_avg || !exp_avg_sq)
+        return GSB200_E_INVALID;
+    adam_kernel<<<grid_for(N * D, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        N * D, D, param, param_grad, exp_avg, exp_avg_sq, valid, lr, b1, b2, eps
     );
     return check_launch();
 }

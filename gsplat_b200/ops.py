@@ -80,12 +80,12 @@ def _camera_model_id(camera_model: str) -> int:
     table = {"pinhole": 0, "ortho": 1, "fisheye": 2, "ftheta": 3, "lidar": 4}
     if camera_model not in table:
         raise ValueError(f"unknown camera_model {camera_model!r}")
-    if camera_model != "pinhole":
+    if camera_model not in ("pinhole", "ortho", "fisheye"):
         raise NotImplementedError(
-            f"camera_model={camera_model!r}: only the pinhole EWA projection is built in gsplat_b200 "
-            "(reference: csrc/ProjectionEWA3DGSFused.cu:135-147)"
+            f"camera_model={camera_model!r}: the EWA projection is built for pinhole / ortho / fisheye "
+            "(reference: csrc/ProjectionEWA3DGSFused.cu:135-147); ftheta and lidar belong to the 3DGUT pipeline"
         )
-    return 0
+    return table[camera_model]
 
 
 # --------------------------------------------------------------------------------------------
@@ -785,4 +785,38 @@ def mcmc_perturb_positions(
                 float(t), float(k), st,
             ),
             "mcmc_perturb_positions",
+        )
+
+
+@torch.no_grad()
+def adam(
+    param: Tensor, param_grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, valid: Optional[Tensor], lr: float, b1: float,
+    b2: float, eps: float,
+) -> None:
+    """Selective Adam step, in place on ``param`` / ``exp_avg`` / ``exp_avg_sq`` ([N, ...]); rows with
+    ``valid[n] == False`` keep their value and their moments (/root/reference/gsplat/cuda/_wrapper.py:419-432,
+    csrc/AdamCUDA.cu:34-70; no bias correction, like the reference)."""
+    dev = require_cuda(param, param_grad, exp_avg, exp_avg_sq)
+    for name, t in (("param", param), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous float32 tensor (updated in place)")
+        if t.shape != param.shape:
+            raise ValueError(f"{name} must have the shape of param")
+    if param_grad.shape != param.shape:
+        raise ValueError("param_grad must have the shape of param")
+    param_grad = f32c(param_grad, "param_grad")
+    N = param.shape[0] if param.dim() > 0 else 1
+    D = param.numel() // max(N, 1)
+    vmask = None
+    if valid is not None:
+        if valid.numel() != N:
+            raise ValueError(f"valid must have {N} entries, got {valid.numel()}")
+        vmask = valid.to(device=dev, dtype=torch.bool).contiguous()
+    with _Ctx(dev) as st:
+        check(
+            lib().gsb200_adam(
+                N, D, ptr(param), ptr(param_grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(vmask), float(lr), float(b1), float(b2),
+                float(eps), st,
+            ),
+            "adam",
         )

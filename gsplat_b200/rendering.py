@@ -101,8 +101,8 @@ def rasterization(
         _unsupported("return_normals")
     if rolling_shutter is not None and getattr(rolling_shutter, "name", str(rolling_shutter)) not in ("GLOBAL", "RollingShutterType.GLOBAL"):
         _unsupported("rolling_shutter")
-    if camera_model != "pinhole":
-        _unsupported(f"camera_model={camera_model!r}", "only the pinhole EWA projection is built")
+    if camera_model not in ("pinhole", "ortho", "fisheye"):
+        _unsupported(f"camera_model={camera_model!r}", "the EWA projection is built for pinhole / ortho / fisheye")
     if render_mode not in _ALL_MODES:
         raise ValueError(f"unknown render_mode {render_mode!r}")
     if render_mode in _HIT_DISTANCE_MODES:
@@ -186,7 +186,7 @@ def rasterization(
     # ---- projection (+ SH): fused single pass when it applies
     fused = (
         has_color and sh_degree is not None and covars is None and nb == 0 and colors.shape[-1] == 3
-        and not viewmats.requires_grad
+        and not viewmats.requires_grad and camera_model == "pinhole"
     )
     if fused:
         radii, means2d, depths, conics, feat, compensations = fused_project_sh(

@@ -199,6 +199,13 @@ extern "C"
         const float *noise, float noise_scale, float t, float k, void *stream
     );
 
+    /* ---- `adam` (ext.cpp, _wrapper.py:419-432, csrc/AdamCUDA.cu:34-70): selective Adam step in place on
+     * param / exp_avg / exp_avg_sq [N, D]; rows with valid[n] == 0 (bool bytes, or NULL = all) are skipped. */
+    int gsb200_adam(
+        int64_t N, int64_t D, float *param, const float *param_grad, float *exp_avg, float *exp_avg_sq,
+        const uint8_t *valid, float lr, float b1, float b2, float eps, void *stream
+    );
+
     /* ---- view-parallel gradient all-reduce (replaces the NCCL all-reduce of
      * gsplat_b200/distributed.py on NVSwitch systems) over NVLS multicast memory, in place.
      * Every rank calls this on its stream with the SAME n_floats (multiple of 4) and `blocks`:

@@ -47,6 +47,7 @@ def main():
     incf = [f"-I{p}" for p in inc]
     defs = [
         "-DTORCH_EXTENSION_NAME=gsplat_ref", "-DTORCH_API_INCLUDE_EXTENSION_H", "-DNDEBUG", "-DGSPLAT_BUILD_3DGS=1",
+        "-DGSPLAT_BUILD_ADAM=1", "-DGSPLAT_BUILD_RELOC=1",
         f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
     ]
     cxx = ["/usr/bin/g++", "-std=c++20", "-O3", "-fPIC", "-Wno-attributes", "-Wno-unknown-pragmas", "-w",

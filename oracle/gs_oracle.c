@@ -25,6 +25,7 @@
 #define R_CEIL ceilf
 #define R_FLOOR floorf
 #define R_FREXP frexpf
+#define R_ATAN2 atan2f
 #include "gso_impl.h"
 #undef REAL
 #undef SUF
@@ -33,6 +34,7 @@
 #undef R_CEIL
 #undef R_FLOOR
 #undef R_FREXP
+#undef R_ATAN2
 
 /* ---- float64 instantiation: *_f64 ---- */
 #define REAL double
@@ -42,6 +44,7 @@
 #define R_CEIL ceil
 #define R_FLOOR floor
 #define R_FREXP frexp
+#define R_ATAN2 atan2
 #include "gso_impl.h"
 #undef REAL
 #undef SUF

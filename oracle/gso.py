@@ -107,12 +107,15 @@ def _bcn(means, viewmats):
     return batch, B, viewmats.shape[-3], means.shape[-2]
 
 
+CAMERA_MODELS = {"pinhole": 0, "ortho": 1, "fisheye": 2}  # reference CameraModelType, ext.cpp:58-64
+
+
 def fully_fused_projection(
     means, covars, quats, scales, viewmats, Ks, width, height, eps2d=0.3, near_plane=0.01, far_plane=1e10,
     radius_clip=0.0, calc_compensations=False, camera_model="pinhole", opacities=None,
 ):
     """Dense (packed=False) projection.  covars: [..., N, 6] triu or None."""
-    assert camera_model == "pinhole"
+    cam_id = CAMERA_MODELS[camera_model]
     suf, dt, cr = _suf(means)
     batch, B, C, N = _bcn(means, viewmats)
     means, covars, quats, scales = _c(means, dt), _c(covars, dt), _c(quats, dt), _c(scales, dt)
@@ -125,7 +128,7 @@ def fully_fused_projection(
     rc = getattr(lib(), "gso_projection_fwd" + suf)(
         ctypes.c_int64(B), ctypes.c_int64(C), ctypes.c_int64(N), _p(means), _p(covars), _p(quats), _p(scales),
         _p(opacities), _p(viewmats), _p(Ks), ctypes.c_uint32(width), ctypes.c_uint32(height), cr(eps2d),
-        cr(near_plane), cr(far_plane), cr(radius_clip), ctypes.c_int(0), _p(radii), _p(means2d), _p(depths),
+        cr(near_plane), cr(far_plane), cr(radius_clip), ctypes.c_int(cam_id), _p(radii), _p(means2d), _p(depths),
         _p(conics), _p(comps),
     )
     assert rc == 0
@@ -134,7 +137,7 @@ def fully_fused_projection(
 
 def fully_fused_projection_bwd(
     means, covars, quats, scales, viewmats, Ks, width, height, eps2d, radii, conics, compensations,
-    v_means2d, v_depths, v_conics, v_compensations=None, viewmats_requires_grad=False,
+    v_means2d, v_depths, v_conics, v_compensations=None, viewmats_requires_grad=False, camera_model="pinhole",
 ):
     suf, dt, cr = _suf(means)
     batch, B, C, N = _bcn(means, viewmats)
@@ -150,7 +153,8 @@ def fully_fused_projection_bwd(
     v_viewmats = np.empty_like(viewmats) if viewmats_requires_grad else None
     rc = getattr(lib(), "gso_projection_bwd" + suf)(
         ctypes.c_int64(B), ctypes.c_int64(C), ctypes.c_int64(N), _p(means), _p(covars), _p(quats), _p(scales),
-        _p(viewmats), _p(Ks), ctypes.c_uint32(width), ctypes.c_uint32(height), cr(eps2d), ctypes.c_int(0), _p(radii),
+        _p(viewmats), _p(Ks), ctypes.c_uint32(width), ctypes.c_uint32(height), cr(eps2d),
+        ctypes.c_int(CAMERA_MODELS[camera_model]), _p(radii),
         _p(conics), _p(compensations), _p(v_means2d), _p(v_depths), _p(v_conics), _p(v_compensations), _p(v_means),
         _p(v_covars), _p(v_quats), _p(v_scales), _p(v_viewmats),
     )
@@ -401,3 +405,18 @@ def mcmc_perturb_positions(positions, quats, scales_log, opacities_logit, noise,
     w = (1.0 / (1.0 + np.exp(k * (dens - t)))) * noise_scale
     nz = noise.astype(dt) * w[:, None]
     return positions + np.einsum("nij,nj->ni", cov, nz)
+
+
+def adam(param, grad, exp_avg, exp_avg_sq, valid, lr, b1, b2, eps):
+    """Selective Adam step without bias correction; returns the new (param, exp_avg, exp_avg_sq).
+    Reference: csrc/AdamCUDA.cu:34-70 (m = b1 m + (1-b1) g; v = b2 v + (1-b2) g g; p += -lr m / (sqrt(v) + eps);
+    rows with valid == False untouched).  Every operation is carried out in the array dtype, in the kernel's order."""
+    dt = param.dtype.type
+    lr, b1, b2, eps = dt(lr), dt(b1), dt(b2), dt(eps)
+    m = b1 * exp_avg + (dt(1.0) - b1) * grad
+    v = b2 * exp_avg_sq + (dt(1.0) - b2) * grad * grad
+    p = param + (-lr * m / (np.sqrt(v) + eps))
+    if valid is not None:
+        keep = ~np.asarray(valid, bool).reshape((-1,) + (1,) * (param.ndim - 1))
+        p, m, v = np.where(keep, param, p), np.where(keep, exp_avg, m), np.where(keep, exp_avg_sq, v)
+    return p.astype(param.dtype), m.astype(param.dtype), v.astype(param.dtype)

@@ -291,12 +291,85 @@ static inline FN(PerspJ) FN(persp_jacobian)(const REAL *pc, REAL fx, REAL fy, RE
     return o;
 }
 
+/* Orthographic and fisheye camera models: dense 2x3 Jacobian J (row-major) + projected mean.
+ * Reference: include/Utils.cuh:498-526 (ortho_proj), :692-731 (fisheye_proj).  camera_model ids follow
+ * the reference's CameraModelType (ext.cpp:58-64): 0 pinhole, 1 ortho, 2 fisheye. */
+static inline void FN(ortho_fisheye_jacobian)(int camera_model, const REAL *pc, REAL fx, REAL fy, REAL cx, REAL cy, REAL *J, REAL *m2)
+{
+    REAL x = pc[0], y = pc[1], z = pc[2];
+    if(camera_model == 1)
+    {
+        J[0] = fx; J[1] = 0; J[2] = 0;
+        J[3] = 0; J[4] = fy; J[5] = 0;
+        m2[0] = fx * x + cx;
+        m2[1] = fy * y + cy;
+        return;
+    }
+    const REAL eps = (REAL)0.0000001;
+    REAL xy_len = R_SQRT(x * x + y * y) + eps;
+    REAL theta  = R_ATAN2(xy_len, z + eps);
+    m2[0]       = x * fx * theta / xy_len + cx;
+    m2[1]       = y * fy * theta / xy_len + cy;
+    REAL x2 = x * x + eps, y2 = y * y, xy = x * y;
+    REAL x2y2 = x2 + y2;
+    REAL inv  = (REAL)1 / (x2y2 + z * z);
+    REAL b    = R_ATAN2(xy_len, z) / xy_len / x2y2;
+    REAL a    = z * inv / x2y2;
+    J[0] = fx * (x2 * a + y2 * b);
+    J[1] = fx * xy * (a - b);
+    J[2] = -fx * x * inv;
+    J[3] = fy * xy * (a - b);
+    J[4] = fy * (y2 * a + x2 * b);
+    J[5] = -fy * y * inv;
+}
+
+/* v_pc (camera-space mean gradient) of the two models given v_mean2d and v_J (2x3, row-major).
+ * Reference: Utils.cuh:528-565 (ortho_proj_vjp), :733-846 (fisheye_proj_vjp: the closed-form dJ/d{x,y,z}). */
+static inline void FN(ortho_fisheye_vjp)(
+    int camera_model, const REAL *pc, REAL fx, REAL fy, const REAL *J, const REAL *vm2, const REAL *v_J, REAL *v_pc
+)
+{
+    for(int j = 0; j < 3; ++j)
+        v_pc[j] = J[0 * 3 + j] * vm2[0] + J[1 * 3 + j] * vm2[1];
+    if(camera_model == 1)
+        return;
+    REAL x = pc[0], y = pc[1], z = pc[2];
+    const REAL eps = (REAL)0.0000001;
+    REAL x2 = x * x + eps, y2 = y * y, xy = x * y;
+    REAL x2y2 = x2 + y2;
+    REAL len  = R_SQRT(x * x + y * y) + eps;
+    REAL r2   = x2y2 + z * z; /* squared distance */
+    REAL ir2  = (REAL)1 / r2;
+    REAL theta = R_ATAN2(len, z);
+    REAL l4 = r2 * r2;
+    REAL E  = -l4 * x2y2 * theta + r2 * x2y2 * len * z;
+    REAL F  = (REAL)3 * l4 * theta - (REAL)3 * r2 * len * z - (REAL)2 * x2y2 * len * z;
+    REAL pA = x * ((REAL)3 * E + x2 * F), pB = y * (E + x2 * F), pC = x * (E + y2 * F), pD = y * ((REAL)3 * E + y2 * F);
+    REAL S1 = x2 - y2 - z * z, S2 = y2 - x2 - z * z;
+    REAL inv1 = ir2 * ir2;
+    REAL inv2 = inv1 / (x2y2 * x2y2 * len);
+    /* d J[r][c] / d {x, y, z}, rows r = 0 (fx) and 1 (fy) */
+    REAL dx[6] = {fx * pA * inv2, fx * pB * inv2, fx * S1 * inv1, fy * pB * inv2, fy * pC * inv2, (REAL)2 * fy * xy * inv1};
+    REAL dy[6] = {dx[1], fx * pC * inv2, (REAL)2 * fx * xy * inv1, dx[4], fy * pD * inv2, fy * S2 * inv1};
+    REAL dz[6] = {dx[2], dy[2], (REAL)2 * fx * x * z * inv1, dx[5], dy[5], (REAL)2 * fy * y * z * inv1};
+    REAL gx = 0, gy = 0, gz = 0;
+    for(int k = 0; k < 6; ++k)
+    {
+        gx += dx[k] * v_J[k];
+        gy += dy[k] * v_J[k];
+        gz += dz[k] * v_J[k];
+    }
+    v_pc[0] += gx;
+    v_pc[1] += gy;
+    v_pc[2] += gz;
+}
+
 /* Forward of one (camera, gaussian).  Returns 0 if culled (radii = 0).
  * Reference: csrc/ProjectionEWA3DGSFused.cu:38-219. */
 static inline int FN(project_one)(
     const REAL *mean, const REAL *covar6, const REAL *quat, const REAL *scale, const REAL *opacity, const REAL *vm,
     const REAL *K, uint32_t W, uint32_t H, REAL eps2d, REAL near_plane, REAL far_plane, REAL radius_clip, int want_comp,
-    int32_t *radii, REAL *mean2d, REAL *depth, REAL *conic, REAL *comp
+    int camera_model, int32_t *radii, REAL *mean2d, REAL *depth, REAL *conic, REAL *comp
 )
 {
     REAL Rv[9] = {vm[0], vm[1], vm[2], vm[4], vm[5], vm[6], vm[8], vm[9], vm[10]};
@@ -325,20 +398,38 @@ static inline int FN(project_one)(
     FN(mat3_mul_bt)(T, Rv, covc);
 
     REAL fx = K[0], fy = K[4], cx = K[2], cy = K[5];
-    FN(PerspJ) pj = FN(persp_jacobian)(pc, fx, fy, cx, cy, W, H);
-    /* T2 = J * covc (2x3) ; cov2d = T2 * J^T */
-    REAL T2[6];
-    for(int j = 0; j < 3; ++j)
+    REAL c00, c01, c10, c11, m2x, m2y;
+    if(camera_model == 0)
     {
-        T2[0 * 3 + j] = pj.J00 * covc[0 * 3 + j] + pj.J02 * covc[2 * 3 + j];
-        T2[1 * 3 + j] = pj.J11 * covc[1 * 3 + j] + pj.J12 * covc[2 * 3 + j];
+        FN(PerspJ) pj = FN(persp_jacobian)(pc, fx, fy, cx, cy, W, H);
+        /* T2 = J * covc (2x3) ; cov2d = T2 * J^T */
+        REAL T2[6];
+        for(int j = 0; j < 3; ++j)
+        {
+            T2[0 * 3 + j] = pj.J00 * covc[0 * 3 + j] + pj.J02 * covc[2 * 3 + j];
+            T2[1 * 3 + j] = pj.J11 * covc[1 * 3 + j] + pj.J12 * covc[2 * 3 + j];
+        }
+        c00 = T2[0] * pj.J00 + T2[2] * pj.J02;
+        c01 = T2[1] * pj.J11 + T2[2] * pj.J12;
+        c10 = T2[3] * pj.J00 + T2[5] * pj.J02;
+        c11 = T2[4] * pj.J11 + T2[5] * pj.J12;
+        m2x = fx * pc[0] * pj.rz + cx;
+        m2y = fy * pc[1] * pj.rz + cy;
     }
-    REAL c00 = T2[0] * pj.J00 + T2[2] * pj.J02;
-    REAL c01 = T2[1] * pj.J11 + T2[2] * pj.J12;
-    REAL c10 = T2[3] * pj.J00 + T2[5] * pj.J02;
-    REAL c11 = T2[4] * pj.J11 + T2[5] * pj.J12;
-    REAL m2x = fx * pc[0] * pj.rz + cx;
-    REAL m2y = fy * pc[1] * pj.rz + cy;
+    else
+    {
+        REAL J[6], m2[2], T2[6];
+        FN(ortho_fisheye_jacobian)(camera_model, pc, fx, fy, cx, cy, J, m2);
+        for(int i = 0; i < 2; ++i)
+            for(int j = 0; j < 3; ++j)
+                T2[i * 3 + j] = J[i * 3 + 0] * covc[0 * 3 + j] + J[i * 3 + 1] * covc[1 * 3 + j] + J[i * 3 + 2] * covc[2 * 3 + j];
+        c00 = T2[0] * J[0] + T2[1] * J[1] + T2[2] * J[2];
+        c01 = T2[0] * J[3] + T2[1] * J[4] + T2[2] * J[5];
+        c10 = T2[3] * J[0] + T2[4] * J[1] + T2[5] * J[2];
+        c11 = T2[3] * J[3] + T2[4] * J[4] + T2[5] * J[5];
+        m2x = m2[0];
+        m2y = m2[1];
+    }
 
     /* add_blur: Utils.cuh:455-463 */
     REAL det_orig = c00 * c11 - c01 * c10;
@@ -389,7 +480,7 @@ static inline int FN(project_one)(
  * quats [B,N,4], scales [B,N,3], opacities [B,N] or NULL, viewmats [B,C,4,4],
  * Ks [B,C,3,3]; outputs [B,C,N,*]; culled rows of the float outputs are set to 0
  * (the reference leaves them uninitialised, csrc/Projection.cpp:395-404).
- * camera_model must be 0 (pinhole). */
+ * camera_model: 0 pinhole, 1 ortho, 2 fisheye. */
 int FN(gso_projection_fwd)(
     int64_t B, int64_t C, int64_t N, const REAL *means, const REAL *covars, const REAL *quats, const REAL *scales,
     const REAL *opacities, const REAL *viewmats, const REAL *Ks, uint32_t W, uint32_t H, REAL eps2d, REAL near_plane,
@@ -397,7 +488,7 @@ int FN(gso_projection_fwd)(
     REAL *compensations
 )
 {
-    if(camera_model != 0)
+    if(camera_model < 0 || camera_model > 2)
         return -1;
 #pragma omp parallel for schedule(static)
     for(int64_t idx = 0; idx < B * C * N; ++idx)
@@ -408,7 +499,7 @@ int FN(gso_projection_fwd)(
             means + (b * N + n) * 3, covars ? covars + (b * N + n) * 6 : NULL, quats ? quats + (b * N + n) * 4 : NULL,
             scales ? scales + (b * N + n) * 3 : NULL, opacities ? opacities + (b * N + n) : NULL,
             viewmats + (b * C + c) * 16, Ks + (b * C + c) * 9, W, H, eps2d, near_plane, far_plane, radius_clip,
-            compensations != NULL, radii + idx * 2, m2, &d, cn, &cp
+            compensations != NULL, camera_model, radii + idx * 2, m2, &d, cn, &cp
         );
         means2d[idx * 2] = m2[0];
         means2d[idx * 2 + 1] = m2[1];
@@ -433,7 +524,7 @@ int FN(gso_projection_bwd)(
     const REAL *v_compensations, REAL *v_means, REAL *v_covars, REAL *v_quats, REAL *v_scales, REAL *v_viewmats
 )
 {
-    if(camera_model != 0)
+    if(camera_model < 0 || camera_model > 2)
         return -1;
     memset(v_means, 0, sizeof(REAL) * (size_t)(B * N * 3));
     if(v_covars)
@@ -498,8 +589,19 @@ int FN(gso_projection_bwd)(
         FN(mat3_mul_bt)(T, Rv, covc);
 
         REAL fx = K[0], fy = K[4], cx = K[2], cy = K[5];
-        FN(PerspJ) pj = FN(persp_jacobian)(pc, fx, fy, cx, cy, W, H);
-        REAL J[6] = {pj.J00, 0, pj.J02, 0, pj.J11, pj.J12};
+        FN(PerspJ) pj;
+        REAL J[6], m2_unused[2];
+        if(camera_model == 0)
+        {
+            pj   = FN(persp_jacobian)(pc, fx, fy, cx, cy, W, H);
+            J[0] = pj.J00; J[1] = 0; J[2] = pj.J02;
+            J[3] = 0; J[4] = pj.J11; J[5] = pj.J12;
+        }
+        else
+        {
+            memset(&pj, 0, sizeof(pj));
+            FN(ortho_fisheye_jacobian)(camera_model, pc, fx, fy, cx, cy, J, m2_unused);
+        }
         /* v_covc = J^T vS J */
         REAL JtG[6]; /* 3x2 = J^T (3x2) * vS (2x2) */
         for(int i = 0; i < 3; ++i)
@@ -521,23 +623,31 @@ int FN(gso_projection_bwd)(
             for(int j = 0; j < 3; ++j)
                 v_J[i * 3 + j] = (GJ[i * 3 + 0] * covc[j * 3 + 0] + GJ[i * 3 + 1] * covc[j * 3 + 1] + GJ[i * 3 + 2] * covc[j * 3 + 2])
                                + (GtJ[i * 3 + 0] * covc[0 * 3 + j] + GtJ[i * 3 + 1] * covc[1 * 3 + j] + GtJ[i * 3 + 2] * covc[2 * 3 + j]);
-        REAL x = pc[0], y = pc[1];
-        REAL rz = pj.rz, rz2 = pj.rz2, rz3 = rz2 * rz;
         REAL vm2x = v_means2d[idx * 2], vm2y = v_means2d[idx * 2 + 1];
         REAL v_pc[3];
-        v_pc[0] = fx * rz * vm2x;
-        v_pc[1] = fy * rz * vm2y;
-        v_pc[2] = -(fx * x * vm2x + fy * y * vm2y) * rz2;
-        if(pj.x_in)
-            v_pc[0] += -fx * rz2 * v_J[0 * 3 + 2];
+        if(camera_model == 0)
+        {
+            REAL x = pc[0], y = pc[1];
+            REAL rz = pj.rz, rz2 = pj.rz2, rz3 = rz2 * rz;
+            v_pc[0] = fx * rz * vm2x;
+            v_pc[1] = fy * rz * vm2y;
+            v_pc[2] = -(fx * x * vm2x + fy * y * vm2y) * rz2;
+            if(pj.x_in)
+                v_pc[0] += -fx * rz2 * v_J[0 * 3 + 2];
+            else
+                v_pc[2] += -fx * rz3 * v_J[0 * 3 + 2] * pj.tx;
+            if(pj.y_in)
+                v_pc[1] += -fy * rz2 * v_J[1 * 3 + 2];
+            else
+                v_pc[2] += -fy * rz3 * v_J[1 * 3 + 2] * pj.ty;
+            v_pc[2] += -fx * rz2 * v_J[0] - fy * rz2 * v_J[1 * 3 + 1] + (REAL)2 * fx * pj.tx * rz3 * v_J[0 * 3 + 2]
+                     + (REAL)2 * fy * pj.ty * rz3 * v_J[1 * 3 + 2];
+        }
         else
-            v_pc[2] += -fx * rz3 * v_J[0 * 3 + 2] * pj.tx;
-        if(pj.y_in)
-            v_pc[1] += -fy * rz2 * v_J[1 * 3 + 2];
-        else
-            v_pc[2] += -fy * rz3 * v_J[1 * 3 + 2] * pj.ty;
-        v_pc[2] += -fx * rz2 * v_J[0] - fy * rz2 * v_J[1 * 3 + 1] + (REAL)2 * fx * pj.tx * rz3 * v_J[0 * 3 + 2]
-                 + (REAL)2 * fy * pj.ty * rz3 * v_J[1 * 3 + 2];
+        {
+            REAL vm2[2] = {vm2x, vm2y};
+            FN(ortho_fisheye_vjp)(camera_model, pc, fx, fy, J, vm2, v_J, v_pc);
+        }
         v_pc[2] += v_depths[idx];
 
         /* world: v_mean = R^T v_pc ; v_cov = R^T v_covc R */

@@ -166,6 +166,49 @@ def make_projection(rng, means_all, viewmats, Ks, W, H):
     )
 
 
+# ---------------------------------------------------------------- projection, ortho / fisheye cameras
+def make_projection_cameras(means_all, viewmats, Ks, W, H):
+    """_fully_fused_projection(camera_model=...) -> _ortho_proj (_torch_impl.py:180) / _fisheye_proj (:111),
+    gradients by autograd (which differentiates the Jacobian as well, like the CUDA closed form)."""
+    for model in ("ortho", "fisheye"):
+        rng = np.random.RandomState({"ortho": 31, "fisheye": 32}[model])
+        N = 600
+        idx = rng.choice(len(means_all), N, replace=False)
+        means = means_all[idx]
+        quats = rng.standard_normal((N, 4)).astype(np.float32)
+        quats /= np.linalg.norm(quats, axis=-1, keepdims=True)
+        scales = (rng.random((N, 3)) * (0.02 - 1e-4) + 1e-4).astype(np.float32)
+        scales[: N // 4] *= 20.0
+        K_use = Ks.copy()
+        if model == "ortho":  # pixels per world unit
+            K_use[:, 0, 0] = 150.0
+            K_use[:, 1, 1] = 140.0
+        m = torch.tensor(means, dtype=f64, requires_grad=True)
+        q = torch.tensor(quats, dtype=f64, requires_grad=True)
+        s = torch.tensor(scales, dtype=f64, requires_grad=True)
+        vm = torch.tensor(viewmats, dtype=f64, requires_grad=True)
+        K = torch.tensor(K_use, dtype=f64)
+        covars, _ = _quat_scale_to_covar_preci(q, s, True, False, triu=False)
+        radii, means2d, depths, conics, comps = _fully_fused_projection(
+            m, covars, vm, K, W, H, eps2d=0.3, near_plane=0.01, far_plane=1e10, calc_compensations=True, camera_model=model
+        )
+        C = viewmats.shape[0]
+        v_means2d = torch.tensor(rng.standard_normal((C, N, 2)))
+        v_depths = torch.tensor(rng.standard_normal((C, N)))
+        v_conics = torch.tensor(rng.standard_normal((C, N, 3)))
+        valid = (radii > 0).all(-1)
+        loss = ((means2d * v_means2d).sum(-1) * valid).sum() + (depths * v_depths * valid).sum() \
+            + ((conics * v_conics).sum(-1) * valid).sum()
+        v_m, v_q, v_s, v_vm = torch.autograd.grad(loss, (m, q, s, vm))
+        save(
+            f"ref_projection_{model}.npz", means=means, quats=quats, scales=scales, viewmats=viewmats, Ks=K_use,
+            width=np.int64(W), height=np.int64(H), radii=radii.int(), means2d=means2d, depths=depths, conics=conics,
+            compensations=comps, v_means2d=v_means2d, v_depths=v_depths, v_conics=v_conics,
+            v_means_nc=v_m, v_quats_nc=v_q, v_scales_nc=v_s, v_viewmats_nc=v_vm,
+        )
+        print(f"  {model}: {int(valid.sum())} of {valid.numel()} visible")
+
+
 # ---------------------------------------------------------------- SH
 def make_sh(rng, viewmats):
     N, D = 200, 3
@@ -325,10 +368,15 @@ def make_mcmc(rng):
 
 
 if __name__ == "__main__":
+    if "--cameras-only" in sys.argv:  # adds the ortho / fisheye fixtures without rewriting the others
+        d = np.load(os.path.join(HERE, "garden.npz"))
+        make_projection_cameras(d["means"], d["viewmats"], d["Ks"], int(d["width"]), int(d["height"]))
+        sys.exit(0)
     rng = np.random.RandomState(20260922)
     means_all, viewmats, Ks, W, H = make_garden()
     make_quat_scale(rng)
     make_projection(rng, means_all, viewmats, Ks, W, H)
+    make_projection_cameras(means_all, viewmats, Ks, W, H)
     make_sh(rng, viewmats)
     make_isect(rng)
     make_accumulate(rng)

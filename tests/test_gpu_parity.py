@@ -129,6 +129,91 @@ def test_projection_vs_oracle_and_golden(gs):
         assert rel < rt, f"{name}: relative L2 error vs reference golden {rel:.3e}"
 
 
+@pytest.mark.parametrize("model", ["ortho", "fisheye"])
+def test_projection_camera_models(gs, model):
+    """Orthographic / fisheye EWA projection (reference Utils.cuh:498-565, 692-846) vs the float32 oracle (bit-exact
+    for ortho; fisheye goes through atan2f, and its Jacobian derivative is computed with dual numbers on the GPU
+    and with the reference's closed form in the oracle -> tolerance) and vs the reference's torch twin goldens."""
+    g = _load(f"ref_projection_{model}.npz")
+    W, H = int(g["width"]), int(g["height"])
+    means, quats, scales = _t(g["means"], True), _t(g["quats"], True), _t(g["scales"], True)
+    vm, Ks = _t(g["viewmats"], True), _t(g["Ks"])
+    radii, m2, dep, con, comp = gs.fully_fused_projection(
+        means, None, quats, scales, vm, Ks, W, H, calc_compensations=True, camera_model=model
+    )
+    o = gso.fully_fused_projection(
+        g["means"], None, g["quats"], g["scales"], g["viewmats"], g["Ks"], W, H, 0.3, 0.01, 1e10, 0.0, True, camera_model=model
+    )
+    if model == "ortho":
+        assert np.array_equal(_n(radii), o[0]), "radii differ from the float32 oracle"
+        for a, b, name in ((m2, o[1], "means2d"), (dep, o[2], "depths"), (con, o[3], "conics"), (comp, o[4], "compensations")):
+            _exactish(_n(a), b, name)
+    else:
+        assert (np.abs(_n(radii) - o[0]) <= 1).all() and (_n(radii) != o[0]).mean() < 2e-3
+        vis = (o[0] > 0).all(-1) & (_n(radii) > 0).all(-1)
+        _close(_n(m2)[vis], o[1][vis], 1e-5, 1e-3, "means2d")
+        _close(_n(con)[vis], o[3][vis], 2e-3, 1e-5, "conics")
+    both = (_n(radii) > 0).all(-1) & (g["radii"] > 0).all(-1)
+    assert both.sum() > 1000
+    _close(_n(m2)[both], g["means2d"][both], 1e-4, 2e-3, "means2d vs reference golden")
+    _close(_n(con)[both], g["conics"][both], 5e-3, 1e-5, "conics vs reference golden")
+    valid_np = (g["radii"] > 0).all(-1) & (_n(radii) > 0).all(-1)
+    valid = _t(valid_np)
+    v_m2, v_d, v_c = (_t(g[k].astype(np.float32)) for k in ("v_means2d", "v_depths", "v_conics"))
+    loss = ((m2 * v_m2).sum(-1) * valid).sum() + (dep * v_d * valid).sum() + ((con * v_c).sum(-1) * valid).sum()
+    gm, gq, gsc, gvm = torch.autograd.grad(loss, (means, quats, scales, vm))
+    radii_v = (o[0] * valid_np[..., None]).astype(np.int32)
+    ov = gso.fully_fused_projection_bwd(
+        g["means"], None, g["quats"], g["scales"], g["viewmats"], g["Ks"], W, H, 0.3, radii_v, o[3], None,
+        g["v_means2d"].astype(np.float32), g["v_depths"].astype(np.float32), g["v_conics"].astype(np.float32), None, True,
+        camera_model=model,
+    )
+    for a, b, name in ((gm, ov[0], "v_means"), (gq, ov[2], "v_quats"), (gsc, ov[3], "v_scales")):
+        rel = np.linalg.norm(_n(a) - b) / np.linalg.norm(b)
+        assert rel < (1e-5 if model == "ortho" else 2e-4), f"{name}: rel L2 error vs f32 oracle {rel:.3e}"
+    rel = np.linalg.norm(_n(gvm) - ov[4]) / np.linalg.norm(ov[4])
+    assert rel < 1e-3, f"v_viewmats: rel L2 error vs f32 oracle {rel:.3e}"
+    sel = valid_np.any(0)
+    for a, name in ((gm, "v_means"), (gq, "v_quats"), (gsc, "v_scales")):
+        ref = g[name + "_nc"]
+        # the golden masks with the twin's own visibility; restrict to gaussians visible in the same cameras
+        same = (valid_np == (g["radii"] > 0).all(-1)).all(0) & sel
+        rel = np.linalg.norm(_n(a)[same] - ref[same]) / np.linalg.norm(ref[same])
+        assert rel < 2e-2, f"{name}: relative L2 error vs reference golden {rel:.3e}"
+
+
+@pytest.mark.parametrize("model", ["ortho", "fisheye"])
+def test_rasterization_camera_models(gs, model):
+    """End to end with a non-pinhole camera: matches the float64 oracle chain projection -> SH -> isect -> raster."""
+    sc = scene.make_scene(n_max=30000, sh_degree=1)
+    W, H = 320, 200
+    Ks = scene.rescale_K(sc["Ks"], sc["width"], sc["height"], W, H)[:1].copy()
+    if model == "ortho":
+        Ks[:, 0, 0], Ks[:, 1, 1] = 60.0, 60.0
+    vm = sc["viewmats"][:1]
+    sh = np.ascontiguousarray(sc["sh"][:, :4])
+    P = [_t(sc[k], True) for k in ("means", "quats", "scales", "opacities")]
+    tsh = _t(sh, True)
+    rc, ra, meta = gs.rasterization(*P, tsh, _t(vm), _t(Ks), W, H, sh_degree=1, camera_model=model)
+    d = lambda a: a.astype(np.float64)  # noqa: E731
+    o = gso.fully_fused_projection(d(sc["means"]), None, d(sc["quats"]), d(sc["scales"]), d(vm), d(Ks), W, H, 0.3, 0.01, 1e10,
+                                   0.0, False, model, d(sc["opacities"]))
+    vis = (o[0] > 0).all(-1)
+    assert vis.sum() > 2000
+    col = np.maximum(gso.spherical_harmonics(1, d(sc["means"]), d(vm), d(sh), vis) + 0.5, 0.0)
+    op = np.broadcast_to(d(sc["opacities"])[None], vis.shape)
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    _, ids, fl = gso.isect_tiles(o[1], o[0], o[2], 16, tw, th, True, o[3], op)
+    off = gso.isect_offset_encode(ids, 1, tw, th)
+    orc, ora, _, omg = gso.rasterize_to_pixels(o[1], o[3], col, op, W, H, 16, off, fl, None, None, True)
+    ok = omg > 1e-4
+    assert ok.mean() > 0.99
+    _close(_n(rc)[ok], orc[ok], 2e-4, 2e-5, "render_colors")
+    _close(_n(ra)[ok], ora[ok], 2e-4, 2e-5, "render_alphas")
+    (rc.sum() + ra.sum()).backward()
+    assert all(torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0 for p in P) and torch.isfinite(tsh.grad).all()
+
+
 def test_projection_opacity_aware_and_covars(gs):
     sc = scene.make_scene(n_max=20000, sh_degree=0)
     W, H = sc["width"], sc["height"]
@@ -515,7 +600,7 @@ def test_rasterization_modes(gs):
     f, _, _ = gs.rasterization(*base, feat, *cam, packed=False)
     f0, _, _ = gs.rasterization(*base, feat[:, :32].contiguous(), *cam, packed=False)
     assert f.shape[-1] == 40 and torch.equal(f[..., :32], f0)
-    for bad in (dict(with_ut=True), dict(camera_model="fisheye"), dict(render_mode="RGB-d"), dict(tile_size=8)):
+    for bad in (dict(with_ut=True), dict(camera_model="ftheta"), dict(render_mode="RGB-d"), dict(tile_size=8)):
         with pytest.raises((NotImplementedError, ValueError)):
             gs.rasterization(*base, col, *cam, packed=False, **bad)
 
@@ -658,3 +743,35 @@ def test_nvls_allreduce_two_ranks():
     """Own all-reduce kernels (multimem + peer-to-peer) vs NCCL, bit-exact at 2 ranks (skipped on a 1-GPU box)."""
     out = _torchrun2("dist_nvls_check.py", 29590)
     assert out.count("nvls check ok") == 7
+
+
+def test_selective_adam(gs):
+    """adam op + SelectiveAdam vs the float32 oracle (bit-exact: same operations in the same order) and, for the
+    visible rows, vs a hand-rolled torch Adam without bias correction."""
+    rng = np.random.RandomState(5)
+    N = 5000
+    for shape in ((N, 3), (N, 16, 3), (N,)):
+        p0 = rng.standard_normal(shape).astype(np.float32)
+        g = (rng.standard_normal(shape) * 0.1).astype(np.float32)
+        m0 = (rng.standard_normal(shape) * 0.01).astype(np.float32)
+        v0 = (rng.random_sample(shape) * 1e-3).astype(np.float32)
+        vis = rng.random_sample(N) < 0.4
+        p, m, v = _t(p0), _t(m0), _t(v0)
+        gs.adam(p, _t(g), m, v, _t(vis), 1e-2, 0.9, 0.999, 1e-8)
+        op, om, ov = gso.adam(p0, g, m0, v0, vis, 1e-2, 0.9, 0.999, 1e-8)
+        assert np.array_equal(_n(m), om) and np.array_equal(_n(v), ov)
+        _exactish(_n(p), op, "param")
+        assert np.array_equal(_n(p)[~vis], p0[~vis]) and np.array_equal(_n(m)[~vis], m0[~vis])
+        gs.adam(p, _t(g), m, v, None, 1e-2, 0.9, 0.999, 1e-8)  # valid=None: every row
+        assert not np.array_equal(_n(p)[~vis], p0[~vis])
+    # the optimizer front-end (reference API: one tensor per group, step(visibility))
+    w = torch.nn.Parameter(_t(rng.standard_normal((N, 3)).astype(np.float32)))
+    opt = gs.SelectiveAdam([{"params": [w], "lr": 1e-2}], eps=1e-8, betas=(0.9, 0.999))
+    w0 = w.detach().clone()
+    (w**2).sum().backward()
+    vis_t = _t(rng.random_sample(N) < 0.5)
+    opt.step(vis_t)
+    gref = 2 * w0
+    expect = w0 - 1e-2 * (0.1 * gref) / ((0.001 * gref * gref).sqrt() + 1e-8)
+    torch.testing.assert_close(w.detach()[vis_t], expect[vis_t], rtol=1e-5, atol=1e-6)
+    assert torch.equal(w.detach()[~vis_t], w0[~vis_t])

@@ -105,6 +105,44 @@ def _ref_isect(ref, m2, radii, dep, con, op, C, tw, th):
     return tpg, ids, fl, off
 
 
+@pytest.mark.parametrize("model,cam_id", [("ortho", 1), ("fisheye", 2)])
+def test_projection_camera_models_vs_reference(ref, gs, model, cam_id):
+    """Ortho / fisheye projection fwd + bwd against the reference CUDA kernels (CameraModelType 1 / 2)."""
+    W, H, C = 960, 540, 2
+    sc, vm, Ks = _scene(60000, W, H, C)
+    if model == "ortho":
+        Ks = Ks.clone()
+        Ks[:, 0, 0], Ks[:, 1, 1] = 180.0, 170.0
+    means, quats, scales, opac = (_t(sc[k]) for k in ("means", "quats", "scales", "opacities"))
+    r = ref.projection_ewa_3dgs_fused(means, None, quats, scales, opac, vm, Ks, W, H, 0.3, 0.01, 1e10, 0.0, False, cam_id)
+    o = gs.fully_fused_projection(means, None, quats, scales, vm, Ks, W, H, opacities=opac, camera_model=model)
+    rv, ov = (r[0] > 0).all(-1), (o[0] > 0).all(-1)
+    assert (rv != ov).float().mean() < 1e-4
+    both = rv & ov
+    assert both.sum() > 5000
+    assert ((r[0][both] - o[0][both]).abs() <= 1).all()
+    torch.testing.assert_close(o[1][both], r[1][both], rtol=1e-4, atol=2e-3)
+    torch.testing.assert_close(o[2][both], r[2][both], rtol=1e-5, atol=1e-6)
+    assert _rel(o[3][both], r[3][both]) < 1e-4
+    g = torch.Generator(device=DEV).manual_seed(1)
+    N = len(means)
+    v_m2, v_dep, v_con = (torch.randn(s, device=DEV, generator=g) for s in ((C, N, 2), (C, N), (C, N, 3)))
+    rb = ref.projection_ewa_3dgs_fused_bwd(
+        means, None, quats, scales, vm, Ks, W, H, 0.3, cam_id, r[0], r[3], None, v_m2, v_dep, v_con, None, True
+    )
+    L = gs._cabi.lib()
+    from gsplat_b200._cabi import ptr, stream
+
+    v_means, v_quats, v_scales, v_vm = (torch.empty_like(x) for x in (means, quats, scales, vm))
+    rc = L.gsb200_projection_bwd(
+        1, C, N, ptr(means), None, ptr(quats), ptr(scales), ptr(vm), ptr(Ks), W, H, 0.3, cam_id, ptr(r[0]), ptr(r[3]), None,
+        ptr(v_m2), 2, ptr(v_dep), 1, ptr(v_con), 3, None, ptr(v_means), None, ptr(v_quats), ptr(v_scales), ptr(v_vm), stream(),
+    )
+    assert rc == 0
+    assert _rel(v_means, rb[0]) < 2e-4 and _rel(v_quats, rb[2]) < 2e-4 and _rel(v_scales, rb[3]) < 2e-4
+    assert _rel(v_vm, rb[4]) < 2e-3
+
+
 def test_isect_vs_reference_on_identical_projection(ref, gs):
     W, H, C = 1280, 720, 2
     sc, vm, Ks = _scene(100000, W, H, C)
@@ -194,3 +232,35 @@ def test_full_path_vs_reference_1080p(ref, gs):
     assert _rel(P["opacities"].grad, v_op.sum(0)) < 1e-3
     assert _rel(P["means"].grad, pb[0] + r_vmeans_sh) < 2e-3
     assert _rel(P["quats"].grad, pb[2]) < 5e-3 and _rel(P["scales"].grad, pb[3]) < 5e-3
+
+
+def test_adam_and_relocation_vs_reference(ref, gs):
+    """Trainer-side ops against the reference kernels (csrc/AdamCUDA.cu, RelocationCUDA.cu, MCMCPerturbCUDA.cu)."""
+    g = torch.Generator(device=DEV).manual_seed(3)
+    N = 20000
+    for shape in ((N, 3), (N, 16, 3)):
+        p = torch.randn(shape, device=DEV, generator=g)
+        grad = torch.randn(shape, device=DEV, generator=g) * 0.1
+        m = torch.randn(shape, device=DEV, generator=g) * 0.01
+        v = torch.rand(shape, device=DEV, generator=g) * 1e-3
+        vis = torch.rand(N, device=DEV, generator=g) < 0.3
+        a = [x.clone() for x in (p, m, v)]
+        b = [x.clone() for x in (p, m, v)]
+        ref.adam(a[0], grad, a[1], a[2], vis, 1e-2, 0.9, 0.999, 1e-8)
+        gs.adam(b[0], grad, b[1], b[2], vis, 1e-2, 0.9, 0.999, 1e-8)
+        for x, y in zip(a, b):
+            torch.testing.assert_close(y, x, rtol=1e-5, atol=1e-7)  # the reference is built with fast-math (FMA: cancellation in m)
+        assert torch.equal(b[0][~vis], p[~vis])
+    # relocation
+    n_max = 51
+    binoms = torch.zeros((n_max, n_max), device=DEV)
+    for n in range(n_max):
+        for k in range(n + 1):
+            binoms[n, k] = math.comb(n, k)
+    opac = torch.rand(N, device=DEV, generator=g) * 0.98 + 0.01
+    scales = torch.rand((N, 3), device=DEV, generator=g) * 0.1 + 1e-3
+    ratios = torch.randint(1, 12, (N,), device=DEV, generator=g)
+    ro, rs = ref.relocation(opac, scales, ratios.int(), binoms, n_max, 0.005)
+    o, s = gs.compute_relocation(opac, scales, ratios.clone(), binoms, 0.005)
+    torch.testing.assert_close(o, ro, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(s, rs, rtol=1e-4, atol=1e-8)

@@ -97,6 +97,44 @@ def test_projection(golden_dir):
         _close(a, ref, 5e-4, 1e-6 * np.abs(ref).max(), name)
 
 
+@pytest.mark.parametrize("model", ["ortho", "fisheye"])
+def test_projection_camera_models(golden_dir, model):
+    """Oracle ortho / fisheye projection fwd + bwd vs the reference's torch twin (_ortho_proj / _fisheye_proj +
+    autograd, which differentiates the Jacobian too -- what the CUDA closed form of Utils.cuh:733-846 does)."""
+    g = _load(golden_dir, f"ref_projection_{model}.npz")
+    W, H = int(g["width"]), int(g["height"])
+    f8 = lambda k: g[k].astype(np.float64)  # noqa: E731
+    radii, m2, dep, con, comp = gso.fully_fused_projection(
+        f8("means"), None, f8("quats"), f8("scales"), f8("viewmats"), f8("Ks"), W, H, 0.3, 0.01, 1e10, 0.0, True,
+        camera_model=model,
+    )
+    ref_valid = (g["radii"] > 0).all(-1)
+    valid = (radii > 0).all(-1)
+    assert not (valid & ~ref_valid).any() and (valid != ref_valid).mean() < 2e-3
+    both = valid & ref_valid
+    assert both.sum() > 1000
+    assert (radii[both] == g["radii"][both]).all()
+    _close(m2[both], g["means2d"][both], 1e-10, 1e-8, "means2d")
+    _close(dep[both], g["depths"][both], 1e-12, 1e-12, "depths")
+    _close(con[both], g["conics"][both], 1e-8, 1e-11, "conics")
+    _close(comp[both], g["compensations"][both], 1e-9, 1e-12, "compensations")
+    v = gso.fully_fused_projection_bwd(
+        f8("means"), None, f8("quats"), f8("scales"), f8("viewmats"), f8("Ks"), W, H, 0.3, g["radii"].astype(np.int32),
+        g["conics"], None, f8("v_means2d"), f8("v_depths"), f8("v_conics"), None, True, camera_model=model,
+    )
+    # fisheye: the closed form treats d mean2d / d xyz as J (ideal map) while the twin differentiates the
+    # eps-regularised expression, and x^2 carries a +1e-7: agreement to ~1e-6 relative, not round-off
+    rtol = 1e-9 if model == "ortho" else 2e-5
+    for name, a in (("v_means", v[0]), ("v_quats", v[2]), ("v_scales", v[3]), ("v_viewmats", v[4])):
+        ref = g[name + "_nc"]
+        _close(a, ref, rtol, (1e-11 if model == "ortho" else 2e-7) * np.abs(ref).max(), name)
+    # float32 instantiation stays close
+    r32 = gso.fully_fused_projection(g["means"], None, g["quats"], g["scales"], g["viewmats"], g["Ks"], W, H,
+                                     0.3, 0.01, 1e10, 0.0, True, camera_model=model)
+    b32 = (r32[0] > 0).all(-1) & ref_valid
+    _close(r32[1][b32], g["means2d"][b32], 1e-4, 2e-3, "means2d f32")
+
+
 def test_projection_f32_close_to_f64(golden_dir):
     g = _load(golden_dir, "ref_projection.npz")
     W, H = int(g["width"]), int(g["height"])
