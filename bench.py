@@ -74,13 +74,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self) -> None:
+        """Samples taken before this call (nvidia-smi start-up, warm-up steps) are not reported."""
+        self.first = len(self.rows)
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        rows = self.rows[getattr(self, "first", 0):] or self.rows
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -346,6 +351,11 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML init touches every GPU of the box) must not
+    # fall into the timed region; it then polls GPU 0 every 100 ms and only samples taken from here on are reported
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for c in consumed:
         c.record()
     for i in range(max(args.warmup, 3)):
@@ -353,9 +363,9 @@ def main():
         issue_copy(i & 1)
         step(True, i & 1)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        time.sleep(0.3)  # let the sampler finish starting up
+        sampler.mark()
     ms_dev = timed(False, args.steps)
     ms_e2e = timed(True, args.steps)
     clocks = sampler.stop() if rank == 0 else None
