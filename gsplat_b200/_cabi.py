@@ -56,6 +56,22 @@ _SIGNATURES = {
         [c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_f32, c_vp, c_vp, c_vp, c_vp,
          c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     ),
+    "gsb200_projection_packed_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
+    "gsb200_projection_packed_count": (
+        c_int,
+        [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_f32, c_f32, c_f32, c_f32, c_int, c_int,
+         c_vp, c_sz, c_vp, c_vp],
+    ),
+    "gsb200_projection_packed_emit": (
+        c_int,
+        [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_f32, c_f32, c_f32, c_f32, c_int,
+         c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    ),
+    "gsb200_projection_packed_bwd": (
+        c_int,
+        [c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_f32, c_int, c_vp, c_vp, c_vp, c_vp,
+         c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    ),
     "gsb200_isect_depth_order_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "gsb200_isect_depth_order": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "gsb200_isect_scan_workspace_bytes": (c_sz, [c_i64]),

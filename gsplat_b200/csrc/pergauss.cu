@@ -559,6 +559,197 @@ __global__ void __launch_bounds__(kThreads, 2) project_sh_bwd_kernel(
         vsh[k] = 0.f;
 }
 
+// ------------------------------------------------------------------ packed (compacting) projection
+// Reference: csrc/ProjectionEWA3DGSPacked.cu:39-284 (two passes over the same kernel: count the visible
+// gaussians per block, scan, then write the visible rows back to back), host csrc/Projection.cpp:858-1060.
+// Rows come out in ascending (batch, camera, gaussian) order; nothing of size B*C*N is ever allocated.
+template<int CAM, bool EMIT>
+__global__ void __launch_bounds__(kThreads) projection_packed_kernel(
+    int64_t C, int64_t N, const float *__restrict__ means, const float *__restrict__ covars,
+    const float *__restrict__ quats, const float *__restrict__ scales, const float *__restrict__ opacities,
+    const float *__restrict__ viewmats, const float *__restrict__ Ks, uint32_t W, uint32_t H, float eps2d,
+    float near_plane, float far_plane, float radius_clip, bool want_comp, const int32_t *__restrict__ block_accum,
+    int32_t *__restrict__ block_cnts, int32_t *__restrict__ indptr, int64_t *__restrict__ batch_ids,
+    int64_t *__restrict__ camera_ids, int64_t *__restrict__ gaussian_ids, int32_t *__restrict__ radii,
+    float *__restrict__ means2d, float *__restrict__ depths, float *__restrict__ conics, float *__restrict__ compensations
+)
+{
+    __shared__ int warp_cnt[kThreads / 32];
+    const int64_t row = blockIdx.y; // (b, c)
+    const int64_t b = row / C, c = row % C;
+    const int64_t n   = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Proj p;
+    p.rx = p.ry = 0;
+    if(n < N)
+    {
+        const int64_t bn = b * N + n;
+        const Cam cam = load_cam(viewmats + row * 16, Ks + row * 9);
+        const float mean[3] = {means[bn * 3], means[bn * 3 + 1], means[bn * 3 + 2]};
+        M3 cov;
+        if(covars)
+            cov = load_cov6(covars + bn * 6);
+        else
+        {
+            const float q[4] = {quats[bn * 4], quats[bn * 4 + 1], quats[bn * 4 + 2], quats[bn * 4 + 3]};
+            const float s[3] = {scales[bn * 3], scales[bn * 3 + 1], scales[bn * 3 + 2]};
+            cov = quat_scale_to_sym<false>(q, s);
+        }
+        float op = 0.f;
+        if(opacities)
+            op = opacities[bn];
+        p = project_one<CAM>(mean, cov, opacities ? &op : nullptr, cam, W, H, eps2d, near_plane, far_plane, radius_clip, want_comp);
+    }
+    const bool vis       = p.rx > 0 && p.ry > 0;
+    const unsigned ball  = __ballot_sync(0xffffffffu, vis);
+    if(lane == 0)
+        warp_cnt[warp] = __popc(ball);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for(int w = 0; w < kThreads / 32; ++w)
+    {
+        before += (w < (int)warp) ? warp_cnt[w] : 0;
+        total += warp_cnt[w];
+    }
+    const int64_t blk = row * gridDim.x + blockIdx.x;
+    if constexpr(!EMIT)
+    {
+        if(threadIdx.x == 0)
+            block_cnts[blk] = total;
+    }
+    else
+    {
+        const int32_t base = blk == 0 ? 0 : block_accum[blk - 1];
+        if(threadIdx.x == 0)
+        {
+            if(blockIdx.x == 0)
+                indptr[row] = base;
+            if(blk == (int64_t)gridDim.x * gridDim.y - 1)
+                indptr[gridDim.y] = base + total;
+        }
+        if(vis)
+        {
+            const int64_t o = (int64_t)base + before + __popc(ball & ((1u << lane) - 1u));
+            batch_ids[o]    = b;
+            camera_ids[o]   = c;
+            gaussian_ids[o] = n;
+            reinterpret_cast<int2 *>(radii)[o]     = make_int2(p.rx, p.ry);
+            reinterpret_cast<float2 *>(means2d)[o] = make_float2(p.mx, p.my);
+            depths[o]         = p.depth;
+            conics[o * 3]     = p.ca;
+            conics[o * 3 + 1] = p.cb;
+            conics[o * 3 + 2] = p.cc;
+            if(compensations)
+                compensations[o] = p.comp;
+        }
+    }
+}
+
+// One thread per packed row.  dense_out: gradients are summed into the [B*N, *] tensors with float atomics (rows
+// of one gaussian differ only in their camera); otherwise (sparse_grad) every row writes its own [nnz, *] entry.
+// Reference: csrc/ProjectionEWA3DGSPacked.cu:385-640.
+template<int CAM>
+__global__ void __launch_bounds__(kThreads) projection_packed_bwd_kernel(
+    int64_t nnz, int64_t C, int64_t N, const float *__restrict__ means, const float *__restrict__ covars,
+    const float *__restrict__ quats, const float *__restrict__ scales, const float *__restrict__ viewmats,
+    const float *__restrict__ Ks, uint32_t W, uint32_t H, float eps2d, const int64_t *__restrict__ batch_ids,
+    const int64_t *__restrict__ camera_ids, const int64_t *__restrict__ gaussian_ids, const float *__restrict__ conics,
+    const float *__restrict__ compensations, const float *__restrict__ v_means2d, int64_t s_m2,
+    const float *__restrict__ v_depths, int64_t s_d, const float *__restrict__ v_conics, int64_t s_c,
+    const float *__restrict__ v_compensations, bool dense_out, float *__restrict__ v_means, float *__restrict__ v_covars,
+    float *__restrict__ v_quats, float *__restrict__ v_scales, float *__restrict__ v_viewmats
+)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= nnz)
+        return;
+    const int64_t b = batch_ids[i], c = camera_ids[i], n = gaussian_ids[i];
+    const int64_t bn = b * N + n, row = b * C + c;
+    const Cam cam = load_cam(viewmats + row * 16, Ks + row * 9);
+    const float mean[3] = {means[bn * 3], means[bn * 3 + 1], means[bn * 3 + 2]};
+    float q[4] = {1.f, 0.f, 0.f, 0.f}, s[3] = {1.f, 1.f, 1.f};
+    M3 cov;
+    if(covars)
+        cov = load_cov6(covars + bn * 6);
+    else
+    {
+#pragma unroll
+        for(int k = 0; k < 4; ++k)
+            q[k] = quats[bn * 4 + k];
+#pragma unroll
+        for(int k = 0; k < 3; ++k)
+            s[k] = scales[bn * 3 + k];
+        cov = quat_scale_to_sym<false>(q, s);
+    }
+    const float conic[3] = {conics[i * 3], conics[i * 3 + 1], conics[i * 3 + 2]};
+    const float vc[3]    = {v_conics[i * s_c], v_conics[i * s_c + 1], v_conics[i * s_c + 2]};
+    const bool has_comp  = v_compensations != nullptr;
+    const ProjGrad g     = project_one_vjp<CAM>(
+        mean, cov, cam, W, H, eps2d, conic, v_means2d[i * s_m2], v_means2d[i * s_m2 + 1], v_depths[i * s_d], vc, has_comp,
+        has_comp ? compensations[i] : 0.f, has_comp ? v_compensations[i] : 0.f
+    );
+    const int64_t o = dense_out ? bn : i;
+    float out[10];
+    int n_out;
+    out[0] = g.v_mean[0], out[1] = g.v_mean[1], out[2] = g.v_mean[2];
+    if(covars)
+    {
+        out[3] = g.v_cov.m[0], out[4] = g.v_cov.m[1] + g.v_cov.m[3], out[5] = g.v_cov.m[2] + g.v_cov.m[6];
+        out[6] = g.v_cov.m[4], out[7] = g.v_cov.m[5] + g.v_cov.m[7], out[8] = g.v_cov.m[8];
+        n_out  = 9;
+    }
+    else
+    {
+        float vq[4] = {0.f, 0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
+        quat_scale_sym_vjp<false>(q, s, g.v_cov, vq, vs);
+        out[3] = vq[0], out[4] = vq[1], out[5] = vq[2], out[6] = vq[3];
+        out[7] = vs[0], out[8] = vs[1], out[9] = vs[2];
+        n_out  = 10;
+    }
+    float *dst[10];
+#pragma unroll
+    for(int k = 0; k < 3; ++k)
+        dst[k] = v_means + o * 3 + k;
+    if(covars)
+    {
+#pragma unroll
+        for(int k = 0; k < 6; ++k)
+            dst[3 + k] = v_covars + o * 6 + k;
+    }
+    else
+    {
+#pragma unroll
+        for(int k = 0; k < 4; ++k)
+            dst[3 + k] = v_quats + o * 4 + k;
+#pragma unroll
+        for(int k = 0; k < 3; ++k)
+            dst[7 + k] = v_scales + o * 3 + k;
+    }
+#pragma unroll
+    for(int k = 0; k < 10; ++k)
+        if(k < n_out)
+        {
+            if(dense_out)
+                atomicAdd(dst[k], out[k]);
+            else
+                *dst[k] = out[k];
+        }
+    if(v_viewmats)
+    { // v_R = v_pc mean^T + v_covc R cov^T + v_covc^T R cov ; v_t = v_pc
+        const M3 A2 = mul_bt(mul(g.v_covc, cam.R), cov);
+        const M3 B2 = mul(mul_at(g.v_covc, cam.R), cov);
+#pragma unroll
+        for(int r = 0; r < 3; ++r)
+        {
+#pragma unroll
+            for(int j = 0; j < 3; ++j)
+                atomicAdd(v_viewmats + row * 16 + r * 4 + j, g.v_pc[r] * mean[j] + A2.m[r * 3 + j] + B2.m[r * 3 + j]);
+            atomicAdd(v_viewmats + row * 16 + r * 4 + 3, g.v_pc[r]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ tile intersection
 // Enumerates the tiles of one gaussian in the reference's emit order, calling f(tile_id).
 // AccuTile / SNUGBOX (csrc/IntersectTile.cu:83-207, 288-373) or the radius AABB (:374-463).
@@ -1162,5 +1353,175 @@ extern "C" int gsb200_adam(
     adam_kernel<<<grid_for(N * D, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         N * D, D, param, param_grad, exp_avg, exp_avg_sq, valid, lr, b1, b2, eps
     );
+    return check_launch();
+}
+
+// ---- packed projection (reference ops projection_ewa_3dgs_packed / _bwd, ext.cpp:1065-1077)
+extern "C" size_t gsb200_projection_packed_workspace_bytes(int64_t B, int64_t C, int64_t N)
+{
+    const int64_t blocks = B * C * ((N + kThreads - 1) / kThreads);
+    if(blocks <= 0)
+        return 0;
+    size_t scan = 0;
+    cub::DeviceScan::InclusiveSum((void *)nullptr, scan, (const int32_t *)nullptr, (int32_t *)nullptr, blocks);
+    return ((scan + 255) & ~(size_t)255) + 2 * (((size_t)blocks * sizeof(int32_t) + 255) & ~(size_t)255) + 256;
+}
+
+namespace
+{
+struct PackedWs
+{
+    int32_t *cnts, *accum;
+    void *scan;
+    size_t scan_bytes;
+};
+PackedWs carve_packed(void *workspace, int64_t blocks)
+{
+    PackedWs w;
+    const size_t seg = ((size_t)blocks * sizeof(int32_t) + 255) & ~(size_t)255;
+    char *p          = static_cast<char *>(workspace);
+    w.cnts           = reinterpret_cast<int32_t *>(p);
+    w.accum          = reinterpret_cast<int32_t *>(p + seg);
+    w.scan           = p + 2 * seg;
+    w.scan_bytes     = 0;
+    cub::DeviceScan::InclusiveSum((void *)nullptr, w.scan_bytes, w.cnts, w.accum, blocks);
+    return w;
+}
+} // namespace
+
+#define GSB_CAM_SWITCH(model, CALL)       \
+    if((model) == kCamPinhole)            \
+    {                                     \
+        CALL(kCamPinhole);                \
+    }                                     \
+    else if((model) == kCamOrtho)         \
+    {                                     \
+        CALL(kCamOrtho);                  \
+    }                                     \
+    else                                  \
+    {                                     \
+        CALL(kCamFisheye);                \
+    }
+
+// Pass 1: per-block visible counts + their inclusive scan in `workspace`; *nnz_dev (device int32) = total.
+extern "C" int gsb200_projection_packed_count(
+    int64_t B, int64_t C, int64_t N, const float *means, const float *covars, const float *quats, const float *scales,
+    const float *opacities, const float *viewmats, const float *Ks, uint32_t image_width, uint32_t image_height,
+    float eps2d, float near_plane, float far_plane, float radius_clip, int calc_compensations, int camera_model,
+    void *workspace, size_t workspace_bytes, int32_t *nnz_dev, void *stream
+)
+{
+    if(B < 0 || C < 0 || N < 0 || !nnz_dev)
+        return GSB200_E_INVALID;
+    if(camera_model < 0 || camera_model > 2)
+        return GSB200_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if(B * C * N == 0)
+    {
+        GSB_CUDA_TRY(cudaMemsetAsync(nnz_dev, 0, sizeof(int32_t), st));
+        return GSB200_OK;
+    }
+    if(!means || !viewmats || !Ks || !workspace || (!covars && (!quats || !scales)) || B * C > 65535)
+        return GSB200_E_INVALID;
+    const int64_t bpr = (N + kThreads - 1) / kThreads, blocks = B * C * bpr;
+    if(gsb200_projection_packed_workspace_bytes(B, C, N) > workspace_bytes)
+        return GSB200_E_WORKSPACE;
+    PackedWs w = carve_packed(workspace, blocks);
+    const dim3 grid((unsigned)bpr, (unsigned)(B * C));
+#define CALL(CAM)                                                                                                      \
+    projection_packed_kernel<CAM, false><<<grid, kThreads, 0, st>>>(                                                    \
+        C, N, means, covars, quats, scales, opacities, viewmats, Ks, image_width, image_height, eps2d, near_plane,      \
+        far_plane, radius_clip, calc_compensations != 0, nullptr, w.cnts, nullptr, nullptr, nullptr, nullptr, nullptr,  \
+        nullptr, nullptr, nullptr, nullptr                                                                              \
+    )
+    GSB_CAM_SWITCH(camera_model, CALL)
+#undef CALL
+    if(int rc = check_launch())
+        return rc;
+    GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(w.scan, w.scan_bytes, w.cnts, w.accum, blocks, st));
+    GSB_CUDA_TRY(cudaMemcpyAsync(nnz_dev, w.accum + blocks - 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return GSB200_OK;
+}
+
+// Pass 2 (same workspace, untouched since pass 1): the nnz visible rows, ascending (b, c, n); indptr [B*C + 1].
+extern "C" int gsb200_projection_packed_emit(
+    int64_t B, int64_t C, int64_t N, const float *means, const float *covars, const float *quats, const float *scales,
+    const float *opacities, const float *viewmats, const float *Ks, uint32_t image_width, uint32_t image_height,
+    float eps2d, float near_plane, float far_plane, float radius_clip, int camera_model, const void *workspace,
+    int32_t *indptr, int64_t *batch_ids, int64_t *camera_ids, int64_t *gaussian_ids, int32_t *radii, float *means2d,
+    float *depths, float *conics, float *compensations, void *stream
+)
+{
+    if(B < 0 || C < 0 || N < 0 || !indptr)
+        return GSB200_E_INVALID;
+    if(camera_model < 0 || camera_model > 2)
+        return GSB200_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if(B * C * N == 0)
+    {
+        GSB_CUDA_TRY(cudaMemsetAsync(indptr, 0, sizeof(int32_t) * (size_t)(B * C + 1), st));
+        return GSB200_OK;
+    }
+    if(!means || !viewmats || !Ks || !workspace || (!covars && (!quats || !scales)) || B * C > 65535)
+        return GSB200_E_INVALID;
+    const int64_t bpr = (N + kThreads - 1) / kThreads, blocks = B * C * bpr;
+    PackedWs w = carve_packed(const_cast<void *>(workspace), blocks);
+    const dim3 grid((unsigned)bpr, (unsigned)(B * C));
+#define CALL(CAM)                                                                                                      \
+    projection_packed_kernel<CAM, true><<<grid, kThreads, 0, st>>>(                                                     \
+        C, N, means, covars, quats, scales, opacities, viewmats, Ks, image_width, image_height, eps2d, near_plane,      \
+        far_plane, radius_clip, compensations != nullptr, w.accum, nullptr, indptr, batch_ids, camera_ids,              \
+        gaussian_ids, radii, means2d, depths, conics, compensations                                                     \
+    )
+    GSB_CAM_SWITCH(camera_model, CALL)
+#undef CALL
+    return check_launch();
+}
+
+// Backward over the nnz rows.  sparse_grad != 0: v_means [nnz,3], v_covars [nnz,6] or v_quats [nnz,4] +
+// v_scales [nnz,3] (one entry per row, written); else dense [B*N,*] outputs, zero-initialised here, summed with atomics.
+extern "C" int gsb200_projection_packed_bwd(
+    int64_t B, int64_t C, int64_t N, int64_t nnz, const float *means, const float *covars, const float *quats,
+    const float *scales, const float *viewmats, const float *Ks, uint32_t image_width, uint32_t image_height, float eps2d,
+    int camera_model, const int64_t *batch_ids, const int64_t *camera_ids, const int64_t *gaussian_ids,
+    const float *conics, const float *compensations, const float *v_means2d, int64_t v_means2d_stride,
+    const float *v_depths, int64_t v_depths_stride, const float *v_conics, int64_t v_conics_stride,
+    const float *v_compensations, int sparse_grad, float *v_means, float *v_covars, float *v_quats, float *v_scales,
+    float *v_viewmats, void *stream
+)
+{
+    if(B < 0 || C < 0 || N < 0 || nnz < 0)
+        return GSB200_E_INVALID;
+    if(camera_model < 0 || camera_model > 2)
+        return GSB200_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if(v_viewmats && B * C > 0)
+        GSB_CUDA_TRY(cudaMemsetAsync(v_viewmats, 0, sizeof(float) * 16 * (size_t)(B * C), st));
+    if(!v_means || (covars ? !v_covars : (!v_quats || !v_scales)))
+        return (B * N == 0 && nnz == 0) ? GSB200_OK : GSB200_E_INVALID;
+    if(!sparse_grad && B * N > 0)
+    {
+        GSB_CUDA_TRY(cudaMemsetAsync(v_means, 0, sizeof(float) * 3 * (size_t)(B * N), st));
+        if(covars)
+            GSB_CUDA_TRY(cudaMemsetAsync(v_covars, 0, sizeof(float) * 6 * (size_t)(B * N), st));
+        else
+        {
+            GSB_CUDA_TRY(cudaMemsetAsync(v_quats, 0, sizeof(float) * 4 * (size_t)(B * N), st));
+            GSB_CUDA_TRY(cudaMemsetAsync(v_scales, 0, sizeof(float) * 3 * (size_t)(B * N), st));
+        }
+    }
+    if(nnz == 0)
+        return GSB200_OK;
+    if(!means || !viewmats || !Ks || !batch_ids || !camera_ids || !gaussian_ids || !conics || !v_means2d || !v_depths
+       || !v_conics || (covars ? false : (!quats || !scales)) || (v_compensations && !compensations))
+        return GSB200_E_INVALID;
+#define CALL(CAM)                                                                                                      \
+    projection_packed_bwd_kernel<CAM><<<grid_for(nnz, kThreads), kThreads, 0, st>>>(                                     \
+        nnz, C, N, means, covars, quats, scales, viewmats, Ks, image_width, image_height, eps2d, batch_ids, camera_ids, \
+        gaussian_ids, conics, compensations, v_means2d, v_means2d_stride, v_depths, v_depths_stride, v_conics,          \
+        v_conics_stride, v_compensations, sparse_grad == 0, v_means, v_covars, v_quats, v_scales, v_viewmats            \
+    )
+    GSB_CAM_SWITCH(camera_model, CALL)
+#undef CALL
     return check_launch();
 }

@@ -210,6 +210,101 @@ class _FullyFusedProjection(torch.autograd.Function):
         return (v_means, v_covars, v_quats, v_scales, None, v_viewmats) + (None,) * 9
 
 
+class _FullyFusedProjectionPacked(torch.autograd.Function):
+    """projection_ewa_3dgs_packed (/root/reference/gsplat/cuda/_wrapper.py:1065-1191): two-pass compacting
+    projection; outputs are the nnz visible (batch, camera, gaussian) rows in ascending order."""
+
+    @staticmethod
+    def forward(
+        ctx, means, covars, quats, scales, opacities, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+        radius_clip, sparse_grad, calc_compensations, camera_model_id,
+    ):
+        dev = require_cuda(means, viewmats, Ks)
+        means, covars, quats, scales = f32c(means, "means"), f32c(covars, "covars"), f32c(quats, "quats"), f32c(scales, "scales")
+        opacities, viewmats, Ks = f32c(opacities, "opacities"), f32c(viewmats, "viewmats"), f32c(Ks, "Ks")
+        batch = tuple(means.shape[:-2])
+        if sparse_grad and len(batch) != 0:
+            raise ValueError("sparse_grad does not support batch dimensions")
+        B, N, C = _prod(batch), means.shape[-2], viewmats.shape[-3]
+        L = lib()
+        o = dict(device=dev, dtype=torch.float32)
+        nnz_dev = torch.empty(1, device=dev, dtype=torch.int32)
+        args = (
+            B, C, N, ptr(means), ptr(covars), ptr(quats), ptr(scales), ptr(opacities), ptr(viewmats), ptr(Ks), width, height,
+            eps2d, near_plane, far_plane, radius_clip,
+        )
+        with _Ctx(dev) as st:
+            ws = torch.empty(max(L.gsb200_projection_packed_workspace_bytes(B, C, N), 256), device=dev, dtype=torch.uint8)
+            check(
+                L.gsb200_projection_packed_count(*args, int(calc_compensations), camera_model_id, ptr(ws), ws.numel(), ptr(nnz_dev), st),
+                "projection_ewa_3dgs_packed (count)",
+            )
+            nnz = int(nnz_dev.item())  # the host sync of the packed path (reference: Projection.cpp:924)
+            ids = torch.empty((3, nnz), device=dev, dtype=torch.int64)
+            indptr = torch.empty(B * C + 1, device=dev, dtype=torch.int32)
+            radii = torch.empty((nnz, 2), device=dev, dtype=torch.int32)
+            means2d, depths, conics = torch.empty((nnz, 2), **o), torch.empty((nnz,), **o), torch.empty((nnz, 3), **o)
+            comps = torch.zeros((nnz,), **o) if calc_compensations else None
+            check(
+                L.gsb200_projection_packed_emit(
+                    *args, camera_model_id, ptr(ws), ptr(indptr), ptr(ids[0]), ptr(ids[1]), ptr(ids[2]), ptr(radii), ptr(means2d),
+                    ptr(depths), ptr(conics), ptr(comps), st,
+                ),
+                "projection_ewa_3dgs_packed (emit)",
+            )
+        batch_ids, camera_ids, gaussian_ids = ids[0], ids[1], ids[2]
+        ctx.save_for_backward(means, covars, quats, scales, viewmats, Ks, batch_ids, camera_ids, gaussian_ids, conics, comps)
+        ctx.meta = (width, height, eps2d, camera_model_id, bool(sparse_grad))
+        ctx.mark_non_differentiable(batch_ids, camera_ids, gaussian_ids, indptr, radii)
+        return batch_ids, camera_ids, gaussian_ids, indptr, radii, means2d, depths, conics, comps
+
+    @staticmethod
+    def backward(ctx, _vb, _vc, _vg, _vi, _vr, v_means2d, v_depths, v_conics, v_comps):
+        means, covars, quats, scales, viewmats, Ks, batch_ids, camera_ids, gaussian_ids, conics, comps = ctx.saved_tensors
+        width, height, eps2d, cam_id, sparse_grad = ctx.meta
+        batch = tuple(means.shape[:-2])
+        B, N, C = _prod(batch), means.shape[-2], viewmats.shape[-3]
+        nnz = conics.shape[0]
+        dev = means.device
+        z = lambda shape: torch.zeros(shape, device=dev, dtype=torch.float32)  # noqa: E731
+        v_means2d = z((nnz, 2)) if v_means2d is None else v_means2d
+        v_depths = z((nnz,)) if v_depths is None else v_depths
+        v_conics = z((nnz, 3)) if v_conics is None else v_conics
+        v_means2d, s_m2 = _rows(v_means2d, 2, "v_means2d")
+        v_depths, s_d = _rows(v_depths, 1, "v_depths")
+        v_conics, s_c = _rows(v_conics, 3, "v_conics")
+        v_comps = None if (v_comps is None or comps is None) else v_comps.contiguous()
+        need_vm = ctx.needs_input_grad[5]
+        lead = (nnz,) if sparse_grad else tuple(means.shape[:-1])
+        e = lambda w: torch.empty(lead + (w,), device=dev, dtype=torch.float32)  # noqa: E731
+        v_means = e(3)
+        v_covars = e(6) if covars is not None else None
+        v_quats = e(4) if covars is None else None
+        v_scales = e(3) if covars is None else None
+        v_viewmats = torch.empty_like(viewmats) if need_vm else None
+        with _Ctx(dev) as st:
+            check(
+                lib().gsb200_projection_packed_bwd(
+                    B, C, N, nnz, ptr(means), ptr(covars), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), width, height, eps2d,
+                    cam_id, ptr(batch_ids), ptr(camera_ids), ptr(gaussian_ids), ptr(conics), ptr(comps), ptr(v_means2d), s_m2,
+                    ptr(v_depths), s_d, ptr(v_conics), s_c, ptr(v_comps), int(sparse_grad), ptr(v_means), ptr(v_covars),
+                    ptr(v_quats), ptr(v_scales), ptr(v_viewmats), st,
+                ),
+                "projection_ewa_3dgs_packed_bwd",
+            )
+        if sparse_grad:
+            # per-row gradients wrapped as COO over the gaussian index (reference Projection.cpp:1188-1206);
+            # coalesced when there is a single camera (every gaussian id then appears at most once)
+            idx = gaussian_ids[None]
+
+            def coo(rows, like):
+                return None if rows is None else torch.sparse_coo_tensor(idx, rows, size=like.shape, is_coalesced=(C == 1))
+
+            v_means, v_covars = coo(v_means, means), coo(v_covars, covars)
+            v_quats, v_scales = coo(v_quats, quats), coo(v_scales, scales)
+        return (v_means, v_covars, v_quats, v_scales, None, v_viewmats) + (None,) * 10
+
+
 def fully_fused_projection(
     means: Tensor,  # [..., N, 3]
     covars: Optional[Tensor],  # [..., N, 6] or None
@@ -232,38 +327,23 @@ def fully_fused_projection(
     """Projects Gaussians to 2D (EWA).  Returns (radii int32 [..., C, N, 2], means2d [..., C, N, 2],
     depths [..., C, N], conics [..., C, N, 3], compensations [..., C, N] | None).  ``radii == 0`` marks
     culled entries; their float outputs are zero."""
-    if sparse_grad:
-        if not packed:
-            raise AssertionError("sparse_grad is only supported when packed is True")
-        raise NotImplementedError("sparse_grad (COO gradients) is a 'next' row (SURVEY.md section 8f.1)")
+    if sparse_grad and not packed:
+        raise AssertionError("sparse_grad is only supported when packed is True")
     if covars is None and (quats is None or scales is None):
         raise ValueError("either covars or (quats, scales) must be given")
     if covars is not None:
         quats = scales = None
     cam = _camera_model_id(camera_model)
-    out = _FullyFusedProjection.apply(
+    if packed:
+        # (batch_ids, camera_ids, gaussian_ids int64 [nnz], indptr int32 [B*C+1], radii [nnz,2], means2d [nnz,2],
+        #  depths [nnz], conics [nnz,3], compensations [nnz] | None), rows in ascending (b, c, n) order
+        return _FullyFusedProjectionPacked.apply(
+            means, covars, quats, scales, opacities, viewmats, Ks, int(width), int(height), float(eps2d), float(near_plane),
+            float(far_plane), float(radius_clip), bool(sparse_grad), bool(calc_compensations), cam,
+        )
+    return _FullyFusedProjection.apply(
         means, covars, quats, scales, opacities, viewmats, Ks, int(width), int(height), float(eps2d), float(near_plane),
         float(far_plane), float(radius_clip), bool(calc_compensations), cam,
-    )
-    if not packed:
-        return out
-    # packed=True: the reference's COO layout (batch_ids, camera_ids, gaussian_ids, indptr, radii, means2d,
-    # depths, conics, compensations), rows in ascending (b, c, n) order.  The compacting two-pass kernel
-    # (csrc/ProjectionEWA3DGSPacked.cu) is a "next" row; here the dense kernel runs and the visible rows are
-    # gathered, which gives the same values, gradients and ordering (not the memory saving).
-    radii, means2d, depths, conics, comps = out
-    C, N = viewmats.shape[-3], means.shape[-2]
-    sel = (radii > 0).all(dim=-1).reshape(-1)
-    rows = torch.nonzero(sel, as_tuple=False).squeeze(-1)
-    gaussian_ids = (rows % N).to(torch.int32)
-    camera_ids = ((rows // N) % C).to(torch.int32)
-    batch_ids = (rows // (N * C)).to(torch.int32)
-    per_image = sel.reshape(-1, N).sum(dim=1)
-    indptr = torch.zeros(per_image.numel() + 1, device=sel.device, dtype=torch.int32)
-    indptr[1:] = torch.cumsum(per_image, 0).to(torch.int32)
-    return (
-        batch_ids, camera_ids, gaussian_ids, indptr, radii.reshape(-1, 2)[rows], means2d.reshape(-1, 2)[rows],
-        depths.reshape(-1)[rows], conics.reshape(-1, 3)[rows], None if comps is None else comps.reshape(-1)[rows],
     )
 
 

@@ -39,6 +39,43 @@ def _unsupported(name: str, why: str = "out of scope for the gsplat_b200 hot pat
     raise NotImplementedError(f"rasterization({name}): {why}")
 
 
+def _project_dense(
+    means, covars, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree, eps2d, near_plane, far_plane,
+    radius_clip, antialiased, camera_model, has_color, nb, batch_dims, C, N,
+):
+    """Dense [..., C, N] projection (+ SH): the fused single pass when it applies, else the per-op kernels."""
+    fused = (
+        has_color and sh_degree is not None and covars is None and nb == 0 and colors.shape[-1] == 3
+        and not viewmats.requires_grad and camera_model == "pinhole"
+    )
+    if fused:
+        radii, means2d, depths, conics, feat, compensations = fused_project_sh(
+            means, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree, eps2d, near_plane,
+            far_plane, radius_clip, antialiased,
+        )
+    else:
+        radii, means2d, depths, conics, compensations = fully_fused_projection(
+            means, covars, quats, scales, viewmats, Ks, width, height, eps2d=eps2d, near_plane=near_plane,
+            far_plane=far_plane, radius_clip=radius_clip, packed=False, calc_compensations=antialiased,
+            camera_model=camera_model, opacities=opacities,
+        )
+        feat = None
+        if has_color:
+            if sh_degree is None:
+                feat = colors
+                if feat.dim() == nb + 2:
+                    feat = torch.broadcast_to(feat[..., None, :, :], batch_dims + (C, N, feat.shape[-1]))
+            else:
+                valid = (radii > 0).all(dim=-1)
+                feat = spherical_harmonics(sh_degree, means, viewmats, colors, masks=valid)
+                feat = torch.clamp_min(feat + 0.5, 0.0)
+
+    opac = torch.broadcast_to(opacities[..., None, :], batch_dims + (C, N))
+    if compensations is not None:
+        opac = opac * compensations
+    return radii, means2d, depths, conics, feat, compensations, opac
+
+
 def rasterization(
     means: Tensor,  # [..., N, 3]
     quats: Optional[Tensor],  # [..., N, 4]
@@ -109,8 +146,10 @@ def rasterization(
         _unsupported(f"render_mode={render_mode!r}", "hit-distance modes belong to the eval3d (3DGUT) renderer")
     if rasterize_mode not in ("classic", "antialiased"):
         raise ValueError(f"unknown rasterize_mode {rasterize_mode!r}")
-    if sparse_grad:
-        _unsupported("sparse_grad", "sparse COO gradients are a 'next' row (SURVEY.md section 8f.1)")
+    if sparse_grad and not packed:
+        raise ValueError("sparse_grad requires packed=True")
+    if sparse_grad and distributed:
+        _unsupported("sparse_grad with distributed=True")
     world_size, world_rank = 1, 0
     if distributed:
         # reference: rendering.py:178-197 -- needs an initialised default group; NCCL in the reference (the CPU
@@ -183,36 +222,39 @@ def rasterization(
         if backgrounds is not None and tuple(backgrounds.shape[:-1]) != (C_world[world_rank],):
             raise ValueError("backgrounds must be [C_local, D] under distributed=True")
 
-    # ---- projection (+ SH): fused single pass when it applies
-    fused = (
-        has_color and sh_degree is not None and covars is None and nb == 0 and colors.shape[-1] == 3
-        and not viewmats.requires_grad and camera_model == "pinhole"
-    )
-    if fused:
-        radii, means2d, depths, conics, feat, compensations = fused_project_sh(
-            means, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree, eps2d, near_plane,
-            far_plane, radius_clip, antialiased,
-        )
-    else:
-        radii, means2d, depths, conics, compensations = fully_fused_projection(
+    # ---- packed=True: native two-pass compacting projection; everything downstream works on the [nnz, ...] rows
+    # (reference rendering.py:347-353, Rendering.cpp:936-973).  Under a multi-rank distributed=True the dense
+    # kernels run and the rows are gathered after the exchange (below).
+    native_packed = packed and not (distributed and world_size > 1)
+    camera_ids = gaussian_ids = batch_ids = None
+    if native_packed:
+        batch_ids, camera_ids, gaussian_ids, _indptr, radii, means2d, depths, conics, compensations = fully_fused_projection(
             means, covars, quats, scales, viewmats, Ks, width, height, eps2d=eps2d, near_plane=near_plane,
-            far_plane=far_plane, radius_clip=radius_clip, packed=False, calc_compensations=antialiased,
-            camera_model=camera_model, opacities=opacities,
+            far_plane=far_plane, radius_clip=radius_clip, packed=True, sparse_grad=sparse_grad,
+            calc_compensations=antialiased, camera_model=camera_model, opacities=opacities,
         )
+        grow = batch_ids * N + gaussian_ids  # row of the gaussian in the flattened [B*N] parameter tensors
+        opac = opacities.reshape(-1)[grow]
+        if compensations is not None:
+            opac = opac * compensations
         feat = None
         if has_color:
             if sh_degree is None:
-                feat = colors
-                if feat.dim() == nb + 2:
-                    feat = torch.broadcast_to(feat[..., None, :, :], batch_dims + (C, N, feat.shape[-1]))
+                if colors.dim() == nb + 2:
+                    feat = colors.reshape(-1, colors.shape[-1])[grow]
+                else:
+                    feat = colors.reshape(-1, colors.shape[-1])[(batch_ids * C + camera_ids) * N + gaussian_ids]
             else:
-                valid = (radii > 0).all(dim=-1)
-                feat = spherical_harmonics(sh_degree, means, viewmats, colors, masks=valid)
+                feat = spherical_harmonics(
+                    sh_degree, means, viewmats, colors[gaussian_ids], batch_ids=batch_ids, camera_ids=camera_ids,
+                    gaussian_ids=gaussian_ids,
+                )
                 feat = torch.clamp_min(feat + 0.5, 0.0)
-
-    opac = torch.broadcast_to(opacities[..., None, :], batch_dims + (C, N))
-    if compensations is not None:
-        opac = opac * compensations
+    else:
+        radii, means2d, depths, conics, feat, compensations, opac = _project_dense(
+            means, covars, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree, eps2d, near_plane, far_plane,
+            radius_clip, antialiased, camera_model, has_color, nb, batch_dims, C, N,
+        )
 
     # ---- Seam B (distributed=True): all-to-all so that each rank holds ALL gaussians projected onto ITS cameras
     if distributed and world_size > 1:
@@ -238,27 +280,29 @@ def rasterization(
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
     # reference-shaped op sequence: (depth order,) count, emit, radix sort on the (image, tile) bits, offsets
-    tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(
-        means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, segmented=segmented, packed=False,
-        n_images=I, conics=conics, opacities=opac,
-    )
+    if native_packed:
+        tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(
+            means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, segmented=segmented, packed=True,
+            n_images=I, image_ids=batch_ids * C + camera_ids, gaussian_ids=gaussian_ids, conics=conics, opacities=opac,
+        )
+    else:
+        tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(
+            means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, segmented=segmented, packed=False,
+            n_images=I, conics=conics, opacities=opac,
+        )
     isect_offsets = isect_offset_encode(isect_ids, I, tile_width, tile_height)
     isect_offsets = isect_offsets.reshape(batch_dims + (C, tile_height, tile_width))
 
-    camera_ids = gaussian_ids = batch_ids = None
-    if packed:
-        # Reference packed=True bookkeeping (rendering.py:347-353, Rendering.cpp:936-973): per-view data
-        # live in [nnz, ...] COO rows addressed by (batch_ids, camera_ids, gaussian_ids).  The projection
-        # itself still runs dense here (the two-pass compacting projection kernel is a "next" row,
-        # SURVEY.md section 8f.1); rows are gathered afterwards so that images, gradients and the meta
-        # contract are those of the reference's packed mode.
+    if packed and not native_packed:
+        # multi-rank distributed=True: the exchange above ran on dense [C, N] rows; gather the visible ones so that
+        # images, gradients and the meta contract are those of the reference's packed mode
         sel = (radii > 0).all(dim=-1)  # [..., C, N]
         flat_sel = sel.reshape(-1)
         rows = torch.nonzero(flat_sel, as_tuple=False).squeeze(-1)  # ascending (b, c, n) order
         inv = torch.cumsum(flat_sel, 0, dtype=torch.int64) - 1
-        gaussian_ids = (rows % N).to(torch.int32)
-        camera_ids = ((rows // N) % C).to(torch.int32)
-        batch_ids = (rows // (N * C)).to(torch.int32)
+        gaussian_ids = rows % N
+        camera_ids = (rows // N) % C
+        batch_ids = rows // (N * C)
         radii = radii.reshape(-1, 2)[rows]
         means2d = means2d.reshape(-1, 2)[rows]
         depths = depths.reshape(-1)[rows]

@@ -118,6 +118,41 @@ extern "C"
         float *v_sh_coeffs, void *stream
     );
 
+    /* ---- projection_ewa_3dgs_packed / _bwd : ext.cpp:1065-1077, _wrapper.py:1065-1191, host
+     * csrc/Projection.cpp:858-1260, kernel csrc/ProjectionEWA3DGSPacked.cu ----
+     * Two passes, nothing of size B*C*N is allocated.  Pass 1 leaves per-block counts and their scan in
+     * `workspace` (gsb200_projection_packed_workspace_bytes) and the row total in *nnz_dev (device int32);
+     * the caller reads it, allocates the [nnz, ...] outputs and runs pass 2 with the SAME workspace.
+     * Rows are in ascending (batch, camera, gaussian) order; ids are int64 like the reference's; indptr
+     * int32 [B*C + 1].  compensations NULL = not computed (and opacities are culled unscaled). */
+    size_t gsb200_projection_packed_workspace_bytes(int64_t B, int64_t C, int64_t N);
+    int gsb200_projection_packed_count(
+        int64_t B, int64_t C, int64_t N, const float *means, const float *covars, const float *quats,
+        const float *scales, const float *opacities, const float *viewmats, const float *Ks, uint32_t image_width,
+        uint32_t image_height, float eps2d, float near_plane, float far_plane, float radius_clip,
+        int calc_compensations, int camera_model, void *workspace, size_t workspace_bytes, int32_t *nnz_dev,
+        void *stream
+    );
+    int gsb200_projection_packed_emit(
+        int64_t B, int64_t C, int64_t N, const float *means, const float *covars, const float *quats,
+        const float *scales, const float *opacities, const float *viewmats, const float *Ks, uint32_t image_width,
+        uint32_t image_height, float eps2d, float near_plane, float far_plane, float radius_clip, int camera_model,
+        const void *workspace, int32_t *indptr, int64_t *batch_ids, int64_t *camera_ids, int64_t *gaussian_ids,
+        int32_t *radii, float *means2d, float *depths, float *conics, float *compensations, void *stream
+    );
+    /* sparse_grad != 0: one gradient row per packed row (v_means [nnz,3], v_covars [nnz,6] | v_quats [nnz,4] +
+     * v_scales [nnz,3]; the caller wraps them as COO over gaussian_ids, Projection.cpp:1188-1206); otherwise
+     * dense [B*N, *] outputs (zero-initialised here, summed over cameras with atomics). */
+    int gsb200_projection_packed_bwd(
+        int64_t B, int64_t C, int64_t N, int64_t nnz, const float *means, const float *covars, const float *quats,
+        const float *scales, const float *viewmats, const float *Ks, uint32_t image_width, uint32_t image_height,
+        float eps2d, int camera_model, const int64_t *batch_ids, const int64_t *camera_ids,
+        const int64_t *gaussian_ids, const float *conics, const float *compensations, const float *v_means2d,
+        int64_t v_means2d_stride, const float *v_depths, int64_t v_depths_stride, const float *v_conics,
+        int64_t v_conics_stride, const float *v_compensations, int sparse_grad, float *v_means, float *v_covars,
+        float *v_quats, float *v_scales, float *v_viewmats, void *stream
+    );
+
     /* ---- intersect_tile : ext.cpp:1022-1026, _wrapper.py:1196-1266, host csrc/Intersect.cpp:170-329 ----
      * Pass 0 (sorted output only): order int32 [rows] = the projected rows in ascending (image, depth bits,
      * row) order, culled rows (radii <= 0) last.  Emitting the intersections in this order leaves only the

@@ -264,3 +264,45 @@ def test_adam_and_relocation_vs_reference(ref, gs):
     o, s = gs.compute_relocation(opac, scales, ratios.clone(), binoms, 0.005)
     torch.testing.assert_close(o, ro, rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(s, rs, rtol=1e-4, atol=1e-8)
+
+
+def test_packed_projection_vs_reference(ref, gs):
+    """Two-pass compacting projection fwd + bwd against the reference's projection_ewa_3dgs_packed kernels."""
+    W, H, C = 960, 540, 3
+    sc, vm, Ks = _scene(70000, W, H, C)
+    means, quats, scales, opac = (_t(sc[k]) for k in ("means", "quats", "scales", "opacities"))
+    r = ref.projection_ewa_3dgs_packed(means, None, quats, scales, opac, vm, Ks, W, H, 0.3, 0.01, 1e10, 0.0, False, True, 0)
+    o = gs.fully_fused_projection(means, None, quats, scales, vm, Ks, W, H, opacities=opac, packed=True, calc_compensations=True)
+    rb, rc_, rg, rind, rrad, rm2, rdep, rcon, rcomp = r
+    # visibility differs on a handful of borderline rows (fast-math radius): compare on the common (camera, gaussian) keys
+    N = len(means)
+    rk, ok = rc_ * N + rg, o[1] * N + o[2]
+    assert abs(len(rk) - len(ok)) <= max(2, int(1e-4 * len(rk)))
+    common, ri, oi = np.intersect1d(rk.cpu().numpy(), ok.cpu().numpy(), return_indices=True)
+    assert len(common) > 0.999 * len(rk)
+    ri, oi = torch.from_numpy(ri).to(DEV), torch.from_numpy(oi).to(DEV)
+    assert (np.diff(ok.cpu().numpy()) > 0).all(), "rows must be in ascending (camera, gaussian) order"
+    torch.testing.assert_close(o[5][oi], rm2[ri], rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(o[6][oi], rdep[ri], rtol=1e-5, atol=1e-6)
+    assert _rel(o[7][oi], rcon[ri]) < 1e-4 and _rel(o[8][oi], rcomp[ri]) < 1e-5
+    if len(rk) == len(ok):
+        assert torch.equal(o[3], rind)
+    # backward on the reference's own rows / conics (dense accumulation)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    nnz = len(rk)
+    v_m2, v_dep, v_con = (torch.randn(s, device=DEV, generator=g) for s in ((nnz, 2), (nnz,), (nnz, 3)))
+    rbw = ref.projection_ewa_3dgs_packed_bwd(
+        means, None, quats, scales, vm, Ks, W, H, 0.3, 0, False, rb, rc_, rg, rcon, None, v_m2, v_dep, v_con, None, True
+    )
+    L = gs._cabi.lib()
+    from gsplat_b200._cabi import ptr, stream
+
+    v_means, v_quats, v_scales, v_vm = (torch.empty_like(x) for x in (means, quats, scales, vm))
+    rc = L.gsb200_projection_packed_bwd(
+        1, C, N, nnz, ptr(means), None, ptr(quats), ptr(scales), ptr(vm), ptr(Ks), W, H, 0.3, 0, ptr(rb), ptr(rc_), ptr(rg),
+        ptr(rcon), None, ptr(v_m2), 2, ptr(v_dep), 1, ptr(v_con), 3, None, 0, ptr(v_means), None, ptr(v_quats), ptr(v_scales),
+        ptr(v_vm), stream(),
+    )
+    assert rc == 0
+    assert _rel(v_means, rbw[0]) < 1e-4 and _rel(v_quats, rbw[2]) < 1e-4 and _rel(v_scales, rbw[3]) < 1e-4
+    assert _rel(v_vm, rbw[4]) < 1e-3
