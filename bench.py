@@ -432,7 +432,7 @@ def main():
             "allreduce": allreduce_kind,
             "allreduce_bytes_per_rank": int(sum(params[k].numel() for k in grad_names) * 4),
             "gaussian_sharded": {
-                "what": "same job with rasterization(distributed=True): Gaussians sharded, all-to-all of projected rows, no all-reduce",
+                "what": "same job with rasterization(distributed=True): Gaussians sharded, all-to-all of the projected rows, no all-reduce (functional parity row, not tuned)",
                 "value": n_gpus * args.steps / (float(ms_sh.item()) * 1e-3), "unit": UNIT,
                 "ms_per_step": float(ms_sh.item()) / args.steps,
             },

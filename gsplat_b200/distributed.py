@@ -221,6 +221,17 @@ def all_gather_ints(value: int, device, group=None) -> List[int]:
     return [int(t.item()) for t in out]
 
 
+def all_gather_int_lists(values: Sequence[int], device, group=None) -> List[List[int]]:
+    """The same-length integer list of every rank (e.g. per-destination row counts), rank-major."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return [list(map(int, values))]
+    mine = torch.tensor(list(map(int, values)), dtype=torch.int64, device=device)
+    out = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return [t.tolist() for t in out]
+
+
 def all_gather_rows(tensors: Sequence[Tensor], counts: Sequence[int], group=None) -> List[Tensor]:
     """Differentiable all-gather of several row-aligned tensors [n_r, ...] (n_r = counts[rank]) in ONE
     collective: columns are concatenated, rows padded to max(counts), gathered, trimmed.  Returns the

@@ -223,12 +223,13 @@ def rasterization(
             raise ValueError("backgrounds must be [C_local, D] under distributed=True")
 
     # ---- packed=True: native two-pass compacting projection; everything downstream works on the [nnz, ...] rows
-    # (reference rendering.py:347-353, Rendering.cpp:936-973).  Under a multi-rank distributed=True the dense
-    # kernels run and the rows are gathered after the exchange (below).
-    native_packed = packed and not (distributed and world_size > 1)
+    # (reference rendering.py:347-353, Rendering.cpp:936-973).  Under a multi-rank distributed=True the compacted
+    # rows are what Seam B exchanges (only the visible (camera, gaussian) pairs travel).
+    sharded = distributed and world_size > 1
+    native_packed = packed
     camera_ids = gaussian_ids = batch_ids = None
     if native_packed:
-        batch_ids, camera_ids, gaussian_ids, _indptr, radii, means2d, depths, conics, compensations = fully_fused_projection(
+        batch_ids, camera_ids, gaussian_ids, indptr, radii, means2d, depths, conics, compensations = fully_fused_projection(
             means, covars, quats, scales, viewmats, Ks, width, height, eps2d=eps2d, near_plane=near_plane,
             far_plane=far_plane, radius_clip=radius_clip, packed=True, sparse_grad=sparse_grad,
             calc_compensations=antialiased, camera_model=camera_model, opacities=opacities,
@@ -257,7 +258,28 @@ def rasterization(
         )
 
     # ---- Seam B (distributed=True): all-to-all so that each rank holds ALL gaussians projected onto ITS cameras
-    if distributed and world_size > 1:
+    if sharded and packed:
+        # rows are sorted by (camera, gaussian): the rows of rank d's cameras are one contiguous range
+        C_local = C_world[world_rank]
+        cam0 = [sum(C_world[:d]) for d in range(world_size + 1)]
+        ip = indptr.tolist()
+        send = [ip[cam0[d + 1]] - ip[cam0[d]] for d in range(world_size)]
+        recv = [row[world_rank] for row in gdist.all_gather_int_lists(send, means.device)]
+        g0 = sum(N_world[:world_rank])  # global index of this rank's first gaussian
+        ints = torch.stack([radii[:, 0], radii[:, 1], (gaussian_ids + g0).int(), camera_ids.int()], dim=-1)
+        fields = [means2d, depths, conics, opac] + ([feat] if feat is not None else []) + [ints]
+        got = gdist.all_to_all_rows(fields, send, recv)
+        means2d, depths, conics, opac = got[0], got[1], got[2], got[3]
+        if feat is not None:
+            feat = got[4]
+        ints = got[-1]
+        radii = ints[:, :2].contiguous()
+        gaussian_ids = ints[:, 2].long()
+        camera_ids = ints[:, 3].long() - cam0[world_rank]
+        batch_ids = torch.zeros_like(camera_ids)
+        C, N = C_local, sum(N_world)
+        I = C
+    elif sharded:
         C_local = C_world[world_rank]
         send = [c * N for c in C_world]          # rows (camera-major) going to each camera owner
         recv = [C_local * n for n in N_world]    # rows arriving from each gaussian owner
@@ -292,26 +314,6 @@ def rasterization(
         )
     isect_offsets = isect_offset_encode(isect_ids, I, tile_width, tile_height)
     isect_offsets = isect_offsets.reshape(batch_dims + (C, tile_height, tile_width))
-
-    if packed and not native_packed:
-        # multi-rank distributed=True: the exchange above ran on dense [C, N] rows; gather the visible ones so that
-        # images, gradients and the meta contract are those of the reference's packed mode
-        sel = (radii > 0).all(dim=-1)  # [..., C, N]
-        flat_sel = sel.reshape(-1)
-        rows = torch.nonzero(flat_sel, as_tuple=False).squeeze(-1)  # ascending (b, c, n) order
-        inv = torch.cumsum(flat_sel, 0, dtype=torch.int64) - 1
-        gaussian_ids = rows % N
-        camera_ids = (rows // N) % C
-        batch_ids = rows // (N * C)
-        radii = radii.reshape(-1, 2)[rows]
-        means2d = means2d.reshape(-1, 2)[rows]
-        depths = depths.reshape(-1)[rows]
-        conics = conics.reshape(-1, 3)[rows]
-        opac = opac.reshape(-1)[rows]
-        if feat is not None:
-            feat = feat.reshape(-1, feat.shape[-1])[rows]
-        tiles_per_gauss = tiles_per_gauss.reshape(-1)[rows]
-        flatten_ids = inv[flatten_ids.long()].to(torch.int32)
 
     # ---- assemble channels: [colour | depth]
     if has_color and has_depth:

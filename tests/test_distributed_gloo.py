@@ -72,6 +72,8 @@ def _worker(rank, world, port, out):
     assert rx.shape == (sum(recv), 1) and rid.dtype == torch.int32 and torch.equal(rx[:, 0].long(), rid.long())
     rx.sum().backward()
     assert torch.allclose(x.grad, torch.ones_like(x))
+    lists = D.all_gather_int_lists([rank, 10 + rank, 7], torch.device("cpu"))
+    assert lists == [[0, 10, 7], [1, 11, 7]]
     # camera-major -> local layout
     t = torch.arange(2 * 3 + 2 * 4).float()
     loc = D.camera_major_to_local(t, 2, [3, 4])

@@ -782,7 +782,7 @@ def _torchrun2(script, port):
 
 def test_distributed_two_ranks_sharded():
     """Launches tests/dist_sharded_check.py on 2 GPUs (skipped on a 1-GPU box)."""
-    assert _torchrun2("dist_sharded_check.py", 29588).count("sharded check ok") == 3
+    assert _torchrun2("dist_sharded_check.py", 29588).count("sharded check ok") == 4
 
 
 def test_nvls_allreduce_two_ranks():
