@@ -1,10 +1,13 @@
-"""View-axis data parallelism for the rasterization() hot path.
+"""Multi-GPU plumbing of the rasterization() hot path.
 
-Every rank holds the full (replicated) set of Gaussian parameters and renders its own camera views; the
-only coupling is the sum of the parameter gradients, done here with ONE bucketed all-reduce of the
-59 floats / Gaussian (means 3 | quats 4 | scales 3 | opacities 1 | SH 48 -> 236 B) over NCCL
-(NVLink 5 / NVSwitch; gloo in the CPU tests).  This is not the reference's ``distributed=True`` mode
-(Gaussian-sharded, /root/reference/gsplat/distributed.py:117-272), which is a "next" row.
+(1) View-axis data parallelism: every rank holds the full (replicated) set of Gaussian
+parameters and renders its own camera views; the only coupling is the sum of the parameter gradients -- ONE
+all-reduce of the 59 floats / Gaussian (means 3 | quats 4 | scales 3 | opacities 1 | SH 48 -> 236 B), done by
+our own kernel over NVSwitch multicast / peer memory (``NvlsGradArena``, csrc/nvls.cu) or by NCCL / gloo
+(``all_reduce_gaussian_grads``).
+(2) The row collectives of the reference's ``distributed=True`` mode (Gaussian-sharded,
+/root/reference/gsplat/distributed.py:117-272): ``all_gather_rows`` (Seam A, cameras) and the differentiable
+uneven ``all_to_all_rows`` (Seam B, projected Gaussians), used by ``rendering.rasterization``.
 
 Launch: one process per GPU (torchrun / ``cli`` below, the reference's spawner restated from
 /root/reference/gsplat/distributed.py:319-375).

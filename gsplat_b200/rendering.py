@@ -4,10 +4,11 @@ offsets -> compositing, channel chunking, depth channels, meta dict) stays in Py
 reference's own Python restatement ``_rasterization`` (rendering.py:722-1106) and the C++ orchestrator it
 mirrors (csrc/Rendering.cpp:745-1481); every kernel is ours (gsplat_b200.ops).
 
-Scope: the 3DGS EWA path named by BASELINE.json (pinhole cameras, dense or "packed" bookkeeping,
-classic / antialiased, RGB / D / ED / RGB+D / RGB+ED, backgrounds, absgrad, SH or post-activation
-colours).  3DGUT (with_ut / with_eval3d), lidar, distortion, rolling shutter, extra signals and normals
-are out of scope and raise NotImplementedError.
+Scope: the 3DGS EWA path named by BASELINE.json (pinhole / orthographic / fisheye cameras, dense or
+``packed=True`` rows with optional ``sparse_grad``, classic / antialiased, RGB / D / ED / RGB+D / RGB+ED,
+backgrounds, masks, absgrad, SH or post-activation colours, ``distributed=True`` Gaussian sharding).
+3DGUT (with_ut / with_eval3d), lidar, distortion, rolling shutter, extra signals and normals are out of scope
+and raise NotImplementedError.
 """
 from __future__ import annotations
 
