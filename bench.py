@@ -404,38 +404,44 @@ def main():
         bounds = [int(round(i * N / world)) for i in range(world + 1)]
         shard = {k: params[k].detach()[bounds[rank] : bounds[rank + 1]].clone().requires_grad_(True) for k in params}
 
-        def sharded_step():
+        def sharded_step(packed):
             for p in shard.values():
                 p.grad = None
             rc, _, _ = gsplat_b200.rasterization(
                 shard["means"], shard["quats"], shard["scales"], shard["opacities"], shard["sh"], vm_dev, K_dev, W_IMG, H_IMG,
-                sh_degree=SH_DEGREE, packed=False, distributed=True,
+                sh_degree=SH_DEGREE, packed=packed, distributed=True,
             )
             (rc - target_dev).abs().mean().backward()
 
-        for _ in range(3):
-            sharded_step()
-        dist.barrier()
-        torch.cuda.synchronize()
-        ev[0].record()
-        for _ in range(args.steps):
-            sharded_step()
-        ev[1].record()
-        torch.cuda.synchronize()
-        dist.barrier()
-        ms_sh = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev)
-        dist.all_reduce(ms_sh, op=dist.ReduceOp.MAX)
+        sharded = {}
+        for packed in (False, True):
+            for _ in range(3):
+                sharded_step(packed)
+            dist.barrier()
+            torch.cuda.synchronize()
+            ev[0].record()
+            for _ in range(args.steps):
+                sharded_step(packed)
+            ev[1].record()
+            torch.cuda.synchronize()
+            dist.barrier()
+            ms_sh = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev)
+            dist.all_reduce(ms_sh, op=dist.ReduceOp.MAX)
+            sharded["packed" if packed else "dense"] = {
+                "value": n_gpus * args.steps / (float(ms_sh.item()) * 1e-3), "unit": UNIT,
+                "ms_per_step": float(ms_sh.item()) / args.steps,
+            }
         dp_info = {
             "per_rank_compute_ms": [round(float(t[0]), 3) for t in allr],
             "per_rank_allreduce_ms": [round(float(t[1]), 3) for t in allr],
             "per_rank_nccl_allreduce_ms": [round(float(t[2]), 3) for t in allr],
             "allreduce": allreduce_kind,
             "allreduce_bytes_per_rank": int(sum(params[k].numel() for k in grad_names) * 4),
-            "gaussian_sharded": {
-                "what": "same job with rasterization(distributed=True): Gaussians sharded, all-to-all of the projected rows, no all-reduce (functional parity row, not tuned)",
-                "value": n_gpus * args.steps / (float(ms_sh.item()) * 1e-3), "unit": UNIT,
-                "ms_per_step": float(ms_sh.item()) / args.steps,
-            },
+            "gaussian_sharded": dict(
+                what="same job with rasterization(distributed=True): Gaussians sharded, all-to-all of the projected rows "
+                "(dense: all C*N rows; packed: only the visible rows of the compacting projection), no all-reduce",
+                **sharded,
+            ),
         }
 
     # ---- roofline of the dominant kernels, timed alone with CUDA events on the launching stream

@@ -56,6 +56,10 @@ _SIGNATURES = {
         [c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_u32, c_f32, c_vp, c_vp, c_vp, c_vp,
          c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     ),
+    "gsb200_sh_rows_fwd": (c_int, [c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gsb200_sh_rows_bwd": (
+        c_int, [c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    ),
     "gsb200_projection_packed_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64]),
     "gsb200_projection_packed_count": (
         c_int,

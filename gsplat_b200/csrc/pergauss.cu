@@ -376,6 +376,87 @@ __global__ void __launch_bounds__(kThreads) sh_bwd_kernel(
         vcf[k * D + d] = 0.f;
 }
 
+// ---- SH on packed rows: row i = (batch_ids[i], camera_ids[i], gaussian_ids[i]); the coefficients stay in their
+// [N, K, D] table and are indexed in the kernel (no [nnz, K, D] gather as in the reference's packed call,
+// rendering.py:1001-1010).  One thread per (row, channel).
+template<int DEG>
+__global__ void __launch_bounds__(kThreads) sh_rows_fwd_kernel(
+    int64_t nnz, int64_t C, int64_t N, int64_t K, int64_t D, const float *__restrict__ means,
+    const float *__restrict__ viewmats, const float *__restrict__ coeffs, const int64_t *__restrict__ batch_ids,
+    const int64_t *__restrict__ camera_ids, const int64_t *__restrict__ gaussian_ids, float *__restrict__ colors
+)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(idx >= nnz * D)
+        return;
+    const int64_t i = idx / D, d = idx % D;
+    const int64_t b = batch_ids[i], c = camera_ids[i], n = gaussian_ids[i];
+    const float mean[3] = {means[(b * N + n) * 3], means[(b * N + n) * 3 + 1], means[(b * N + n) * 3 + 2]};
+    float dir[3];
+    sh_view_dir(mean, viewmats + (b * C + c) * 16, dir);
+    const float inorm = 1.f / sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    constexpr int NB  = (DEG + 1) * (DEG + 1);
+    Dual<false> Y[NB];
+    sh_basis<DEG, false>(dir[0] * inorm, dir[1] * inorm, dir[2] * inorm, Y);
+    const float *cf = coeffs + n * K * D;
+    float acc       = 0.f;
+#pragma unroll
+    for(int k = 0; k < NB; ++k)
+        acc += Y[k].v * cf[k * D + d];
+    colors[idx] = acc;
+}
+
+// v_coeffs [N, K, D], v_means [B*N, 3] and v_dirsum [B*C, 3] are zero-initialised by the host and summed with
+// atomics (a gaussian seen by several cameras owns several rows).
+template<int DEG>
+__global__ void __launch_bounds__(kThreads) sh_rows_bwd_kernel(
+    int64_t nnz, int64_t C, int64_t N, int64_t K, int64_t D, const float *__restrict__ means,
+    const float *__restrict__ viewmats, const float *__restrict__ coeffs, const int64_t *__restrict__ batch_ids,
+    const int64_t *__restrict__ camera_ids, const int64_t *__restrict__ gaussian_ids, const float *__restrict__ v_colors,
+    float *__restrict__ v_coeffs, float *__restrict__ v_means, float *__restrict__ v_dirsum
+)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(idx >= nnz * D)
+        return;
+    const int64_t i = idx / D, d = idx % D;
+    const int64_t b = batch_ids[i], c = camera_ids[i], n = gaussian_ids[i];
+    const float *mean = means + (b * N + n) * 3;
+    float dir[3];
+    sh_view_dir(mean, viewmats + (b * C + c) * 16, dir);
+    const float inorm = 1.f / sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    const float u[3]  = {dir[0] * inorm, dir[1] * inorm, dir[2] * inorm};
+    constexpr int NB  = (DEG + 1) * (DEG + 1);
+    Dual<true> Y[NB];
+    sh_basis<DEG, true>(u[0], u[1], u[2], Y);
+    const float vc  = v_colors[idx];
+    const float *cf = coeffs + n * K * D;
+    float *vcf      = v_coeffs + n * K * D;
+    float vu[3]     = {0.f, 0.f, 0.f};
+#pragma unroll
+    for(int k = 0; k < NB; ++k)
+    {
+        atomicAdd(vcf + k * D + d, Y[k].v * vc);
+        const float g = cf[k * D + d] * vc;
+        vu[0] += g * Y[k].x;
+        vu[1] += g * Y[k].y;
+        vu[2] += g * Y[k].z;
+    }
+    if(DEG >= 1 && (v_means != nullptr || v_dirsum != nullptr))
+    {
+        const float dot = vu[0] * u[0] + vu[1] * u[1] + vu[2] * u[2];
+#pragma unroll
+        for(int j = 0; j < 3; ++j)
+        {
+            const float vd = (vu[j] - dot * u[j]) * inorm;
+            if(v_means != nullptr)
+                atomicAdd(v_means + (b * N + n) * 3 + j, vd);
+            if(v_dirsum != nullptr)
+                atomicAdd(v_dirsum + (b * C + c) * 3 + j, vd);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ fused projection + conic + SH -> RGB
 // One thread per (camera, gaussian).  SH coefficients of a visible gaussian are fetched with 128-bit
 // loads (48 floats = 12 x float4 when K = 16); culled gaussians never touch them.
@@ -1522,6 +1603,53 @@ extern "C" int gsb200_projection_packed_bwd(
         v_conics_stride, v_compensations, sparse_grad == 0, v_means, v_covars, v_quats, v_scales, v_viewmats            \
     )
     GSB_CAM_SWITCH(camera_model, CALL)
+#undef CALL
+    return check_launch();
+}
+
+// ---- SH on packed rows (coefficients indexed in place; used by rasterization(packed=True))
+extern "C" int gsb200_sh_rows_fwd(
+    int64_t nnz, int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, int degrees_to_use, const float *means,
+    const float *viewmats, const float *coeffs, const int64_t *batch_ids, const int64_t *camera_ids,
+    const int64_t *gaussian_ids, float *colors, void *stream
+)
+{
+    if(nnz < 0 || B < 0 || C < 0 || N < 0 || K <= 0 || D <= 0 || degrees_to_use < 0 || degrees_to_use > 4
+       || (int64_t)(degrees_to_use + 1) * (degrees_to_use + 1) > K)
+        return GSB200_E_INVALID;
+    if(nnz == 0)
+        return GSB200_OK;
+    if(!means || !viewmats || !coeffs || !batch_ids || !camera_ids || !gaussian_ids || !colors)
+        return GSB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(d) sh_rows_fwd_kernel<d><<<grid_for(nnz * D, kThreads), kThreads, 0, st>>>(nnz, C, N, K, D, means, viewmats, coeffs, batch_ids, camera_ids, gaussian_ids, colors)
+    GSB_DEG_SWITCH(degrees_to_use, CALL)
+#undef CALL
+    return check_launch();
+}
+
+extern "C" int gsb200_sh_rows_bwd(
+    int64_t nnz, int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, int degrees_to_use, const float *means,
+    const float *viewmats, const float *coeffs, const int64_t *batch_ids, const int64_t *camera_ids,
+    const int64_t *gaussian_ids, const float *v_colors, float *v_coeffs, float *v_means, float *v_dirsum, void *stream
+)
+{
+    if(nnz < 0 || B < 0 || C < 0 || N < 0 || K <= 0 || D <= 0 || degrees_to_use < 0 || degrees_to_use > 4
+       || (int64_t)(degrees_to_use + 1) * (degrees_to_use + 1) > K || !v_coeffs)
+        return GSB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if(N > 0)
+        GSB_CUDA_TRY(cudaMemsetAsync(v_coeffs, 0, sizeof(float) * (size_t)(N * K * D), st));
+    if(v_means && B * N > 0)
+        GSB_CUDA_TRY(cudaMemsetAsync(v_means, 0, sizeof(float) * 3 * (size_t)(B * N), st));
+    if(v_dirsum && B * C > 0)
+        GSB_CUDA_TRY(cudaMemsetAsync(v_dirsum, 0, sizeof(float) * 3 * (size_t)(B * C), st));
+    if(nnz == 0)
+        return GSB200_OK;
+    if(!means || !viewmats || !coeffs || !batch_ids || !camera_ids || !gaussian_ids || !v_colors)
+        return GSB200_E_INVALID;
+#define CALL(d) sh_rows_bwd_kernel<d><<<grid_for(nnz * D, kThreads), kThreads, 0, st>>>(nnz, C, N, K, D, means, viewmats, coeffs, batch_ids, camera_ids, gaussian_ids, v_colors, v_coeffs, v_means, v_dirsum)
+    GSB_DEG_SWITCH(degrees_to_use, CALL)
 #undef CALL
     return check_launch();
 }

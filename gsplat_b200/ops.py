@@ -401,6 +401,73 @@ class _SphericalHarmonics(torch.autograd.Function):
         return None, v_means, v_viewmats, v_coeffs, None
 
 
+class _SphericalHarmonicsRows(torch.autograd.Function):
+    """SH colours of packed rows (batch_ids, camera_ids, gaussian_ids) with the coefficient table [N, K, D] indexed
+    inside the kernel -- what rasterization(packed=True) uses instead of gathering [nnz, K, D] rows first."""
+
+    @staticmethod
+    def forward(ctx, degrees_to_use, means, viewmats, coeffs, batch_ids, camera_ids, gaussian_ids):
+        dev = require_cuda(means, viewmats, coeffs)
+        means, viewmats, coeffs = f32c(means, "means"), f32c(viewmats, "viewmats"), f32c(coeffs, "coeffs")
+        ids = [t.to(torch.int64).contiguous() for t in (batch_ids, camera_ids, gaussian_ids)]
+        batch = tuple(means.shape[:-2])
+        B, N, C = _prod(batch), means.shape[-2], viewmats.shape[-3]
+        K, D = coeffs.shape[-2:]
+        nnz = ids[0].shape[0]
+        colors = torch.empty((nnz, D), device=dev, dtype=torch.float32)
+        with _Ctx(dev) as st:
+            check(
+                lib().gsb200_sh_rows_fwd(
+                    nnz, B, C, N, K, D, degrees_to_use, ptr(means), ptr(viewmats), ptr(coeffs), ptr(ids[0]), ptr(ids[1]),
+                    ptr(ids[2]), ptr(colors), st,
+                ),
+                "spherical_harmonics (rows)",
+            )
+        ctx.save_for_backward(means, viewmats, coeffs, *ids)
+        ctx.deg = degrees_to_use
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        means, viewmats, coeffs, b_ids, c_ids, g_ids = ctx.saved_tensors
+        batch = tuple(means.shape[:-2])
+        B, N, C = _prod(batch), means.shape[-2], viewmats.shape[-3]
+        K, D = coeffs.shape[-2:]
+        v_colors = v_colors.contiguous()
+        v_coeffs = torch.empty_like(coeffs)
+        v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
+        need_vm = ctx.needs_input_grad[2]
+        v_dirsum = torch.empty(batch + (C, 3), device=means.device, dtype=torch.float32) if need_vm else None
+        with _Ctx(means.device) as st:
+            check(
+                lib().gsb200_sh_rows_bwd(
+                    b_ids.shape[0], B, C, N, K, D, ctx.deg, ptr(means), ptr(viewmats), ptr(coeffs), ptr(b_ids), ptr(c_ids),
+                    ptr(g_ids), ptr(v_colors), ptr(v_coeffs), ptr(v_means), ptr(v_dirsum), st,
+                ),
+                "spherical_harmonics_bwd (rows)",
+            )
+        v_viewmats = None
+        if need_vm:  # dir = mean + R^T t  =>  dL/dR[i][j] = t[i] S[j],  dL/dt = R S,  S = sum of dL/ddir over the camera's rows
+            R, t = viewmats[..., :3, :3], viewmats[..., :3, 3]
+            v_viewmats = torch.zeros_like(viewmats)
+            v_viewmats[..., :3, :3] = t[..., :, None] * v_dirsum[..., None, :]
+            v_viewmats[..., :3, 3] = torch.einsum("...ij,...j->...i", R, v_dirsum)
+        return None, v_means, v_viewmats, v_coeffs, None, None, None
+
+
+def spherical_harmonics_rows(
+    degrees_to_use: int, means: Tensor, viewmats: Tensor, coeffs: Tensor, batch_ids: Tensor, camera_ids: Tensor,
+    gaussian_ids: Tensor,
+) -> Tensor:
+    """SH colours [nnz, D] of the packed rows (batch_ids, camera_ids, gaussian_ids); ``coeffs`` is the full
+    [N, K, D] table (NOT pre-gathered).  Same values as ``spherical_harmonics(..., coeffs[gaussian_ids], ids)``."""
+    if coeffs.dim() != 3 or coeffs.shape[0] != means.shape[-2]:
+        raise ValueError(f"coeffs must be [N, K, D]; got {tuple(coeffs.shape)} for N={means.shape[-2]}")
+    if not (0 <= degrees_to_use <= 4) or (degrees_to_use + 1) ** 2 > coeffs.shape[-2]:
+        raise ValueError(f"degrees_to_use={degrees_to_use} needs K >= {(degrees_to_use + 1) ** 2}, got {coeffs.shape[-2]}")
+    return _SphericalHarmonicsRows.apply(int(degrees_to_use), means, viewmats, coeffs, batch_ids, camera_ids, gaussian_ids)
+
+
 def spherical_harmonics(
     degrees_to_use: int,
     means: Tensor,  # [..., N, 3]

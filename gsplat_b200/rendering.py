@@ -26,6 +26,7 @@ from .ops import (
     isect_tiles,
     rasterize_to_pixels,
     spherical_harmonics,
+    spherical_harmonics_rows,
 )
 
 
@@ -236,21 +237,21 @@ def rasterization(
             calc_compensations=antialiased, camera_model=camera_model, opacities=opacities,
         )
         grow = batch_ids * N + gaussian_ids  # row of the gaussian in the flattened [B*N] parameter tensors
-        opac = opacities.reshape(-1)[grow]
+        # index_select: its backward is an atomic index_add (advanced indexing would sort the nnz indices)
+        opac = torch.index_select(opacities.reshape(-1), 0, grow)
         if compensations is not None:
             opac = opac * compensations
         feat = None
         if has_color:
             if sh_degree is None:
                 if colors.dim() == nb + 2:
-                    feat = colors.reshape(-1, colors.shape[-1])[grow]
+                    feat = torch.index_select(colors.reshape(-1, colors.shape[-1]), 0, grow)
                 else:
-                    feat = colors.reshape(-1, colors.shape[-1])[(batch_ids * C + camera_ids) * N + gaussian_ids]
+                    feat = torch.index_select(
+                        colors.reshape(-1, colors.shape[-1]), 0, (batch_ids * C + camera_ids) * N + gaussian_ids
+                    )
             else:
-                feat = spherical_harmonics(
-                    sh_degree, means, viewmats, colors[gaussian_ids], batch_ids=batch_ids, camera_ids=camera_ids,
-                    gaussian_ids=gaussian_ids,
-                )
+                feat = spherical_harmonics_rows(sh_degree, means, viewmats, colors, batch_ids, camera_ids, gaussian_ids)
                 feat = torch.clamp_min(feat + 0.5, 0.0)
     else:
         radii, means2d, depths, conics, feat, compensations, opac = _project_dense(

@@ -118,6 +118,22 @@ extern "C"
         float *v_sh_coeffs, void *stream
     );
 
+    /* ---- spherical harmonics on packed rows (reference: spherical_harmonics with batch_ids / camera_ids /
+     * gaussian_ids, ext.cpp:994-1002, rendering.py:1001-1010).  Row i = (batch_ids[i], camera_ids[i],
+     * gaussian_ids[i]); coeffs stay [N, K, D] and are indexed in the kernel.  colors / v_colors [nnz, D].
+     * bwd: v_coeffs [N,K,D], v_means [B*N,3] (or NULL), v_dirsum [B*C,3] (or NULL) are zeroed here, then summed. */
+    int gsb200_sh_rows_fwd(
+        int64_t nnz, int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, int degrees_to_use, const float *means,
+        const float *viewmats, const float *coeffs, const int64_t *batch_ids, const int64_t *camera_ids,
+        const int64_t *gaussian_ids, float *colors, void *stream
+    );
+    int gsb200_sh_rows_bwd(
+        int64_t nnz, int64_t B, int64_t C, int64_t N, int64_t K, int64_t D, int degrees_to_use, const float *means,
+        const float *viewmats, const float *coeffs, const int64_t *batch_ids, const int64_t *camera_ids,
+        const int64_t *gaussian_ids, const float *v_colors, float *v_coeffs, float *v_means, float *v_dirsum,
+        void *stream
+    );
+
     /* ---- projection_ewa_3dgs_packed / _bwd : ext.cpp:1065-1077, _wrapper.py:1065-1191, host
      * csrc/Projection.cpp:858-1260, kernel csrc/ProjectionEWA3DGSPacked.cu ----
      * Two passes, nothing of size B*C*N is allocated.  Pass 1 leaves per-block counts and their scan in

@@ -678,6 +678,7 @@ def test_mcmc_ops(gs):
 
 def test_packed_operator_variants(gs):
     """packed=True forms of the per-op surface (COO rows) against the dense ops."""
+    from gsplat_b200 import ops
     sc = scene.make_scene(n_max=30000, sh_degree=2)
     W, H, C = 320, 180, 2
     Ks = scene.rescale_K(sc["Ks"], sc["width"], sc["height"], W, H)[:C]
@@ -735,6 +736,14 @@ def test_packed_operator_variants(gs):
     dense = gs.spherical_harmonics(2, means, vm, sh, masks=sel)
     packed = gs.spherical_harmonics(2, means, vm, sh[g_ids.long()], batch_ids=b_ids, camera_ids=c_ids, gaussian_ids=g_ids)
     torch.testing.assert_close(packed, dense[sel], rtol=1e-5, atol=1e-6)
+    # rows variant (coefficient table indexed in the kernel) == dense kernel on the visible rows, bit for bit; grads close
+    rows_col = ops.spherical_harmonics_rows(2, means, vm, sh, b_ids, c_ids, g_ids)
+    assert torch.equal(rows_col, dense[sel])
+    v = torch.randn_like(rows_col)
+    ga = torch.autograd.grad((rows_col * v).sum(), (sh, means), retain_graph=True)
+    gb = torch.autograd.grad((dense[sel] * v).sum(), (sh, means), retain_graph=True)
+    for a, b in zip(ga, gb):
+        assert float((a - b).norm() / b.norm()) < 1e-5
     # and the packed rows render the same image through rasterize_to_pixels(packed=True)
     off = gs.isect_offset_encode(p_ids, C, tw, th)
     col = torch.clamp_min(packed + 0.5, 0.0)

@@ -26,6 +26,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--grid", type=int, default=3)
 ap.add_argument("--breakdown", action="store_true")
+ap.add_argument("--packed", action="store_true")
 args = ap.parse_args()
 dev = "cuda:0"
 W, H = 1920, 1080
@@ -39,7 +40,7 @@ target = torch.rand((1, H, W, 3), device=dev)
 def step():
     for p in P.values():
         p.grad = None
-    rc, ra, meta = gsplat_b200.rasterization(P["means"], P["quats"], P["scales"], P["opacities"], P["sh"], vm, K, W, H, sh_degree=3, packed=False)
+    rc, ra, meta = gsplat_b200.rasterization(P["means"], P["quats"], P["scales"], P["opacities"], P["sh"], vm, K, W, H, sh_degree=3, packed=args.packed)
     (rc - target).abs().mean().backward()
     return meta
 
@@ -53,6 +54,13 @@ for _ in range(args.steps):
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print("n_isects", meta["flatten_ids"].numel(), "visible", int((meta["radii"] > 0).all(-1).sum()))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    step()
+e1.record()
+torch.cuda.synchronize()
+print(f"STEP ms (packed={args.packed}): {e0.elapsed_time(e1) / 10:.3f}")
 
 if args.breakdown:
     def t(fn, reps=20):
