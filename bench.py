@@ -42,7 +42,7 @@ def workload_config(n_gpus: int) -> dict:
     return {
         "workload": "BASELINE configs[2]: synthetic 1M Gaussians (test_garden crop tiled 3x3 = 1006065), "
         "1 view 1920x1080 per GPU, SH3, packed=False, near=0.01 far=1e10 eps2d=0.3",
-        "step": "rasterization fwd + L1 loss + bwd to means/quats/scales/opacities/SH"
+        "step": "rasterization fwd + L1 loss (fused l1_loss) + bwd to means/quats/scales/opacities/SH"
         + (" + all-reduce (SUM) of the Gaussian grads over NVLink" if n_gpus > 1 else ""),
         "views_per_step": n_gpus,
         "parallelism": f"view-axis DP x{n_gpus} (replicated Gaussians)" if n_gpus > 1 else "single GPU",
@@ -73,6 +73,12 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
+
+    def wait_ready(self, timeout: float = 5.0) -> None:
+        """Blocks until nvidia-smi has delivered its first sample (its start-up is then over)."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
 
     def mark(self) -> None:
         """Samples taken before this call (nvidia-smi start-up, warm-up steps) are not reported."""
@@ -316,7 +322,7 @@ def main():
             params["means"], params["quats"], params["scales"], params["opacities"], params["sh"], vm, K, W_IMG, H_IMG,
             sh_degree=SH_DEGREE, packed=False,
         )
-        loss = (rc - tgt).abs().mean()
+        loss = gsplat_b200.l1_loss(rc, tgt)  # == (rc - tgt).abs().mean(), fused (losses.py)
         loss.backward()
         if world > 1:
             all_reduce_grads()  # the 59 floats / Gaussian, one launch, in place
@@ -351,20 +357,23 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML init touches every GPU of the box) must not
-    # fall into the timed region; it then polls GPU 0 every 100 ms and only samples taken from here on are reported
+    # nvidia-smi is started, and waited for, BEFORE the warm-up: its start-up (NVML init touches every GPU of the
+    # box) must not fall into the timed region; it then polls GPU 0 every 100 ms; only samples taken after the
+    # warm-up are reported
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
+    if world > 1:
+        dist.barrier()
     for c in consumed:
         c.record()
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3)):  # the warm-up runs right before the timed region: clocks are up
         meta = step(False)
         issue_copy(i & 1)
         step(True, i & 1)
     torch.cuda.synchronize()
     if rank == 0:
-        time.sleep(0.3)  # let the sampler finish starting up
         sampler.mark()
     ms_dev = timed(False, args.steps)
     ms_e2e = timed(True, args.steps)
@@ -387,7 +396,7 @@ def main():
                 params["means"], params["quats"], params["scales"], params["opacities"], params["sh"], vm_dev, K_dev, W_IMG,
                 H_IMG, sh_degree=SH_DEGREE, packed=False,
             )
-            (rc - target_dev).abs().mean().backward()
+            gsplat_b200.l1_loss(rc, target_dev).backward()
             ev[1].record()
             all_reduce_grads()
             ev[2].record()
@@ -411,7 +420,7 @@ def main():
                 shard["means"], shard["quats"], shard["scales"], shard["opacities"], shard["sh"], vm_dev, K_dev, W_IMG, H_IMG,
                 sh_degree=SH_DEGREE, packed=packed, distributed=True,
             )
-            (rc - target_dev).abs().mean().backward()
+            gsplat_b200.l1_loss(rc, target_dev).backward()
 
         sharded = {}
         for packed in (False, True):
@@ -515,9 +524,9 @@ def main():
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
             },
             # our own kernels per step: project_sh_fwd, depth_key, isect_count, isect_emit, isect_offsets,
-            # pack_records, tile_order, raster_fwd, raster_bwd, project_sh_bwd (= 10; cub scan / radix-sort launches
+            # pack_records, tile_order, raster_fwd, l1 partial/final/bwd, raster_bwd, project_sh_bwd (= 13; cub scan / radix-sort launches
             # made by the library are not counted); timed region = `steps` device-resident + `steps` e2e steps
-            "gpu_launches": args.steps * 2 * (10 + (1 if arena is not None else 0)),
+            "gpu_launches": args.steps * 2 * (13 + (1 if arena is not None else 0)),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "ref_cuda": ref_cuda, "dp": dp_info,
         }
         print(json.dumps(line))

@@ -17,6 +17,7 @@ from .ops import (  # noqa: F401
     rasterize_to_pixels,
     spherical_harmonics,
 )
+from .losses import l1_loss  # noqa: F401
 from .optimizers import SelectiveAdam  # noqa: F401
 from .rendering import rasterization  # noqa: F401
 
@@ -42,5 +43,6 @@ __all__ = [
     "mcmc_perturb_positions",
     "adam",
     "SelectiveAdam",
+    "l1_loss",
     "has_3dgs",
 ]

@@ -25,6 +25,7 @@ UNITS = {
     "pergauss.cu": ["-fmad=false"],
     "sort.cu": [],
     "nvls.cu": [],
+    "loss.cu": [],
 }
 HEADERS = ["common.cuh", "gaussmath.cuh", os.path.join("..", "..", "include", "gsplat_b200.h")]
 

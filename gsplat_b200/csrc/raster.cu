@@ -83,14 +83,28 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(
     for(int t = threadIdx.x; t < n_tiles; t += blockDim.x)
         atomicAdd(&hist[bin_of(t)], 1);
     __syncthreads();
-    if(threadIdx.x == 0)
-    {
-        int32_t run = 0;
-        for(int i = 0; i < 256; ++i)
+    if(threadIdx.x < 32)
+    { // exclusive scan of the 256 bins by one warp: 8 consecutive bins per lane
+        const int base = threadIdx.x * 8;
+        int32_t local[8], sum = 0;
+#pragma unroll
+        for(int i = 0; i < 8; ++i)
         {
-            cursor[i] = run;
-            run += hist[i];
+            local[i] = sum;
+            sum += hist[base + i];
         }
+        int32_t incl = sum;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1)
+        {
+            const int32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if((int)threadIdx.x >= o)
+                incl += up;
+        }
+        const int32_t excl = incl - sum;
+#pragma unroll
+        for(int i = 0; i < 8; ++i)
+            cursor[base + i] = excl + local[i];
     }
     __syncthreads();
     for(int t = threadIdx.x; t < n_tiles; t += blockDim.x)

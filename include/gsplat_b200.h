@@ -257,6 +257,13 @@ extern "C"
         const uint8_t *valid, float lr, float b1, float b2, float eps, void *stream
     );
 
+    /* ---- fused photometric L1 of the train step (caller-side fusion; the reference trainer's
+     * F.l1_loss(colors, pixels), examples/simple_trainer.py): loss[0] = mean |a - b| (device scalar, deterministic
+     * two-level sum); bwd: v_a[i] = v_loss[0] / n * sign(a[i] - b[i]) with v_loss a device scalar. */
+    size_t gsb200_l1_loss_workspace_bytes(void);
+    int gsb200_l1_loss_fwd(int64_t n, const float *a, const float *b, float *loss, void *workspace, void *stream);
+    int gsb200_l1_loss_bwd(int64_t n, const float *a, const float *b, const float *v_loss, float *v_a, void *stream);
+
     /* ---- view-parallel gradient all-reduce (replaces the NCCL all-reduce of
      * gsplat_b200/distributed.py on NVSwitch systems) over NVLS multicast memory, in place.
      * Every rank calls this on its stream with the SAME n_floats (multiple of 4) and `blocks`:

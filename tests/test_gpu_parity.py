@@ -830,3 +830,20 @@ def test_selective_adam(gs):
     expect = w0 - 1e-2 * (0.1 * gref) / ((0.001 * gref * gref).sqrt() + 1e-8)
     torch.testing.assert_close(w.detach()[vis_t], expect[vis_t], rtol=1e-5, atol=1e-6)
     assert torch.equal(w.detach()[~vis_t], w0[~vis_t])
+
+
+def test_fused_l1_loss(gs):
+    """l1_loss == (a - b).abs().mean() and its autograd gradient; deterministic; odd sizes; scaled upstream gradient."""
+    g = torch.Generator(device=DEV).manual_seed(9)
+    for shape in ((1, 1080, 1920, 3), (3, 37, 53, 3), (5,)):
+        a = torch.rand(shape, device=DEV, generator=g).requires_grad_(True)
+        b = torch.rand(shape, device=DEV, generator=g)
+        b.view(-1)[::7] = a.detach().view(-1)[::7]  # exact zeros of a - b: subgradient 0 like torch
+        ours = gs.l1_loss(a, b)
+        ref = (a - b).abs().mean()
+        np.testing.assert_allclose(float(ours), float((a.double() - b.double()).abs().mean()), rtol=2e-6)
+        np.testing.assert_allclose(float(ours), float(ref), rtol=1e-5)
+        (g1,) = torch.autograd.grad(ours * 3.0, a)
+        (g2,) = torch.autograd.grad(ref * 3.0, a)
+        torch.testing.assert_close(g1, g2, rtol=1e-6, atol=0)
+        assert float(gs.l1_loss(a, b)) == float(ours)
