@@ -420,3 +420,23 @@ def adam(param, grad, exp_avg, exp_avg_sq, valid, lr, b1, b2, eps):
         keep = ~np.asarray(valid, bool).reshape((-1,) + (1,) * (param.ndim - 1))
         p, m, v = np.where(keep, param, p), np.where(keep, exp_avg, m), np.where(keep, exp_avg_sq, v)
     return p.astype(param.dtype), m.astype(param.dtype), v.astype(param.dtype)
+
+
+def l1_loss(a, b):
+    """mean |a - b| and d loss / d a = sign(a - b) / n  (the trainer's F.l1_loss; sign(0) = 0 like torch.abs)."""
+    d = a.astype(np.float64) - b.astype(np.float64)
+    return float(np.abs(d).mean()), (np.sign(d) / d.size).astype(a.dtype)
+
+
+def fully_fused_projection_packed(*args, **kwargs):
+    """packed=True bookkeeping over the dense projection (reference csrc/Projection.cpp:858-1060): the visible
+    (batch, camera, gaussian) rows in ascending order.  Returns (batch_ids, camera_ids, gaussian_ids int64 [nnz],
+    indptr int32 [B*C+1], radii, means2d, depths, conics, compensations) with [nnz, ...] rows."""
+    radii, means2d, depths, conics, comps = fully_fused_projection(*args, **kwargs)
+    C, N = radii.shape[-3], radii.shape[-2]
+    vis = (radii > 0).all(-1).reshape(-1, C, N)
+    b, c, n = np.nonzero(vis)
+    indptr = np.concatenate([[0], np.cumsum(vis.reshape(-1, N).sum(-1))]).astype(np.int32)
+    sel = vis.reshape(radii.shape[:-1])
+    return (b.astype(np.int64), c.astype(np.int64), n.astype(np.int64), indptr, radii[sel], means2d[sel], depths[sel],
+            conics[sel], None if comps is None else comps[sel])

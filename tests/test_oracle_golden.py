@@ -312,3 +312,41 @@ def test_mcmc_ops(golden_dir):
     newp = gso.mcmc_perturb_positions(f8("positions"), f8("quats"), f8("scales_log"), f8("opacities_logit"), f8("noise"),
                                       float(g["noise_scale"]), float(g["t"]), float(g["k"]))
     _close(newp, g["new_positions"], 1e-10, 1e-10, "new_positions")
+
+
+def test_adam_l1_and_packed_bookkeeping(golden_dir):
+    """Trainer-side oracle pieces against independent float64 torch formulas (CPU)."""
+    import torch
+
+    rng = np.random.RandomState(2)
+    p, g = rng.standard_normal((50, 3)), rng.standard_normal((50, 3)) * 0.1
+    m, v = rng.standard_normal((50, 3)) * 0.01, rng.random_sample((50, 3)) * 1e-3
+    vis = rng.random_sample(50) < 0.5
+    op, om, ov = gso.adam(p, g, m, v, vis, 1e-2, 0.9, 0.999, 1e-8)
+    tp, tg, tm, tv = (torch.tensor(x) for x in (p, g, m, v))
+    tm2 = 0.9 * tm + 0.1 * tg
+    tv2 = 0.999 * tv + 0.001 * tg * tg
+    tp2 = tp - 1e-2 * tm2 / (tv2.sqrt() + 1e-8)  # Adam without bias correction (csrc/AdamCUDA.cu:57-64)
+    sel = torch.tensor(vis)[:, None]
+    _close(op, torch.where(sel, tp2, tp).numpy(), 1e-12, 1e-14, "adam param")
+    _close(om, torch.where(sel, tm2, tm).numpy(), 1e-12, 1e-14, "adam exp_avg")
+    _close(ov, torch.where(sel, tv2, tv).numpy(), 1e-12, 1e-16, "adam exp_avg_sq")
+    a, b = rng.standard_normal((4, 5, 3)), rng.standard_normal((4, 5, 3))
+    b.reshape(-1)[::5] = a.reshape(-1)[::5]
+    ta = torch.tensor(a, requires_grad=True)
+    tl = (ta - torch.tensor(b)).abs().mean()
+    tl.backward()
+    loss, grad = gso.l1_loss(a, b)
+    assert abs(loss - float(tl.detach())) < 1e-15
+    _close(grad, ta.grad.numpy(), 1e-12, 1e-15, "l1 grad")
+    # packed rows == the dense rows with radii > 0, ascending (camera, gaussian), CSR indptr per camera
+    g = _load(golden_dir, "ref_projection.npz")
+    W, H = int(g["width"]), int(g["height"])
+    args = (g["means"], None, g["quats"], g["scales"], g["viewmats"], g["Ks"], W, H, 0.3, 0.01, 1e10, 0.0, True)
+    d = gso.fully_fused_projection(*args)
+    pk = gso.fully_fused_projection_packed(*args)
+    vis = (d[0] > 0).all(-1)
+    assert pk[3].tolist() == [0] + np.cumsum(vis.sum(-1)).tolist() and len(pk[0]) == vis.sum()
+    key = pk[1] * vis.shape[1] + pk[2]
+    assert (np.diff(key) > 0).all() and (pk[0] == 0).all()
+    assert np.array_equal(pk[5], d[1][vis]) and np.array_equal(pk[8], d[4][vis])
