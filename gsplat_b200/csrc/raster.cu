@@ -547,6 +547,7 @@ __global__ void __launch_bounds__(kWarps * 32, (CDIM <= 4 ? 5 : 1)) raster_bwd_k
     }
     // element offsets fit 32 bits (checked on the host: rows * stride < 2^32)
     const uint32_t my_stride = (uint32_t)my_stride64, my_stride_b = (uint32_t)my_stride_b64;
+    uint32_t lane_r = lane, has_dst = my_dst != nullptr ? 1u : 0u;
 
     const int num_batches = (range_end - range_start + kBatch - 1) / kBatch;
     // batch b covers sorted indices [first, first + count), walking back to front
@@ -588,8 +589,12 @@ __global__ void __launch_bounds__(kWarps * 32, (CDIM <= 4 ? 5 : 1)) raster_bwd_k
             const float4 *sgeom   = ring.geom(stage);
             const float4 *scol    = ring.color(stage);
             const int32_t *sid    = ring.ids(stage);
-            const int lim         = bin_final - first;      // local index of this pixel's last contributor
+            int lim               = bin_final - first;      // local index of this pixel's last contributor
             const int warp_lim    = warp_bin_final - first; // ... of the warp's
+            // keep these loop invariants in registers: ptxas otherwise rematerialises them (64-bit batch arithmetic,
+            // S2R of the lane id, the ids pointer) once per surviving gaussian
+            uint32_t sid_addr = (uint32_t)__cvta_generic_to_shared(sid);
+            asm volatile("" : "+r"(lim), "+r"(sid_addr), "+r"(lane_r), "+r"(has_dst));
             for(int c1 = count; c1 > 0; c1 -= 32)
             {
                 const int c0   = c1 - 32; // chunk covers local [c0, c1); c0 may be negative
@@ -654,9 +659,10 @@ __global__ void __launch_bounds__(kWarps * 32, (CDIM <= 4 ? 5 : 1)) raster_bwd_k
                             }
                         }
                     }
-                    Butterfly<MA, 16>::run(part, lane);
-                    const uint32_t gid = (uint32_t)sid[t];
-                    if(my_dst != nullptr)
+                    Butterfly<MA, 16>::run(part, lane_r);
+                    uint32_t gid;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(gid) : "r"(sid_addr + 4u * (uint32_t)t));
+                    if(has_dst != 0u)
                         atomicAdd(my_dst + (size_t)(gid * my_stride), part[0]);
                     if constexpr(MB > 0)
                     {
