@@ -590,11 +590,11 @@ __global__ void __launch_bounds__(kWarps * 32, (CDIM <= 4 ? 5 : 1)) raster_bwd_k
             const float4 *scol    = ring.color(stage);
             const int32_t *sid    = ring.ids(stage);
             int lim               = bin_final - first;      // local index of this pixel's last contributor
-            const int warp_lim    = warp_bin_final - first; // ... of the warp's
+            int warp_lim          = warp_bin_final - first; // ... of the warp's
             // keep these loop invariants in registers: ptxas otherwise rematerialises them (64-bit batch arithmetic,
             // S2R of the lane id, the ids pointer) once per surviving gaussian
             uint32_t sid_addr = (uint32_t)__cvta_generic_to_shared(sid);
-            asm volatile("" : "+r"(lim), "+r"(sid_addr), "+r"(lane_r), "+r"(has_dst));
+            asm volatile("" : "+r"(lim), "+r"(warp_lim), "+r"(sid_addr), "+r"(lane_r), "+r"(has_dst));
             for(int c1 = count; c1 > 0; c1 -= 32)
             {
                 const int c0   = c1 - 32; // chunk covers local [c0, c1); c0 may be negative
