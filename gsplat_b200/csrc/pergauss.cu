@@ -545,99 +545,136 @@ __global__ void __launch_bounds__(kThreads, 2) project_sh_bwd_kernel(
     float *__restrict__ v_scales, float *__restrict__ v_sh
 )
 {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if(n >= N)
-        return;
+    const int64_t n     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
     constexpr int NB    = (DEG + 1) * (DEG + 1);
-    const float mean[3] = {means[n * 3], means[n * 3 + 1], means[n * 3 + 2]};
-    const float4 q4     = *reinterpret_cast<const float4 *>(quats + n * 4);
-    const float q[4]    = {q4.x, q4.y, q4.z, q4.w};
-    const float s[3]    = {scales[n * 3], scales[n * 3 + 1], scales[n * 3 + 2]};
-    const M3 cov        = quat_scale_to_sym<false>(q, s);
-    float v_mean[3] = {0.f, 0.f, 0.f};
-    M3 v_cov;
-#pragma unroll
-    for(int k = 0; k < 9; ++k)
-        v_cov.m[k] = 0.f;
-    float acc[NB * 3];
-#pragma unroll
-    for(int k = 0; k < NB * 3; ++k)
-        acc[k] = 0.f;
-    const float *cf = sh + n * K * 3;
-    for(int64_t c = 0; c < C; ++c)
+    // Most gaussians are culled in every view: their gradient rows are zeros.  Those rows are written by the whole
+    // warp, coalesced (32 consecutive rows = one contiguous block), and their parameters are never loaded.
+    bool seen = false;
+    if(n < N)
+        for(int64_t c = 0; c < C; ++c)
+            seen |= radii[(c * N + n) * 2] > 0 && radii[(c * N + n) * 2 + 1] > 0;
+    if(seen)
     {
-        const int64_t idx = c * N + n;
-        if(!(radii[idx * 2] > 0 && radii[idx * 2 + 1] > 0))
-            continue;
-        const float *vm      = viewmats + c * 16;
-        const Cam cam        = load_cam(vm, Ks + c * 9);
-        const float conic[3] = {conics[idx * 3], conics[idx * 3 + 1], conics[idx * 3 + 2]};
-        const float vc[3]    = {v_conics[idx * s_c], v_conics[idx * s_c + 1], v_conics[idx * s_c + 2]};
-        const bool has_comp  = v_compensations != nullptr;
-        const ProjGrad g     = project_one_vjp(
-            mean, cov, cam, W, H, eps2d, conic, v_means2d[idx * s_m2], v_means2d[idx * s_m2 + 1], v_depths ? v_depths[idx * s_d] : 0.f,
-            vc, has_comp, has_comp ? compensations[idx] : 0.f, has_comp ? v_compensations[idx] : 0.f
-        );
-#pragma unroll
-        for(int k = 0; k < 3; ++k)
-            v_mean[k] += g.v_mean[k];
+        const float mean[3] = {means[n * 3], means[n * 3 + 1], means[n * 3 + 2]};
+        const float4 q4     = *reinterpret_cast<const float4 *>(quats + n * 4);
+        const float q[4]    = {q4.x, q4.y, q4.z, q4.w};
+        const float s[3]    = {scales[n * 3], scales[n * 3 + 1], scales[n * 3 + 2]};
+        const M3 cov        = quat_scale_to_sym<false>(q, s);
+        float v_mean[3] = {0.f, 0.f, 0.f};
+        M3 v_cov;
 #pragma unroll
         for(int k = 0; k < 9; ++k)
-            v_cov.m[k] += g.v_cov.m[k];
-        // SH part: relu mask re-derived from the stored post-activation colour
-        float vcol[3];
-#pragma unroll
-        for(int d = 0; d < 3; ++d)
-            vcol[d] = colors[idx * 3 + d] > 0.f ? v_colors[idx * s_col + d] : 0.f;
-        float dir[3];
-        sh_view_dir(mean, vm, dir);
-        const float inorm = 1.f / sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
-        const float u[3]  = {dir[0] * inorm, dir[1] * inorm, dir[2] * inorm};
-        float vu[3] = {0.f, 0.f, 0.f};
-        sh_visit<DEG, true>(u[0], u[1], u[2], [&](int k, const Dual<true> &Yk) {
-            float gk = 0.f;
-#pragma unroll
-            for(int d = 0; d < 3; ++d)
-            {
-                acc[k * 3 + d] += Yk.v * vcol[d];
-                gk += __ldg(cf + k * 3 + d) * vcol[d];
-            }
-            vu[0] += gk * Yk.x;
-            vu[1] += gk * Yk.y;
-            vu[2] += gk * Yk.z;
-        });
-        if(DEG >= 1)
-        {
-            const float dot = vu[0] * u[0] + vu[1] * u[1] + vu[2] * u[2];
-#pragma unroll
-            for(int j = 0; j < 3; ++j)
-                v_mean[j] += (vu[j] - dot * u[j]) * inorm;
-        }
-    }
-#pragma unroll
-    for(int k = 0; k < 3; ++k)
-        v_means[n * 3 + k] = v_mean[k];
-    float vq[4] = {0.f, 0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
-    quat_scale_sym_vjp<false>(q, s, v_cov, vq, vs);
-    *reinterpret_cast<float4 *>(v_quats + n * 4) = make_float4(vq[0], vq[1], vq[2], vq[3]);
-#pragma unroll
-    for(int k = 0; k < 3; ++k)
-        v_scales[n * 3 + k] = vs[k];
-    float *vsh = v_sh + n * K * 3;
-    if(((K * 3) & 3) == 0 && (NB * 3) % 4 == 0)
-    {
-#pragma unroll
-        for(int v = 0; v < NB * 3 / 4; ++v)
-            reinterpret_cast<float4 *>(vsh)[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
-    }
-    else
-    {
+            v_cov.m[k] = 0.f;
+        float acc[NB * 3];
 #pragma unroll
         for(int k = 0; k < NB * 3; ++k)
-            vsh[k] = acc[k];
+            acc[k] = 0.f;
+        const float *cf = sh + n * K * 3;
+        for(int64_t c = 0; c < C; ++c)
+        {
+            const int64_t idx = c * N + n;
+            if(!(radii[idx * 2] > 0 && radii[idx * 2 + 1] > 0))
+                continue;
+            const float *vm      = viewmats + c * 16;
+            const Cam cam        = load_cam(vm, Ks + c * 9);
+            const float conic[3] = {conics[idx * 3], conics[idx * 3 + 1], conics[idx * 3 + 2]};
+            const float vc[3]    = {v_conics[idx * s_c], v_conics[idx * s_c + 1], v_conics[idx * s_c + 2]};
+            const bool has_comp  = v_compensations != nullptr;
+            const ProjGrad g     = project_one_vjp(
+                mean, cov, cam, W, H, eps2d, conic, v_means2d[idx * s_m2], v_means2d[idx * s_m2 + 1], v_depths ? v_depths[idx * s_d] : 0.f,
+                vc, has_comp, has_comp ? compensations[idx] : 0.f, has_comp ? v_compensations[idx] : 0.f
+            );
+#pragma unroll
+            for(int k = 0; k < 3; ++k)
+                v_mean[k] += g.v_mean[k];
+#pragma unroll
+            for(int k = 0; k < 9; ++k)
+                v_cov.m[k] += g.v_cov.m[k];
+            // SH part: relu mask re-derived from the stored post-activation colour
+            float vcol[3];
+#pragma unroll
+            for(int d = 0; d < 3; ++d)
+                vcol[d] = colors[idx * 3 + d] > 0.f ? v_colors[idx * s_col + d] : 0.f;
+            float dir[3];
+            sh_view_dir(mean, vm, dir);
+            const float inorm = 1.f / sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+            const float u[3]  = {dir[0] * inorm, dir[1] * inorm, dir[2] * inorm};
+            float vu[3] = {0.f, 0.f, 0.f};
+            sh_visit<DEG, true>(u[0], u[1], u[2], [&](int k, const Dual<true> &Yk) {
+                float gk = 0.f;
+#pragma unroll
+                for(int d = 0; d < 3; ++d)
+                {
+                    acc[k * 3 + d] += Yk.v * vcol[d];
+                    gk += __ldg(cf + k * 3 + d) * vcol[d];
+                }
+                vu[0] += gk * Yk.x;
+                vu[1] += gk * Yk.y;
+                vu[2] += gk * Yk.z;
+            });
+            if(DEG >= 1)
+            {
+                const float dot = vu[0] * u[0] + vu[1] * u[1] + vu[2] * u[2];
+#pragma unroll
+                for(int j = 0; j < 3; ++j)
+                    v_mean[j] += (vu[j] - dot * u[j]) * inorm;
+            }
+        }
+#pragma unroll
+        for(int k = 0; k < 3; ++k)
+            v_means[n * 3 + k] = v_mean[k];
+        float vq[4] = {0.f, 0.f, 0.f, 0.f}, vs[3] = {0.f, 0.f, 0.f};
+        quat_scale_sym_vjp<false>(q, s, v_cov, vq, vs);
+        *reinterpret_cast<float4 *>(v_quats + n * 4) = make_float4(vq[0], vq[1], vq[2], vq[3]);
+#pragma unroll
+        for(int k = 0; k < 3; ++k)
+            v_scales[n * 3 + k] = vs[k];
+        float *vsh = v_sh + n * K * 3;
+        if(((K * 3) & 3) == 0 && (NB * 3) % 4 == 0)
+        {
+#pragma unroll
+            for(int v = 0; v < NB * 3 / 4; ++v)
+                reinterpret_cast<float4 *>(vsh)[v] = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+        }
+        else
+        {
+#pragma unroll
+            for(int k = 0; k < NB * 3; ++k)
+                vsh[k] = acc[k];
+        }
+        for(int64_t k = NB * 3; k < K * 3; ++k)
+            vsh[k] = 0.f;
     }
-    for(int64_t k = NB * 3; k < K * 3; ++k)
-        vsh[k] = 0.f;
+    else if(n < N)
+    {
+#pragma unroll
+        for(int k = 0; k < 3; ++k)
+            v_means[n * 3 + k] = 0.f, v_scales[n * 3 + k] = 0.f;
+        *reinterpret_cast<float4 *>(v_quats + n * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // zero rows of v_sh, warp-cooperatively: lane l writes chunk l, l + 32, ... of the warp's 32-row block
+    const unsigned zero_rows = __ballot_sync(0xffffffffu, n < N && !seen);
+    if(zero_rows != 0u)
+    {
+        const int64_t row0 = n - lane; // first row of this warp
+        const int64_t W3   = K * 3;
+        if((W3 & 3) == 0)
+        {
+            const int per_row = (int)(W3 >> 2);
+            float4 *base      = reinterpret_cast<float4 *>(v_sh + row0 * W3);
+            for(int f = (int)lane; f < 32 * per_row; f += 32)
+                if((zero_rows >> (f / per_row)) & 1u)
+                    base[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        else
+        {
+            float *base = v_sh + row0 * W3;
+            for(int f = (int)lane; f < 32 * (int)W3; f += 32)
+                if((zero_rows >> (f / (int)W3)) & 1u)
+                    base[f] = 0.f;
+        }
+    }
 }
 
 // ------------------------------------------------------------------ packed (compacting) projection
