@@ -19,6 +19,8 @@
 //    a sum issue one red.global.add each.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gsb
@@ -449,8 +451,11 @@ struct GradDst
     int64_t s_means2d, s_conics, s_colors, s_opacities, s_abs;
 };
 
-template<int CDIM, bool ABS>
-__global__ void __launch_bounds__(kWarps * 32, (CDIM <= 4 ? 5 : 1)) raster_bwd_kernel(
+// MINB = CTAs per SM the register allocation is held to (48 registers at 5): the kernel is issue-bound, so
+// occupancy and code quality trade against each other; the host picks the variant (default 5 for CDIM <= 4,
+// GSB200_BWD_MINBLOCKS = 4 | 5 | 6 overrides it for measurements).
+template<int CDIM, bool ABS, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd_kernel(
     const uint32_t I, const int64_t n_isects, const float4 *__restrict__ gcull, const float4 *__restrict__ ggeom,
     const float4 *__restrict__ gcolor, const int32_t *__restrict__ order, const int32_t *__restrict__ flatten_ids,
     const float *__restrict__ backgrounds,
@@ -734,26 +739,55 @@ static int launch_bwd(
     const size_t smem  = ring_smem_bytes<CDIM>();
     const unsigned n_tiles = (unsigned)(I * tw * th);
     const int32_t *order   = (n_tiles >= 2 * 148) ? r.order : nullptr; // written by the forward
-    if(dst.abs != nullptr)
+#define GSB_BWD_LAUNCH(ABSV, MINBV)                                                                                     \
+    do                                                                                                                  \
+    {                                                                                                                   \
+        GSB_CUDA_TRY(cudaFuncSetAttribute(                                                                              \
+            raster_bwd_kernel<CDIM, ABSV, MINBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem                \
+        ));                                                                                                             \
+        raster_bwd_kernel<CDIM, ABSV, MINBV><<<n_tiles, kWarps * 32, smem, st>>>(                                        \
+            (uint32_t)I, S, r.cull, r.geom, r.color, order, flatten_ids, backgrounds, masks, W, H, tw, th, offsets,     \
+            render_alphas, last_ids, v_render_colors, v_render_alphas, dst                                              \
+        );                                                                                                              \
+    } while(0)
+    const bool absg = dst.abs != nullptr;
+    if constexpr(CDIM <= 4)
     {
-        GSB_CUDA_TRY(cudaFuncSetAttribute(
-            raster_bwd_kernel<CDIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem
-        ));
-        raster_bwd_kernel<CDIM, true><<<n_tiles, kWarps * 32, smem, st>>>(
-            (uint32_t)I, S, r.cull, r.geom, r.color, order, flatten_ids, backgrounds, masks, W, H, tw, th, offsets,
-            render_alphas, last_ids, v_render_colors, v_render_alphas, dst
-        );
+        static const int minb = [] {
+            const char *e = std::getenv("GSB200_BWD_MINBLOCKS");
+            const int v   = e ? std::atoi(e) : 5;
+            return (v == 4 || v == 6) ? v : 5;
+        }();
+        if(minb == 4)
+        {
+            if(absg)
+                GSB_BWD_LAUNCH(true, 4);
+            else
+                GSB_BWD_LAUNCH(false, 4);
+        }
+        else if(minb == 6)
+        {
+            if(absg)
+                GSB_BWD_LAUNCH(true, 6);
+            else
+                GSB_BWD_LAUNCH(false, 6);
+        }
+        else
+        {
+            if(absg)
+                GSB_BWD_LAUNCH(true, 5);
+            else
+                GSB_BWD_LAUNCH(false, 5);
+        }
     }
     else
     {
-        GSB_CUDA_TRY(cudaFuncSetAttribute(
-            raster_bwd_kernel<CDIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem
-        ));
-        raster_bwd_kernel<CDIM, false><<<n_tiles, kWarps * 32, smem, st>>>(
-            (uint32_t)I, S, r.cull, r.geom, r.color, order, flatten_ids, backgrounds, masks, W, H, tw, th, offsets,
-            render_alphas, last_ids, v_render_colors, v_render_alphas, dst
-        );
+        if(absg)
+            GSB_BWD_LAUNCH(true, 1);
+        else
+            GSB_BWD_LAUNCH(false, 1);
     }
+#undef GSB_BWD_LAUNCH
     return check_launch();
 }
 } // namespace gsb
