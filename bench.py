@@ -506,6 +506,15 @@ def main():
         "note": "compositing is FP32/MUFU-bound, not HBM-bound (SURVEY.md section 8d): the HBM fraction is reported as "
         "required, pair throughput below is the meaningful figure",
         "raster_fwd": {"ms": ms_rfwd, "achieved": bytes_fwd / (ms_rfwd * 1e-3) / 1e9, "algorithmic_bytes": bytes_fwd},
+        # compute-side figure: candidate (pixel, gaussian) pairs = 256 per (tile, gaussian)
+        # intersection; the kernels are instruction-issue bound (profiles/r01_v6_ncu.md: 81 % / 87 % issue-active)
+        "pairs": {
+            "candidate_pairs": 256 * S,
+            "bwd_gpairs_per_s": 256 * S / (ms_rbwd * 1e-3) / 1e9,
+            "fwd_gpairs_per_s": 256 * S / (ms_rfwd * 1e-3) / 1e9,
+            "issue_peak_ginst_per_s": 148 * 4 * 1.965,
+            "issue_evidence": "profiles/r01_v6_ncu.md (smsp__issue_active, smsp__inst_executed)",
+        },
     }
 
     if rank == 0:
