@@ -104,3 +104,29 @@ def test_argument_validation_is_reference_like():
         gsplat_b200.rasterization(z(4, 3), z(4, 4), z(4, 3), z(4), z(4, 3), torch.eye(4)[None], torch.eye(3)[None], 32, 32, tile_size=8)
     with pytest.raises(ValueError):
         gsplat_b200.spherical_harmonics(3, z(4, 3), torch.eye(4)[None], z(4, 9, 3))
+
+
+def test_rasterization_argument_validation_on_cpu():
+    """Flags outside the path raise before any kernel is touched (reference: ValueError / NotImplementedError from the
+    renderer-config checks, rendering.py:526-600); everything else fails loudly on non-CUDA tensors."""
+    import pytest
+    import torch
+
+    import gsplat_b200 as gs
+    from gsplat_b200._cabi import GsplatB200Error
+
+    N = 10
+    args = (torch.rand(N, 3), torch.rand(N, 4), torch.rand(N, 3), torch.rand(N), torch.rand(N, 3), torch.eye(4)[None],
+            torch.eye(3)[None], 64, 64)
+    for kw in (dict(with_ut=True), dict(with_eval3d=True), dict(camera_model="ftheta"), dict(camera_model="lidar"),
+               dict(return_normals=True)):
+        with pytest.raises(NotImplementedError):
+            gs.rasterization(*args, **kw)
+    for kw in (dict(render_mode="bogus"), dict(tile_size=8), dict(rasterize_mode="soft"), dict(sparse_grad=True, packed=False),
+               dict(distributed=True)):
+        with pytest.raises(ValueError):
+            gs.rasterization(*args, **kw)
+    with pytest.raises(ValueError):  # SH degree needs K >= (deg + 1)^2
+        gs.rasterization(*args[:4], torch.rand(N, 4, 3), *args[5:], sh_degree=2)
+    with pytest.raises(GsplatB200Error):
+        gs.rasterization(*args)
