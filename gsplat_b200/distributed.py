@@ -159,9 +159,16 @@ class NvlsGradArena:
 
     def allocator(self, name: str, like: Tensor) -> Optional[Tensor]:
         v = self.views.get(name)
+        if v is None or v.shape != like.shape:
+            return None
+        p = self.params.get(name)
+        if p is not None and p.grad is not None and p.grad.data_ptr() == v.data_ptr():
+            # gradient accumulation across backward passes: the segment still holds the accumulated .grad, so this
+            # backward must write elsewhere (autograd then adds it in); the arena expects zero_grad(set_to_none=True)
+            return None
         # a FRESH tensor object over the arena segment: autograd adopts a gradient as .grad without copying only
         # when nothing else references that tensor object
-        return v.detach() if v is not None and v.shape == like.shape else None
+        return v.detach()
 
     def all_reduce(self) -> None:
         """Sums the .grad of all registered parameters over the ranks, in place in the arena."""
