@@ -104,3 +104,36 @@ def test_single_process_is_identity():
     D.all_reduce_gaussian_grads(p)
     assert torch.allclose(p[0].grad, torch.full((3,), 5.0))
     assert D.shard_views(5, rank=1, world_size=2) == [1, 3]
+
+
+def test_grad_arena_allocator_logic():
+    """NvlsGradArena.allocator (host logic only; the arena memory itself needs GPUs): hands out FRESH views of its
+    segments -- which autograd then adopts as .grad without a copy -- except while a segment still holds an
+    accumulated gradient."""
+    from gsplat_b200 import distributed as D
+
+    p = torch.nn.Parameter(torch.ones(4, 3))
+    flat = torch.zeros(64)
+    arena = D.NvlsGradArena.__new__(D.NvlsGradArena)
+    arena.params = {"means": p}
+    arena.views = {"means": flat[:12].view(4, 3)}
+    a = arena.allocator("means", p)
+    assert a is not arena.views["means"] and a.data_ptr() == flat.data_ptr()
+    assert arena.allocator("quats", p) is None and arena.allocator("means", torch.ones(5, 3)) is None
+
+    class F(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            return x * 2
+
+        @staticmethod
+        def backward(ctx, g):
+            out = arena.allocator("means", p)
+            out = torch.empty_like(p) if out is None else out
+            out.copy_(g * 2)
+            return out
+
+    F.apply(p).sum().backward()
+    assert p.grad.data_ptr() == flat.data_ptr() and torch.equal(p.grad, torch.full((4, 3), 2.0))
+    F.apply(p).sum().backward()  # accumulation: the segment is occupied, the second gradient is added into it
+    assert p.grad.data_ptr() == flat.data_ptr() and torch.equal(p.grad, torch.full((4, 3), 4.0))
