@@ -330,6 +330,64 @@ def camera_major_to_local(t: Tensor, C_local: int, N_world: Sequence[int]) -> Te
     return torch.cat(parts, dim=1)
 
 
+# ---- the reference's helper names (gsplat/distributed.py:25-272), same arguments and results, over the collectives above
+def all_gather_int32(world_size: int, value, device: Optional[torch.device] = None) -> List:
+    """One 32-bit integer from every rank (a list of ints for an int input, of 0-d tensors for a tensor input).
+    Reference: gsplat/distributed.py:25-67.  Not differentiable."""
+    if world_size == 1:
+        return [value]
+    if isinstance(value, int):
+        assert device is not None, "device is required for scalar input"
+        return [int(v) for v in all_gather_ints(value, device)]
+    mine = value.reshape(1)
+    out = [torch.empty_like(mine) for _ in range(world_size)]
+    dist.all_gather(out, mine)
+    return [t.reshape(()) for t in out]
+
+
+def all_to_all_int32(world_size: int, values: Sequence, device: Optional[torch.device] = None) -> List:
+    """Rank r sends values[j] to rank j and receives one integer from every rank (gsplat/distributed.py:70-114)."""
+    if world_size == 1:
+        return list(values)
+    assert len(values) == world_size, "The length of values should be equal to world_size"
+    scalars = [isinstance(v, int) for v in values]
+    if any(scalars):
+        assert device is not None, "device is required for scalar input"
+    dev = device if device is not None else next(v.device for v in values if not isinstance(v, int))
+    table = all_gather_int_lists([int(v) for v in values], dev)  # table[src][dst]
+    me = dist.get_rank()
+    got = [table[src][me] for src in range(world_size)]
+    return [g if is_int else torch.tensor(g, dtype=torch.int, device=dev) for g, is_int in zip(got, scalars)]
+
+
+def all_gather_tensor_list(world_size: int, tensor_list: Sequence[Tensor]) -> List[Tensor]:
+    """Differentiable all-gather of row-aligned tensors [(N, *), ...] -> [(N * world_size, *), ...], rank-major
+    (gsplat/distributed.py:117-182).  Every rank must pass the same N."""
+    if world_size == 1:
+        return list(tensor_list)
+    n = len(tensor_list[0])
+    for t in tensor_list:
+        assert len(t) == n, "All tensors should have the same first dimension size"
+    return all_gather_rows(list(tensor_list), [n] * world_size)
+
+
+def all_to_all_tensor_list(
+    world_size: int, tensor_list: Sequence[Tensor], splits: Sequence, output_splits: Optional[Sequence] = None
+) -> List[Tensor]:
+    """Differentiable all-to-all of row-aligned tensors: the first splits[j] rows... go to rank j
+    (gsplat/distributed.py:185-272).  ``output_splits`` = all_to_all_int32(world_size, splits) when omitted."""
+    if world_size == 1:
+        return list(tensor_list)
+    n = len(tensor_list[0])
+    for t in tensor_list:
+        assert len(t) == n, "All tensors should have the same first dimension size"
+    assert len(splits) == world_size, "The length of splits should be equal to world_size"
+    send = [int(s) for s in splits]
+    if output_splits is None:
+        output_splits = all_to_all_int32(world_size, send, device=tensor_list[0].device)
+    return all_to_all_rows(list(tensor_list), send, [int(r) for r in output_splits])
+
+
 def cli(fn: Callable, args, verbose: bool = False) -> None:
     """Spawn one process per visible GPU and run ``fn(local_rank, world_rank, world_size, args)``
     (single node).  Under torchrun (RANK set) the process group is created from the environment."""

@@ -72,6 +72,21 @@ def _worker(rank, world, port, out):
     assert rx.shape == (sum(recv), 1) and rid.dtype == torch.int32 and torch.equal(rx[:, 0].long(), rid.long())
     rx.sum().backward()
     assert torch.allclose(x.grad, torch.ones_like(x))
+    # the reference's helper names, on the examples of its docstrings (gsplat/distributed.py:133-141, 210-221)
+    cpu = torch.device("cpu")
+    assert D.all_gather_int32(world, 5 + rank, cpu) == [5, 6]
+    assert D.all_to_all_int32(world, [10 * rank + 1, 10 * rank + 2], cpu) == [1 + rank, 11 + rank]
+    tl = [torch.tensor([1, 2, 3]), torch.tensor([4, 5, 6])] if rank == 0 else [torch.tensor([7, 8, 9]), torch.tensor([10, 11, 12])]
+    g0, g1 = D.all_gather_tensor_list(world, tl)
+    assert g0.tolist() == [1, 2, 3, 7, 8, 9] and g1.tolist() == [4, 5, 6, 10, 11, 12]
+    if rank == 0:
+        tl, sp = [torch.tensor([1.0, 2.0, 3.0], requires_grad=True), torch.tensor([4, 5, 6])], [2, 1]
+    else:
+        tl, sp = [torch.tensor([7.0, 8.0], requires_grad=True), torch.tensor([9, 10])], [1, 1]
+    e0, e1 = D.all_to_all_tensor_list(world, tl, sp)
+    assert (e0.tolist(), e1.tolist()) == (([1.0, 2.0, 7.0], [4, 5, 9]) if rank == 0 else ([3.0, 8.0], [6, 10]))
+    (e0 * (rank + 1)).sum().backward()  # row r of the input went to rank dst: its gradient is dst + 1
+    assert tl[0].grad.tolist() == ([1.0, 1.0, 2.0] if rank == 0 else [1.0, 2.0])
     lists = D.all_gather_int_lists([rank, 10 + rank, 7], torch.device("cpu"))
     assert lists == [[0, 10, 7], [1, 11, 7]]
     # camera-major -> local layout

@@ -31,6 +31,11 @@ def _params(path, fn):
         ("quat_scale_to_covar_preci", "cuda/_wrapper.py", "ops.py"),
         ("adam", "cuda/_wrapper.py", "ops.py"),
         ("compute_relocation", "relocation.py", "ops.py"),
+        ("all_gather_int32", "distributed.py", "distributed.py"),
+        ("all_to_all_int32", "distributed.py", "distributed.py"),
+        ("all_gather_tensor_list", "distributed.py", "distributed.py"),
+        ("all_to_all_tensor_list", "distributed.py", "distributed.py"),
+        ("cli", "distributed.py", "distributed.py"),
     ],
 )
 def test_same_parameters_as_reference(fn, ref_file, our_file):
