@@ -30,6 +30,33 @@ def has_3dgs() -> bool:
     return True
 
 
+def has_adam() -> bool:
+    """Reference: _wrapper.py:286 -- the selective ``adam`` op is built."""
+    return True
+
+
+def has_reloc() -> bool:
+    """Reference: _wrapper.py:290 -- ``relocation`` (and the MCMC position perturbation) are built."""
+    return True
+
+
+def has_2dgs() -> bool:
+    return False
+
+
+def has_3dgut() -> bool:
+    return False
+
+
+def has_losses() -> bool:
+    """The reference's fused Gaussian regularisation losses (losses_fused.py) are out of scope."""
+    return False
+
+
+def has_camera_wrappers() -> bool:
+    return False
+
+
 __all__ = [
     "rasterization",
     "fully_fused_projection",
@@ -45,4 +72,10 @@ __all__ = [
     "SelectiveAdam",
     "l1_loss",
     "has_3dgs",
+    "has_adam",
+    "has_reloc",
+    "has_2dgs",
+    "has_3dgut",
+    "has_losses",
+    "has_camera_wrappers",
 ]
