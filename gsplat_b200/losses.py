@@ -21,6 +21,11 @@ class _L1Loss(torch.autograd.Function):
         if a.dtype != torch.float32 or b.dtype != torch.float32:
             raise TypeError("l1_loss: float32 tensors expected")
         a, b = a.contiguous(), b.contiguous()
+        # the kernels read float4: a contiguous VIEW with a storage offset may be only 4-byte aligned
+        if a.data_ptr() % 16:
+            a = a.clone()
+        if b.data_ptr() % 16:
+            b = b.clone()
         if a.numel() == 0:
             raise ValueError("l1_loss of an empty tensor")
         L = lib()
