@@ -17,7 +17,7 @@ from .ops import (  # noqa: F401
     rasterize_to_pixels,
     spherical_harmonics,
 )
-from .losses import l1_loss  # noqa: F401
+from .losses import l1_loss, ssim_loss  # noqa: F401
 from .optimizers import SelectiveAdam  # noqa: F401
 from .rendering import rasterization  # noqa: F401
 
@@ -71,6 +71,7 @@ __all__ = [
     "adam",
     "SelectiveAdam",
     "l1_loss",
+    "ssim_loss",
     "has_3dgs",
     "has_adam",
     "has_reloc",

@@ -226,11 +226,25 @@ __global__ void __launch_bounds__(kThreads) projection_bwd_kernel(
             }
         }
         if(v_viewmats)
-        { // warp butterfly reduce of the 12 pose-gradient entries, one atomic per owning lane
-            Butterfly<12, 16>::run(vm_part, lane);
-            const int slot = butterfly_slot<12>(lane);
-            if(slot >= 0 && vm_part[0] != 0.f)
-                atomicAdd(v_viewmats + (b * C + c) * 16 + slot, vm_part[0]);
+        {
+            // warp butterfly reduce of the 12 pose-gradient entries, one atomic per owning lane -- valid only when
+            // every lane of the warp belongs to the same batch element (a warp straddles a batch boundary when N is
+            // not a multiple of 32: those lanes add their own entries)
+            const int64_t b0    = __shfl_sync(0xffffffffu, b, 0);
+            const bool same_b   = __all_sync(0xffffffffu, !active || b == b0);
+            if(same_b)
+            {
+                Butterfly<12, 16>::run(vm_part, lane);
+                const int slot = butterfly_slot<12>(lane);
+                if(slot >= 0 && vm_part[0] != 0.f)
+                    atomicAdd(v_viewmats + (b0 * C + c) * 16 + slot, vm_part[0]);
+            }
+            else if(vis)
+            {
+#pragma unroll
+                for(int k = 0; k < 12; ++k)
+                    atomicAdd(v_viewmats + (b * C + c) * 16 + k, vm_part[k]);
+            }
         }
     }
     if(!active)

@@ -29,11 +29,11 @@ constexpr int kBatch  = 128; // gaussians per ring stage
 constexpr int kStages = 2;
 constexpr int kWarps  = 8;
 
-template<int CDIM>
+template<int CDIM, int BATCH = kBatch>
 struct RecLayout
 {
     static constexpr int kColorVec4 = (CDIM + 3) / 4; // float4 per record for colours
-    static constexpr int kStageBytes = kBatch * (16 + 16 + 16 + 16 * kColorVec4);
+    static constexpr int kStageBytes = BATCH * (16 + 16 + 16 + 16 * kColorVec4);
 };
 
 struct RecordStreams
@@ -206,30 +206,30 @@ __device__ __forceinline__ const float4 *gaxis_from(const float4 *gcull, const f
 }
 
 // shared-memory ring: per stage [cull | axis | geom | color] + one full-barrier per stage
-template<int CDIM>
+template<int CDIM, int BATCH = kBatch>
 struct Ring
 {
     static constexpr int CV = RecLayout<CDIM>::kColorVec4;
+    static constexpr int kStageBytes = RecLayout<CDIM, BATCH>::kStageBytes;
     unsigned char *base;
 
     __device__ __forceinline__ void carve(unsigned char *smem) { base = smem; }
     __device__ __forceinline__ float4 *cull(int s) const
     {
-        return reinterpret_cast<float4 *>(base + (size_t)s * RecLayout<CDIM>::kStageBytes);
+        return reinterpret_cast<float4 *>(base + (size_t)s * kStageBytes);
     }
-    __device__ __forceinline__ float4 *axis(int s) const { return cull(s) + kBatch; }
-    __device__ __forceinline__ float4 *geom(int s) const { return cull(s) + 2 * kBatch; }
-    __device__ __forceinline__ float4 *color(int s) const { return cull(s) + 3 * kBatch; }
+    __device__ __forceinline__ float4 *axis(int s) const { return cull(s) + BATCH; }
+    __device__ __forceinline__ float4 *geom(int s) const { return cull(s) + 2 * BATCH; }
+    __device__ __forceinline__ float4 *color(int s) const { return cull(s) + 3 * BATCH; }
     __device__ __forceinline__ uint64_t *full(int s) const
     {
-        return reinterpret_cast<uint64_t *>(base + (size_t)kStages * RecLayout<CDIM>::kStageBytes) + s;
+        return reinterpret_cast<uint64_t *>(base + (size_t)kStages * kStageBytes) + s;
     }
     __device__ __forceinline__ int32_t *ids(int s) const
     {
-        return reinterpret_cast<int32_t *>(base + (size_t)kStages * RecLayout<CDIM>::kStageBytes + kStages * sizeof(uint64_t))
-             + s * kBatch;
+        return reinterpret_cast<int32_t *>(base + (size_t)kStages * kStageBytes + kStages * sizeof(uint64_t)) + s * BATCH;
     }
-    // one thread: arm the barrier and launch the three bulk copies of records [first, first+count)
+    // one thread: arm the barrier and launch the four bulk copies of records [first, first+count)
     __device__ __forceinline__ void issue(
         int stage, const float4 *gcull, const float4 *ggeom, const float4 *gcolor, int64_t first, int count
     ) const
@@ -244,11 +244,12 @@ struct Ring
     }
 };
 
-template<int CDIM>
+template<int CDIM, int BATCH = kBatch>
 constexpr size_t ring_smem_bytes()
 {
     // stages | full barriers | per-stage gaussian ids (backward only)
-    return (size_t)kStages * RecLayout<CDIM>::kStageBytes + kStages * sizeof(uint64_t) + (size_t)kStages * kBatch * sizeof(int32_t);
+    return (size_t)kStages * RecLayout<CDIM, BATCH>::kStageBytes + kStages * sizeof(uint64_t)
+         + (size_t)kStages * BATCH * sizeof(int32_t);
 }
 
 // Can the gaussian reach alpha >= 1/255 anywhere in the 8x4 pixel block centred at (cx, cy)?  Conservative:
@@ -689,6 +690,347 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
+// backward, version 2: transposed reduction.
+//
+// Version 1 above reduces the 9 (+2) per-pixel partials of every surviving (warp, gaussian) pair across the 32
+// lanes right away (butterfly: 12 shuffles + 12 adds + ~26 selects, 50 of its 130 instructions per survivor) and
+// issues 9 scalar REDs.  Version 2 splits the work in two phases per warp:
+//   phase A (lane = pixel, sequential over the depth-sorted survivors, as before): per survivor each lane only
+//     computes TWO scalars -- f = alpha * T (the weight of the gaussian's colour in this pixel) and
+//     o = vis * v_alpha (gated like the reference gates v_sigma) -- and stores them into a per-warp shared
+//     [survivor][pixel] buffer.  Everything the 9 gradients need is linear in f and o:
+//        v_rgb[k] = sum_p f v_c[k](p),  v_opacity = sum_p o,  v_sigma = -opacity * o  and
+//        v_xy / v_conic = sums of v_sigma * {dx, dy, dx^2, dx dy, dy^2}.
+//     The colour part of v_alpha needs only the SCALAR sum_{behind} fac_j (c_j . v_c) instead of the reference's
+//     per-channel `buffer[k]` (same value, one accumulator).
+//   phase B (lane = gaussian, after 16 survivors): each lane walks the 16 pixels of one half of the warp's 8x4
+//     block for ITS gaussian and accumulates the 6 moments of o about the half block's centre (pixel offsets are
+//     compile-time immediates) and the D colour sums in registers -- no cross-lane traffic; the moments are
+//     re-centred on the gaussian's mean once per gaussian, the two halves are combined with one shuffle per
+//     value, and the 12-float gradient record is added with three 128-bit REDs instead of nine scalar ones.
+// Per survivor: ~45 + ~16 instructions instead of 130.
+constexpr int kBwdBatch = 64; // records per ring stage (smaller than the forward's: the per-warp buffers need the room)
+constexpr int kRound    = 16; // survivors per reduction round of a warp
+constexpr int kRowF2    = 33; // row stride of the round buffer in float2 units (odd: conflict-free in both phases)
+
+template<int CDIM>
+struct Bwd2Smem
+{
+    static constexpr int CV          = RecLayout<CDIM>::kColorVec4;
+    static constexpr size_t ring_al  = (ring_smem_bytes<CDIM, kBwdBatch>() + 15) & ~size_t(15);
+    static constexpr size_t rbuf     = (size_t)kRound * kRowF2 * sizeof(float2);
+    static constexpr size_t meta     = (size_t)kRound * 2 * sizeof(float4);
+    static constexpr size_t pixc     = (size_t)32 * CV * sizeof(float4);
+    static constexpr size_t slot_t   = (size_t)kRound * sizeof(int32_t);
+    static constexpr size_t per_warp = rbuf + meta + pixc + slot_t;
+    static constexpr size_t total    = ring_al + kWarps * per_warp;
+};
+
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template<int CDIM, bool ABS, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
+    const uint32_t I, const int64_t n_isects, const float4 *__restrict__ gcull, const float4 *__restrict__ ggeom,
+    const float4 *__restrict__ gcolor, const int32_t *__restrict__ order, const int32_t *__restrict__ flatten_ids,
+    const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks, const uint32_t W, const uint32_t H,
+    const uint32_t tw, const uint32_t th, const int32_t *__restrict__ offsets, const float *__restrict__ render_alphas,
+    const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,
+    const float *__restrict__ v_render_alphas, const GradDst dst, const uint32_t packed_stride
+)
+{
+    constexpr int CV  = RecLayout<CDIM>::kColorVec4;
+    constexpr int NV  = 6 + CDIM + (ABS ? 2 : 0); // [v_xy 2 | v_conic 3 | v_opacity 1 | v_rgb CDIM | abs 2]
+    constexpr int NV4 = (NV + 3) / 4;
+    using SM          = Bwd2Smem<CDIM>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Ring<CDIM, kBwdBatch> ring;
+    ring.carve(smem_raw);
+    __shared__ int32_t s_tile_bin;
+
+    const TileGeom tg      = decode_tile(order, tw, th);
+    const unsigned tid     = threadIdx.x;
+    const unsigned warp    = tid >> 5, lane = tid & 31;
+    const int64_t tile_lin = (int64_t)tg.image_id * tw * th + tg.tile_id;
+    if(masks != nullptr && !masks[tile_lin])
+        return;
+    const int32_t range_start = offsets[tile_lin];
+    const int32_t range_end0  = (tile_lin == (int64_t)I * tw * th - 1) ? (int32_t)n_isects : offsets[tile_lin + 1];
+    if(range_end0 <= range_start)
+        return;
+
+    const int bx0 = tg.tile_x * kTile + (warp & 1) * 8;
+    const int by0 = tg.tile_y * kTile + (warp >> 1) * 4;
+    const int px_i = bx0 + (lane & 7), py_i = by0 + (lane >> 3);
+    const float px = (float)px_i + 0.5f, py = (float)py_i + 0.5f;
+    const bool inside = (px_i < (int)W) && (py_i < (int)H);
+    const int64_t pix = inside ? ((int64_t)tg.image_id * H + py_i) * W + px_i : 0;
+    const float *bg   = backgrounds ? backgrounds + (size_t)tg.image_id * CDIM : nullptr;
+
+    const float T_final = inside ? 1.0f - render_alphas[pix] : 1.f;
+    float T             = T_final;
+    float v_render_c[CV * 4];
+    float bg_dot = 0.f;
+#pragma unroll
+    for(int k = 0; k < CV * 4; ++k)
+    {
+        v_render_c[k] = (k < CDIM && inside) ? v_render_colors[pix * CDIM + k] : 0.f;
+        if(bg && k < CDIM)
+            bg_dot += bg[k] * v_render_c[k];
+    }
+    const float v_render_a       = inside ? v_render_alphas[pix] : 0.f;
+    const int32_t bin_final      = inside ? last_ids[pix] : -1;
+    const int32_t warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
+
+    if(tid == 0)
+    {
+        s_tile_bin = -1;
+#pragma unroll
+        for(int s = 0; s < kStages; ++s)
+            mbar_init(ring.full(s), 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if(lane == 0)
+        atomicMax(&s_tile_bin, warp_bin_final);
+    __syncthreads();
+    const int32_t range_end = min(range_end0, s_tile_bin + 1);
+    if(range_end <= range_start)
+        return;
+
+    // per-warp scratch: round buffer [survivor][pixel] of (f, o), per-survivor gaussian data, per-pixel v_render_c
+    unsigned char *wbase = smem_raw + SM::ring_al + (size_t)warp * SM::per_warp;
+    float2 *rbuf         = reinterpret_cast<float2 *>(wbase);
+    float4 *meta         = reinterpret_cast<float4 *>(wbase + SM::rbuf);
+    float4 *pixc         = reinterpret_cast<float4 *>(wbase + SM::rbuf + SM::meta);
+    int32_t *slot_t      = reinterpret_cast<int32_t *>(wbase + SM::rbuf + SM::meta + SM::pixc); // batch-local record index per slot
+#pragma unroll
+    for(int v = 0; v < CV; ++v)
+        pixc[lane * CV + v] = make_float4(v_render_c[4 * v], v_render_c[4 * v + 1], v_render_c[4 * v + 2], v_render_c[4 * v + 3]);
+
+    const int num_batches = (range_end - range_start + kBwdBatch - 1) / kBwdBatch;
+    auto batch_first = [&](int b) -> int64_t {
+        const int64_t bf = (int64_t)range_end - (int64_t)(b + 1) * kBwdBatch;
+        return bf > range_start ? bf : (int64_t)range_start;
+    };
+    auto batch_count = [&](int b) -> int { return (int)((int64_t)range_end - (int64_t)b * kBwdBatch - batch_first(b)); };
+    if(tid == 0)
+    {
+#pragma unroll
+        for(int s = 0; s < kStages; ++s)
+            if(s < num_batches)
+                ring.issue(s, gcull, ggeom, gcolor, batch_first(s), batch_count(s));
+    }
+    const float cx = (float)bx0 + 4.0f, cy = (float)by0 + 2.0f;
+    const float Tf_va = T_final * v_render_a - (bg ? T_final * bg_dot : 0.f); // T_final * (v_render_a - bg . v_render_c)
+    float behind      = 0.f; // sum over the contributors behind the current one of fac_j * (c_j . v_render_c)
+
+    // ---- phase B: 16 buffered survivors -> gradient records
+    // Per-survivor gaussian data is NOT copied in phase A (that cost 20 instructions per survivor on one lane): the
+    // batch-local record index goes into slot_t and slots [ncopied, nslots) are copied from the ring stage to `meta`,
+    // one slot per lane, right before they are needed (a flush) or before their stage is recycled (end of a batch).
+    int ncopied = 0;
+    auto materialise = [&](const int nslots, const float4 *scull, const float4 *sgeom, const int32_t *sid) {
+        __syncwarp();
+        const int sl = (int)lane;
+        if(sl >= ncopied && sl < nslots)
+        {
+            const int t      = slot_t[sl];
+            const float4 q   = scull[t];
+            const float4 g   = sgeom[t];
+            meta[sl * 2]     = make_float4(q.x, q.y, g.x, g.y);
+            meta[sl * 2 + 1] = make_float4(g.z, g.w, __int_as_float(sid[t]), 0.f);
+        }
+        ncopied = nslots;
+    };
+    auto flush = [&](const int nslots) {
+        __syncwarp();
+        const int gslot   = lane & (kRound - 1);
+        const int half    = lane >> 4; // which 8x2 half of the 8x4 pixel block this lane sums
+        const float2 *row = rbuf + gslot * kRowF2 + half * 16;
+        const float4 *pc  = pixc + half * 16 * CV;
+        const float4 m0 = meta[gslot * 2], m1 = meta[gslot * 2 + 1]; // {mx, my, a, b}, {c, opacity, id, -}
+        const float Dx = m0.x - cx, Dy = m0.y - (cy - 1.0f + 2.0f * (float)half); // mean relative to the half's centre
+        float M0 = 0.f, M1 = 0.f, M2 = 0.f, M3 = 0.f, M4 = 0.f, ax = 0.f, ay = 0.f;
+        float rgb[CV * 4];
+#pragma unroll
+        for(int k = 0; k < CV * 4; ++k)
+            rgb[k] = 0.f;
+#pragma unroll
+        for(int i = 0; i < 16; ++i)
+        {
+            const float2 fo = row[i];
+            const float xi = (float)(i & 7) - 3.5f, eta = (float)(i >> 3) - 0.5f; // pixel centre - half centre
+            M0 += fo.y;
+            M1 = fmaf(fo.y, xi, M1);
+            M2 = fmaf(fo.y, eta, M2);
+            M3 = fmaf(fo.y, xi * xi, M3);
+            M4 = fmaf(fo.y, xi * eta, M4); // eta is +-0.5: the eta^2 moment is 0.25 * M0
+#pragma unroll
+            for(int v = 0; v < CV; ++v)
+            {
+                const float4 c4 = pc[i * CV + v];
+                rgb[4 * v]     = fmaf(fo.x, c4.x, rgb[4 * v]);
+                rgb[4 * v + 1] = fmaf(fo.x, c4.y, rgb[4 * v + 1]);
+                rgb[4 * v + 2] = fmaf(fo.x, c4.z, rgb[4 * v + 2]);
+                rgb[4 * v + 3] = fmaf(fo.x, c4.w, rgb[4 * v + 3]);
+            }
+            if constexpr(ABS)
+            { // |v_sigma * d sigma/d mean| is not linear in o: summed per pixel
+                const float dxp = Dx - xi, dyp = Dy - eta;
+                ax += fabsf(fo.y * (m0.z * dxp + m0.w * dyp));
+                ay += fabsf(fo.y * (m0.w * dxp + m1.x * dyp));
+            }
+        }
+        // v_sigma = -opacity * o; moments about the gaussian's mean from the moments about the half's centre
+        const float nop = -m1.y;
+        const float U0 = nop * M0, U1 = nop * M1, U2 = nop * M2, U3 = nop * M3, U4 = nop * M4, U5 = 0.25f * U0;
+        const float Sdx = Dx * U0 - U1, Sdy = Dy * U0 - U2; // sum v_sigma dx, sum v_sigma dy
+        float vals[NV4 * 4];
+        vals[0] = m0.z * Sdx + m0.w * Sdy;
+        vals[1] = m0.w * Sdx + m1.x * Sdy;
+        vals[2] = 0.5f * (Dx * (Sdx - U1) + U3);
+        vals[3] = Dx * Sdy - Dy * U1 + U4;
+        vals[4] = 0.5f * (Dy * (Sdy - U2) + U5);
+        vals[5] = M0;
+#pragma unroll
+        for(int k = 0; k < CDIM; ++k)
+            vals[6 + k] = rgb[k];
+        if constexpr(ABS)
+        {
+            vals[6 + CDIM] = m1.y * ax;
+            vals[7 + CDIM] = m1.y * ay;
+        }
+#pragma unroll
+        for(int k = NV; k < NV4 * 4; ++k)
+            vals[k] = 0.f;
+#pragma unroll
+        for(int k = 0; k < NV; ++k)
+            vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], 16);
+        if(gslot < nslots)
+        {
+            const uint32_t gid = __float_as_uint(m1.z);
+            if(packed_stride != 0u)
+            { // one 16-byte aligned record per gaussian: 128-bit REDs, alternating between the two halves
+                float *rec = dst.means2d + (size_t)(gid * packed_stride);
+#pragma unroll
+                for(int c = 0; c < NV4; ++c)
+                    if((c & 1) == half)
+                        red_add_v4(rec + 4 * c, vals[4 * c], vals[4 * c + 1], vals[4 * c + 2], vals[4 * c + 3]);
+            }
+            else if(half == 0)
+            {
+                atomicAdd(dst.means2d + (size_t)gid * dst.s_means2d, vals[0]);
+                atomicAdd(dst.means2d + (size_t)gid * dst.s_means2d + 1, vals[1]);
+                atomicAdd(dst.conics + (size_t)gid * dst.s_conics, vals[2]);
+                atomicAdd(dst.conics + (size_t)gid * dst.s_conics + 1, vals[3]);
+                atomicAdd(dst.conics + (size_t)gid * dst.s_conics + 2, vals[4]);
+                atomicAdd(dst.opacities + (size_t)gid * dst.s_opacities, vals[5]);
+#pragma unroll
+                for(int k = 0; k < CDIM; ++k)
+                    atomicAdd(dst.colors + (size_t)gid * dst.s_colors + k, vals[6 + k]);
+                if constexpr(ABS)
+                {
+                    atomicAdd(dst.abs + (size_t)gid * dst.s_abs, vals[6 + CDIM]);
+                    atomicAdd(dst.abs + (size_t)gid * dst.s_abs + 1, vals[7 + CDIM]);
+                }
+            }
+        }
+        __syncwarp();
+    };
+
+    int nslots = 0;
+    for(int b = 0; b < num_batches; ++b)
+    {
+        const int stage       = b % kStages;
+        const uint32_t parity = (uint32_t)(b / kStages) & 1u;
+        const int32_t first   = (int32_t)batch_first(b);
+        const int count       = batch_count(b);
+        if((int)tid < count)
+            ring.ids(stage)[tid] = flatten_ids[first + tid];
+        __syncthreads();
+        if(first <= warp_bin_final)
+        {
+            mbar_wait(ring.full(stage), parity);
+            const float4 *scull = ring.cull(stage);
+            const float4 *saxis = ring.axis(stage);
+            const float4 *sgeom = ring.geom(stage);
+            const float4 *scol  = ring.color(stage);
+            const int32_t *sid  = ring.ids(stage);
+            const int lim       = bin_final - first;      // local index of this pixel's last contributor
+            const int warp_lim  = warp_bin_final - first; // ... of the warp's
+            for(int c1 = count; c1 > 0; c1 -= 32)
+            {
+                const int c0   = c1 - 32; // chunk covers local [c0, c1); c0 may be negative
+                const int mine = c0 + (int)lane;
+                bool hit       = false;
+                if(mine >= 0 && mine <= warp_lim)
+                    hit = block_may_touch(scull[mine], saxis[mine], cx, cy);
+                uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                while(mask)
+                {
+                    const int j = 31 - __clz(mask); // back to front
+                    mask ^= 1u << j;
+                    const int t    = c0 + j;
+                    const float4 q = scull[t];
+                    const float4 g = sgeom[t];
+                    const float dx = q.x - px, dy = q.y - py;
+                    const float sigma = 0.5f * (g.x * dx * dx + g.z * dy * dy) + g.y * dx * dy;
+                    const float vis   = fast_exp(-sigma);
+                    const float ov    = g.w * vis;
+                    const float alpha = fminf(kMaxAlpha, ov);
+                    const bool valid  = (t <= lim) && sigma >= 0.f && alpha >= kAlphaThreshold;
+                    if(!__any_sync(0xffffffffu, valid))
+                        continue;
+                    float f = 0.f, o = 0.f;
+                    if(valid)
+                    {
+                        float dot = 0.f;
+#pragma unroll
+                        for(int v = 0; v < CV; ++v)
+                        {
+                            const float4 cc = scol[t * CV + v];
+                            dot = fmaf(cc.x, v_render_c[4 * v], dot);
+                            if(4 * v + 1 < CDIM) dot = fmaf(cc.y, v_render_c[4 * v + 1], dot);
+                            if(4 * v + 2 < CDIM) dot = fmaf(cc.z, v_render_c[4 * v + 2], dot);
+                            if(4 * v + 3 < CDIM) dot = fmaf(cc.w, v_render_c[4 * v + 3], dot);
+                        }
+                        const float ra = fast_rcp(fmaxf(kMinOneMinusAlpha, 1.0f - alpha));
+                        T *= ra;
+                        f                   = alpha * T;
+                        const float v_alpha = fmaf(dot, T, ra * (Tf_va - behind));
+                        behind              = fmaf(dot, f, behind);
+                        if(ov <= kMaxAlpha)
+                            o = vis * v_alpha;
+                    }
+                    rbuf[nslots * kRowF2 + lane] = make_float2(f, o);
+                    slot_t[nslots]               = t; // every lane writes the same value: no predicate needed
+                    if(++nslots == kRound)
+                    {
+                        materialise(kRound, scull, sgeom, sid);
+                        flush(kRound);
+                        nslots = ncopied = 0;
+                    }
+                }
+            }
+            if(nslots > ncopied) // pending survivors of this batch: keep their data before the stage is recycled
+                materialise(nslots, scull, sgeom, sid);
+        }
+        __syncthreads(); // stage (records + ids) fully consumed
+        if(tid == 0)
+        {
+            mbar_wait(ring.full(stage), parity); // landed even if every warp skipped it
+            if(b + kStages < num_batches)
+                ring.issue(stage, gcull, ggeom, gcolor, batch_first(b + kStages), batch_count(b + kStages));
+        }
+    }
+    if(nslots > 0)
+        flush(nslots);
+}
+
+// ---------------------------------------------------------------------------------------------
 template<int CDIM>
 static int launch_fwd(
     int64_t I, int64_t N, const float *means2d, const float *conics, const float *colors, const float *opacities,
@@ -736,9 +1078,53 @@ static int launch_bwd(
     if(S == 0)
         return GSB200_OK; // reference: no launch when there are no intersections (Bwd.cu:350-354)
     RecordStreams r    = carve_records(const_cast<void *>(records), S, RecLayout<CDIM>::kColorVec4);
-    const size_t smem  = ring_smem_bytes<CDIM>();
     const unsigned n_tiles = (unsigned)(I * tw * th);
     const int32_t *order   = (n_tiles >= 2 * 148) ? r.order : nullptr; // written by the forward
+    const bool absg        = dst.abs != nullptr;
+    // version 2 (transposed reduction) is the default; GSB200_BWD_ALGO=butterfly selects version 1 (measurements)
+    static const bool use_v2 = [] {
+        const char *e = std::getenv("GSB200_BWD_ALGO");
+        return !(e && e[0] == 'b');
+    }();
+    if(use_v2)
+    {
+        // are the five destinations one packed, 16-byte aligned record [v_xy 2 | v_conic 3 | v_opacity 1 | v_rgb D | abs 2]?
+        const int64_t P  = dst.s_means2d;
+        uint32_t packed  = 0;
+        if(P > 0 && (P % 4) == 0 && P >= 6 + CDIM + (absg ? 2 : 0) && dst.s_conics == P && dst.s_colors == P && dst.s_opacities == P
+           && dst.conics == dst.means2d + 2 && dst.opacities == dst.means2d + 5 && dst.colors == dst.means2d + 6
+           && (!absg || (dst.s_abs == P && dst.abs == dst.means2d + 6 + CDIM)) && (reinterpret_cast<uintptr_t>(dst.means2d) & 15) == 0)
+            packed = (uint32_t)P;
+        const size_t smem2 = Bwd2Smem<CDIM>::total;
+#define GSB_BWD2_LAUNCH(ABSV, MINBV)                                                                                    \
+    do                                                                                                                  \
+    {                                                                                                                   \
+        GSB_CUDA_TRY(cudaFuncSetAttribute(                                                                              \
+            raster_bwd2_kernel<CDIM, ABSV, MINBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2              \
+        ));                                                                                                             \
+        raster_bwd2_kernel<CDIM, ABSV, MINBV><<<n_tiles, kWarps * 32, smem2, st>>>(                                      \
+            (uint32_t)I, S, r.cull, r.geom, r.color, order, flatten_ids, backgrounds, masks, W, H, tw, th, offsets,     \
+            render_alphas, last_ids, v_render_colors, v_render_alphas, dst, packed                                      \
+        );                                                                                                              \
+    } while(0)
+        if constexpr(CDIM <= 4)
+        {
+            if(absg)
+                GSB_BWD2_LAUNCH(true, 4);
+            else
+                GSB_BWD2_LAUNCH(false, 4);
+        }
+        else
+        {
+            if(absg)
+                GSB_BWD2_LAUNCH(true, 1);
+            else
+                GSB_BWD2_LAUNCH(false, 1);
+        }
+#undef GSB_BWD2_LAUNCH
+        return check_launch();
+    }
+    const size_t smem  = ring_smem_bytes<CDIM>();
 #define GSB_BWD_LAUNCH(ABSV, MINBV)                                                                                     \
     do                                                                                                                  \
     {                                                                                                                   \
@@ -750,7 +1136,6 @@ static int launch_bwd(
             render_alphas, last_ids, v_render_colors, v_render_alphas, dst                                              \
         );                                                                                                              \
     } while(0)
-    const bool absg = dst.abs != nullptr;
     if constexpr(CDIM <= 4)
     {
         static const int minb = [] {

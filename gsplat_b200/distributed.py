@@ -49,7 +49,12 @@ class GradBucket:
             o += n
         return self.flat
 
-    def unpack(self, scale: float = 1.0) -> None:
+    def unpack(self, scale: Optional[float] = None) -> None:
+        """Copy the (reduced) flat buffer back into the ``.grad`` tensors.  ``scale=None`` uses the factor stored
+        by ``all_reduce_gaussian_grads(average=True, async_op=True)`` (1.0 otherwise)."""
+        if scale is None:
+            scale = getattr(self, "_scale", 1.0)
+        self._scale = 1.0
         o = 0
         for p, n in zip(self.params, self.sizes):
             g = self.flat[o : o + n].view_as(p)
@@ -155,6 +160,7 @@ class NvlsGradArena:
             raise RuntimeError("NvlsGradArena: signal pad too small for the requested number of blocks")
         self.flat.zero_()
         self.views = {k: self.flat[self.offsets[k] : self.offsets[k] + p.numel()].view(p.shape) for k, p in self.params.items()}
+        self._handed_out = set()  # segments given to a backward kernel since the last all_reduce() / reset()
         self._lib = lib()
 
     def allocator(self, name: str, like: Tensor) -> Optional[Tensor]:
@@ -166,14 +172,26 @@ class NvlsGradArena:
             # gradient accumulation across backward passes: the segment still holds the accumulated .grad, so this
             # backward must write elsewhere (autograd then adds it in); the arena expects zero_grad(set_to_none=True)
             return None
+        if name in self._handed_out:
+            # a second fused rasterization() in the same backward graph (several renders summed into one loss): the
+            # backward kernels WRITE their outputs, so the same segment twice would overwrite the first gradient
+            # before autograd adds the two.  The second request gets ordinary memory; autograd accumulates.
+            return None
+        self._handed_out.add(name)
         # a FRESH tensor object over the arena segment: autograd adopts a gradient as .grad without copying only
         # when nothing else references that tensor object
         return v.detach()
+
+    def reset(self) -> None:
+        """Forget which segments were handed out (call after optimizer.zero_grad() when a step is abandoned
+        without all_reduce())."""
+        self._handed_out.clear()
 
     def all_reduce(self) -> None:
         """Sums the .grad of all registered parameters over the ranks, in place in the arena."""
         from ._cabi import check
 
+        self._handed_out.clear()
         for k, p in self.params.items():
             v = self.views[k]
             if p.grad is None:
@@ -388,6 +406,20 @@ def all_to_all_tensor_list(
     return all_to_all_rows(list(tensor_list), send, [int(r) for r in output_splits])
 
 
+def _distributed_worker(local_rank: int, world: int, fn: Callable, args) -> None:
+    """Spawn target of :func:`cli` (module level: the spawn start method pickles it; the reference keeps its
+    ``_distributed_worker`` at module level for the same reason, gsplat/distributed.py:275-316)."""
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", rank=local_rank, world_size=world)
+    try:
+        fn(local_rank, local_rank, world, args)
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def cli(fn: Callable, args, verbose: bool = False) -> None:
     """Spawn one process per visible GPU and run ``fn(local_rank, world_rank, world_size, args)``
     (single node).  Under torchrun (RANK set) the process group is created from the environment."""
@@ -406,15 +438,4 @@ def cli(fn: Callable, args, verbose: bool = False) -> None:
         fn(0, 0, 1, args)
         return
 
-    def _worker(local_rank: int):
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29511")
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", rank=local_rank, world_size=world)
-        try:
-            fn(local_rank, local_rank, world, args)
-        finally:
-            dist.barrier()
-            dist.destroy_process_group()
-
-    torch.multiprocessing.spawn(_worker, nprocs=world, join=True)
+    torch.multiprocessing.spawn(_distributed_worker, args=(world, fn, args), nprocs=world, join=True)

@@ -6,6 +6,8 @@ one backward instead of seven ATen launches over the 25 MB image.  The sum is a 
 reduction: bit-reproducible run to run."""
 from __future__ import annotations
 
+import ctypes
+
 import torch
 from torch import Tensor
 
@@ -51,3 +53,60 @@ class _L1Loss(torch.autograd.Function):
 def l1_loss(input: Tensor, target: Tensor) -> Tensor:
     """Mean absolute error over all elements (``torch.nn.functional.l1_loss`` with the default reduction)."""
     return _L1Loss.apply(input, target)
+
+
+class _SsimLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img1: Tensor, img2: Tensor):
+        dev = require_cuda(img1, img2)
+        B, C, H, W = img1.shape
+        L = lib()
+        need_grad = ctx.needs_input_grad[0]
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        maps = torch.empty((3, B, C, H, W), device=dev, dtype=torch.float32) if need_grad else None
+        ws = torch.empty(max(L.gsb200_ssim_workspace_bytes(B, C, H, W), 4), device=dev, dtype=torch.uint8)
+        xs = (ctypes.c_int64 * 4)(*img1.stride())
+        ys = (ctypes.c_int64 * 4)(*img2.stride())
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            check(L.gsb200_ssim_fwd(B, C, H, W, ptr(img1), xs, ptr(img2), ys, ptr(maps), ptr(ws), ptr(loss), st), "ssim_loss")
+        ctx.save_for_backward(img1, img2, maps)
+        return loss
+
+    @staticmethod
+    def backward(ctx, v_loss: Tensor):
+        img1, img2, maps = ctx.saved_tensors
+        if maps is None:
+            return None, None
+        B, C, H, W = img1.shape
+        v_loss = v_loss.to(dtype=torch.float32).contiguous()
+        v_x = torch.empty_strided(img1.shape, img1.stride(), device=img1.device, dtype=torch.float32)
+        xs = (ctypes.c_int64 * 4)(*img1.stride())
+        ys = (ctypes.c_int64 * 4)(*img2.stride())
+        vs = (ctypes.c_int64 * 4)(*v_x.stride())
+        with torch.cuda.device(img1.device):
+            st = torch.cuda.current_stream().cuda_stream
+            check(
+                lib().gsb200_ssim_bwd(B, C, H, W, ptr(img1), xs, ptr(img2), ys, ptr(maps), ptr(v_loss), ptr(v_x), vs, st),
+                "ssim_loss_bwd",
+            )
+        return v_x, None
+
+
+def ssim_loss(img1: Tensor, img2: Tensor, window_size: int = 11) -> Tensor:
+    """``1 - SSIM`` of two image batches ``(B, C, H, W)`` -- the reference's ``gsplat.losses.ssim_loss``
+    (/root/reference/gsplat/losses.py:154-201) as it evaluates without the third-party ``fused_ssim`` package:
+    11x11 Gaussian window (sigma 1.5), zero padding, mean over batch, channels and pixels.  One fused pass forward,
+    one backward; the images are read through their strides (the trainer's ``render.permute(0, 3, 1, 2)`` view is
+    not copied).  Gradient flows to ``img1`` only (the trainer's target image needs none)."""
+    if window_size != 11:
+        raise NotImplementedError("gsplat_b200.ssim_loss is built for the reference's default window_size=11")
+    if img1.dim() != 4 or img1.shape != img2.shape:
+        raise ValueError(f"ssim_loss expects two (B, C, H, W) tensors of equal shape, got {tuple(img1.shape)} and {tuple(img2.shape)}")
+    if img1.dtype != torch.float32 or img2.dtype != torch.float32:
+        raise TypeError("ssim_loss: float32 tensors expected")
+    if img2.requires_grad:
+        raise NotImplementedError("ssim_loss: gradient with respect to the second image is not implemented")
+    if any(s < 0 for s in img1.stride() + img2.stride()):
+        img1, img2 = img1.contiguous(), img2.contiguous()
+    return _SsimLoss.apply(img1, img2)

@@ -226,6 +226,9 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
         if sparse_grad and len(batch) != 0:
             raise ValueError("sparse_grad does not support batch dimensions")
         B, N, C = _prod(batch), means.shape[-2], viewmats.shape[-3]
+        if B * C > 65535:
+            # same launch geometry limit as the reference's packed kernel (ProjectionEWA3DGSPacked.cu:325-333): B*C on grid.y
+            raise RuntimeError(f"projection_ewa_3dgs_packed: B * C = {B * C} exceeds the CUDA grid.y limit of 65535")
         L = lib()
         o = dict(device=dev, dtype=torch.float32)
         nnz_dev = torch.empty(1, device=dev, dtype=torch.int32)
@@ -483,6 +486,15 @@ def spherical_harmonics(
     ``-R^T t``).  Returns [..., C, N, D]; masked-off rows are 0."""
     if viewmats_rs is not None:
         raise NotImplementedError("rolling-shutter view matrices are out of scope")
+    # the reference rejects these with TORCH_CHECK (RuntimeError), csrc/SphericalHarmonics.cpp
+    if not (0 <= degrees_to_use <= 4):
+        raise RuntimeError(f"degrees_to_use must be between 0 and 4, got {degrees_to_use}")
+    if coeffs.dim() == 3 and coeffs.shape[-1] == 0:
+        raise RuntimeError("spherical_harmonics: coeffs must have at least one channel (D > 0)")
+    if coeffs.dtype in (torch.float16, torch.bfloat16):
+        # half-precision coefficient storage (the trainer's sh_fp16 option): evaluated in fp32 like the reference
+        # kernel; the cast is differentiable, so v_coeffs comes back in the storage dtype
+        coeffs = coeffs.float()
     if batch_ids is not None or camera_ids is not None or gaussian_ids is not None:
         # packed mode: coeffs [nnz, K, D] pre-gathered, one (batch, camera, gaussian) triple per row.  The view
         # direction mean + R^T t is formed per row (torch, differentiable) and evaluated by the dense kernel
@@ -772,7 +784,9 @@ class _RasterizeToPixels(torch.autograd.Function):
         image_dims = tuple(isect_offsets.shape[:-2])
         row_dims = tuple(means2d.shape[:-1])
         I, R, D = _prod(image_dims), _prod(row_dims), colors.shape[-1]
-        N = R // I if I > 0 and R % max(I, 1) == 0 else R
+        # N only feeds the C ABI's 32-bit offset guard (I * N * stride < 2^32).  Dense rows: R == I * N.  Packed rows
+        # [nnz, *] are addressed flat: ceil(R / I) keeps I * N within I - 1 rows of the real row count R.
+        N = (R + I - 1) // I if I > 0 else R
         th, tw = isect_offsets.shape[-2:]
         m8 = None
         if masks is not None:

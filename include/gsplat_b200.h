@@ -264,6 +264,22 @@ extern "C"
     int gsb200_l1_loss_fwd(int64_t n, const float *a, const float *b, float *loss, void *workspace, void *stream);
     int gsb200_l1_loss_bwd(int64_t n, const float *a, const float *b, const float *v_loss, float *v_a, void *stream);
 
+    /* Fused SSIM loss of the train step (reference: gsplat/losses.py:110-201 torch_ssim_loss / ssim_loss, the
+     * D-SSIM term at examples/simple_trainer.py:951-961; torch path: 11x11 Gaussian window sigma 1.5, zero padding,
+     * per channel): loss[0] = 1 - mean SSIM(x, y) over B*C*H*W (device scalar, deterministic fixed-order sum).
+     * Images are addressed as p[b*s[0] + c*s[1] + h*s[2] + w*s[3]] (element strides: NCHW views of NHWC renders are
+     * read in place).  maps = 3*B*C*H*W floats kept for the backward (NULL: forward only); workspace:
+     * gsb200_ssim_workspace_bytes.  Backward: v_x = v_loss[0] * d loss / d x, written through v_strides. */
+    size_t gsb200_ssim_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W);
+    int gsb200_ssim_fwd(
+        int64_t B, int64_t C, int64_t H, int64_t W, const float *x, const int64_t *x_strides, const float *y,
+        const int64_t *y_strides, float *maps, void *workspace, float *loss, void *stream
+    );
+    int gsb200_ssim_bwd(
+        int64_t B, int64_t C, int64_t H, int64_t W, const float *x, const int64_t *x_strides, const float *y,
+        const int64_t *y_strides, const float *maps, const float *v_loss, float *v_x, const int64_t *v_strides, void *stream
+    );
+
     /* ---- view-parallel gradient all-reduce (replaces the NCCL all-reduce of
      * gsplat_b200/distributed.py on NVSwitch systems) over NVLS multicast memory, in place.
      * Every rank calls this on its stream with the SAME n_floats (multiple of 4) and `blocks`:

@@ -9,9 +9,12 @@ restated: -std=c++20 -O3 -DNDEBUG -use_fast_math -DGSPLAT_BUILD_3DGS=1 (every ot
 to off, csrc/Config.h:28-60) and -DGSPLAT_NUM_CHANNELS=1,3,4 (Config.h:70-72) to keep compile time sane.
 Target: sm_100a.  Only runs where /root/reference exists (the build container); the resulting .so is
 git-ignored but travels to the GPU box, where tests/test_gpu_vs_reference_cuda.py and bench.py load it
-with torch.ops.load_library and call torch.ops.gsplat.* directly.
+with torch.ops.load_library and call torch.ops.gsplat.* directly.  The pybind module inside is named ``csrc``
+(TORCH_EXTENSION_NAME), so that baseline/install_ref.py can also place a copy as the prebuilt ``gsplat/csrc.so``
+the reference's Python package imports first (gsplat/cuda/_backend.py:30) -- one process must load only ONE of
+the two copies (oracle/refcuda.py picks), else the TORCH_LIBRARY registration would run twice.
 
-    python oracle/build_ref.py [-j JOBS]
+    python oracle/build_ref.py [-j JOBS] [--full]
 """
 from __future__ import annotations
 
@@ -46,7 +49,7 @@ def main():
     inc += [sysconfig.get_paths()["include"]]
     incf = [f"-I{p}" for p in inc]
     defs = [
-        "-DTORCH_EXTENSION_NAME=gsplat_ref", "-DTORCH_API_INCLUDE_EXTENSION_H", "-DNDEBUG", "-DGSPLAT_BUILD_3DGS=1",
+        "-DTORCH_EXTENSION_NAME=csrc", "-DTORCH_API_INCLUDE_EXTENSION_H", "-DNDEBUG", "-DGSPLAT_BUILD_3DGS=1",
         "-DGSPLAT_BUILD_ADAM=1", "-DGSPLAT_BUILD_RELOC=1",
         f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
     ]
@@ -59,9 +62,24 @@ def main():
         "-D__CUDA_NO_HALF_OPERATORS__", "-D__CUDA_NO_HALF_CONVERSIONS__", "-D__CUDA_NO_BFLOAT16_CONVERSIONS__",
         "-D__CUDA_NO_HALF2_OPERATORS__",
     ]
+    # --full: the configuration the reference's own hot-path tests need to RUN rather than skip (tests/refsuite):
+    #   GSPLAT_BUILD_3DGUT=1          two tests of the 3DGS path (test_basic.py test_isect / the eval3d twins) are gated on it
+    #   GSPLAT_BUILD_CAMERA_WRAPPERS  tests/test_rasterization.py imports tests/test_cameras.py, which skips itself without them
+    #   GSPLAT_NUM_CHANNELS + 6, 32   channel counts test_basic.py renders (128 needs tile_size 4: not part of the b200 path)
+    # None of this changes the 3DGS kernels that get timed; it adds instantiations.  Objects go to obj_full/.
+    full = "--full" in sys.argv
+    objdir = OBJ
+    if full:
+        defs += ["-DGSPLAT_BUILD_3DGUT=1", "-DGSPLAT_BUILD_CAMERA_WRAPPERS=1"]
+        channels = "1,3,4,6,32"
+        cxx[-1] = f"-DGSPLAT_NUM_CHANNELS={channels}"
+        nvcc[nvcc.index("-DGSPLAT_NUM_CHANNELS=" + NUM_CHANNELS.replace(",", "\\,"))] = "-DGSPLAT_NUM_CHANNELS=" + channels.replace(",", "\\,")
+        sources.insert(0, os.path.join(REF, "csrc", "CameraWrappers.cu"))
+        objdir = OBJ + "_full"
+        os.makedirs(objdir, exist_ok=True)
     cmds, objs = [], []
     for s in sources:
-        o = os.path.join(OBJ, os.path.basename(s) + ".o")
+        o = os.path.join(objdir, os.path.basename(s) + ".o")
         objs.append(o)
         if os.path.exists(o) and os.path.getmtime(o) > os.path.getmtime(s):
             continue
@@ -84,7 +102,8 @@ def main():
         print("build_ref: compilation failed")
         return 1
     tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
-    link = ["/usr/bin/g++", "-shared", "-o", LIB] + objs + [
+    out_lib = LIB
+    link = ["/usr/bin/g++", "-shared", "-o", out_lib] + objs + [
         f"-L{tlib}", "-L/usr/local/cuda/lib64", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
         "-lcudart", f"-Wl,-rpath,{tlib}",
     ]
@@ -92,7 +111,7 @@ def main():
     if r.returncode != 0:
         print(r.stderr[-4000:])
         return 1
-    print("built", LIB, os.path.getsize(LIB) // 1024, "kB")
+    print("built", out_lib, os.path.getsize(out_lib) // 1024, "kB")
     return 0
 
 

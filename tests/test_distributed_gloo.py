@@ -132,7 +132,9 @@ def test_grad_arena_allocator_logic():
     arena = D.NvlsGradArena.__new__(D.NvlsGradArena)
     arena.params = {"means": p}
     arena.views = {"means": flat[:12].view(4, 3)}
+    arena._handed_out = set()
     a = arena.allocator("means", p)
+    arena.reset()
     assert a is not arena.views["means"] and a.data_ptr() == flat.data_ptr()
     assert arena.allocator("quats", p) is None and arena.allocator("means", torch.ones(5, 3)) is None
 
@@ -152,3 +154,56 @@ def test_grad_arena_allocator_logic():
     assert p.grad.data_ptr() == flat.data_ptr() and torch.equal(p.grad, torch.full((4, 3), 2.0))
     F.apply(p).sum().backward()  # accumulation: the segment is occupied, the second gradient is added into it
     assert p.grad.data_ptr() == flat.data_ptr() and torch.equal(p.grad, torch.full((4, 3), 4.0))
+
+
+def test_grad_arena_two_renders_in_one_graph():
+    """Two fused backward nodes feeding the same leaf within ONE backward graph (several renders summed into one
+    loss): the kernels write (not accumulate) their outputs, so only the first may get the arena segment; the leaf
+    must end up with g1 + g2."""
+    from gsplat_b200 import distributed as D
+
+    p = torch.nn.Parameter(torch.ones(4, 3))
+    flat = torch.zeros(64)
+    arena = D.NvlsGradArena.__new__(D.NvlsGradArena)
+    arena.params, arena.views, arena._handed_out = {"means": p}, {"means": flat[:12].view(4, 3)}, set()
+
+    class F(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, k):
+            ctx.k = k
+            return x * k
+
+        @staticmethod
+        def backward(ctx, g):
+            out = arena.allocator("means", p)
+            out = torch.empty_like(p) if out is None else out
+            out.copy_(g * ctx.k)  # WRITES, like project_sh_bwd
+            return out, None
+
+    (F.apply(p, 2.0).sum() + F.apply(p, 3.0).sum()).backward()
+    assert torch.equal(p.grad, torch.full((4, 3), 5.0)), p.grad
+    assert arena._handed_out == {"means"}
+
+
+def test_cli_spawn_target_is_picklable():
+    """cli() hands its worker to torch.multiprocessing.spawn, which pickles the target."""
+    import pickle
+
+    from gsplat_b200 import distributed as D
+
+    assert pickle.loads(pickle.dumps(D._distributed_worker)) is D._distributed_worker
+
+
+def test_async_average_scale_is_applied_by_unpack():
+    from gsplat_b200 import distributed as D
+
+    p = [torch.ones(3, requires_grad=True)]
+    (p[0] * 4).sum().backward()
+    bucket = D.GradBucket(p)
+    bucket.pack()
+    bucket._scale = 0.5  # what all_reduce_gaussian_grads(average=True, async_op=True) stores for world_size 2
+    bucket.unpack()
+    assert torch.allclose(p[0].grad, torch.full((3,), 2.0))
+    bucket.pack()
+    bucket.unpack()  # the stored factor is consumed once
+    assert torch.allclose(p[0].grad, torch.full((3,), 2.0))

@@ -847,3 +847,48 @@ def test_fused_l1_loss(gs):
         (g2,) = torch.autograd.grad(ref * 3.0, a)
         torch.testing.assert_close(g1, g2, rtol=1e-6, atol=0)
         assert float(gs.l1_loss(a, b)) == float(ours)
+
+
+def _torch_ssim_loss_f64(img1, img2):
+    """float64 restatement of the reference's torch path (gsplat/losses.py:82-151, 190-201): 11-tap Gaussian
+    window sigma 1.5, zero padding, per channel, 1 - mean."""
+    import torch.nn.functional as F
+
+    x = torch.arange(11, dtype=torch.float32)
+    g = torch.exp(-((x - 5) ** 2) / (2 * 1.5**2))
+    g = (g / g.sum()).double()
+    C = img1.shape[1]
+    w = (g[:, None] @ g[None, :])[None, None].expand(C, 1, 11, 11).contiguous().to(img1.device)
+    conv = lambda t: F.conv2d(t, w, padding=5, groups=C)  # noqa: E731
+    mu1, mu2 = conv(img1), conv(img2)
+    s11, s22, s12 = conv(img1 * img1) - mu1 * mu1, conv(img2 * img2) - mu2 * mu2, conv(img1 * img2) - mu1 * mu2
+    m = ((2 * mu1 * mu2 + 0.01**2) * (2 * s12 + 0.03**2)) / ((mu1 * mu1 + mu2 * mu2 + 0.01**2) * (s11 + s22 + 0.03**2))
+    return 1.0 - m.mean()
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc_view"])
+@pytest.mark.parametrize("shape", [(2, 3, 70, 95), (1, 3, 16, 16), (1, 1, 5, 37)])
+def test_fused_ssim_loss(gs, layout, shape):
+    torch.manual_seed(3)
+    B, C, H, W = shape
+    if layout == "nchw":
+        a = torch.rand(shape, device=DEV)
+        b = torch.rand(shape, device=DEV)
+    else:  # what the trainer passes: render[B,H,W,C].permute(0,3,1,2)
+        a = torch.rand((B, H, W, C), device=DEV).permute(0, 3, 1, 2)
+        b = torch.rand((B, H, W, C), device=DEV).permute(0, 3, 1, 2)
+    b = (0.7 * a + 0.3 * b).detach()  # correlated images: SSIM away from 0
+    a.requires_grad_(True)
+    loss = gs.ssim_loss(a, b)
+    (loss * 1.7).backward()
+    a64 = a.detach().double().contiguous().requires_grad_(True)
+    ref = _torch_ssim_loss_f64(a64, b.double().contiguous())
+    (ref * 1.7).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-6, (loss.item(), ref.item())
+    g, gr = a.grad.double(), a64.grad
+    assert g.shape == gr.shape
+    err = (g - gr).abs().max().item()
+    assert err <= 1e-4 * gr.abs().max().item() + 1e-9, f"ssim grad max err {err:.3e} vs max {gr.abs().max().item():.3e}"
+    # forward-only call allocates no derivative maps and agrees
+    with torch.no_grad():
+        assert abs(gs.ssim_loss(a.detach(), b).item() - loss.item()) < 1e-7

@@ -20,15 +20,13 @@ from tests import scene
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-REF_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "gsplat_ref.so")
-
-
 @pytest.fixture(scope="module")
 def ref():
-    if not os.path.exists(REF_SO):
-        pytest.skip("oracle/_ref/gsplat_ref.so not built (python oracle/build_ref.py in the build container)")
-    torch.ops.load_library(REF_SO)
-    return torch.ops.gsplat
+    from oracle import refcuda  # one policy for which physical copy of the reference build a process loads
+
+    if not refcuda.available():
+        pytest.skip("reference CUDA build missing (python baseline/install_ref.py in the build container)")
+    return refcuda.load_ops()
 
 
 @pytest.fixture(scope="module")
