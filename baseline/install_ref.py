@@ -13,7 +13,8 @@ result because baseline/_ref is git-ignored but NOT gpurun-ignored):
     from a scratch copy under /tmp (the source tree is read-only and setuptools writes egg-info in place).
     BUILD_NO_CUDA=1 is the reference's own switch (setup.py:40) for a Python-only install.
  2. compiles the reference's CUDA sources where they lie with the committed recipe oracle/build_ref.py
-    (3DGS + adam + relocation modules, sm_100a, the reference's release flags) and places the result as the
+    (--full: 3DGS + 3DGUT + adam + relocation + camera wrappers, channels 1,3,4,6,32, sm_100a, the reference's release
+    flags; about 25 minutes from scratch on 8 cores, seconds when oracle/_ref/obj_full is warm) and places the result as the
     prebuilt module the package looks for first: ``gsplat/csrc.so`` (gsplat/cuda/_backend.py:30).
  3. copies what the reference's own hot-path tests need at run time: tests/ + the root conftest.py (the
     reference's GPU-CI XFAIL list) -> baseline/_ref/reference_suite/ (a rootdir of its own: the tests import each
@@ -88,7 +89,7 @@ def main() -> int:
             return 1
         shutil.rmtree(tmp, ignore_errors=True)
     # 2. the CUDA extension, as the prebuilt module gsplat.csrc
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "build_ref.py")])
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "build_ref.py"), "--full"])
     if r.returncode != 0:
         return r.returncode
     so = os.path.join(ROOT, "oracle", "_ref", "gsplat_ref.so")

@@ -296,6 +296,59 @@ def run_ref_cuda_stock(params, vm, K, target, steps: int, scale_mul: float = 1.0
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
+def run_big_s(params, vm, K, target, steps: int, scale_mul: float = 4.0):
+    """Second driver-timed workload: the same scene with the Gaussians' scales x4 -- about
+    9x the tile intersections (S = 20 M instead of 2.3 M), the regime of trained 1080p scenes, where the tile
+    intersection / sort stage and the record pack weigh as much as compositing.  Same step as the headline
+    (rasterization fwd + fused L1 + bwd), ours and the reference's stock path, CUDA events."""
+    import torch
+
+    import gsplat_b200
+
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    scales = (p["scales"].detach() * scale_mul).requires_grad_(True)
+
+    def step():
+        for t in list(p.values()) + [scales]:
+            t.grad = None
+        rc, _, meta = gsplat_b200.rasterization(
+            p["means"], p["quats"], scales, p["opacities"], p["sh"], vm, K, W_IMG, H_IMG, sh_degree=SH_DEGREE, packed=False,
+        )
+        gsplat_b200.l1_loss(rc, target).backward()
+        return meta
+
+    for _ in range(3):
+        meta = step()
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record()
+    for _ in range(steps):
+        meta = step()
+    e[1].record()
+    with torch.no_grad():
+        for _ in range(steps):
+            gsplat_b200.rasterization(
+                p["means"], p["quats"], scales, p["opacities"], p["sh"], vm, K, W_IMG, H_IMG, sh_degree=SH_DEGREE, packed=False,
+            )
+    e[2].record()
+    torch.cuda.synchronize()
+    out = {
+        "workload": f"BASELINE configs[2] scene with scales x{scale_mul:g} (1 006 065 Gaussians, 1 view 1920x1080, SH3)",
+        "n_isects": int(meta["flatten_ids"].numel()),
+        "ms_per_step": e[0].elapsed_time(e[1]) / steps, "fwd_only_ms": e[1].elapsed_time(e[2]) / steps,
+    }
+    del p, scales, meta
+    torch.cuda.empty_cache()
+    ref = run_ref_cuda_stock(params, vm, K, target, steps, scale_mul=scale_mul)
+    out["ref_cuda_stock_ms_per_step"] = None if not ref else ref.get("ms_per_step", ref.get("error"))
+    if ref and ref.get("ms_per_step"):
+        out["speedup_vs_ref_cuda_stock"] = ref["ms_per_step"] / out["ms_per_step"]
+    return out
+
+
+TRAINER_GROW_GRAD2D = 0.0002  # DefaultStrategy threshold used by the cfg5 runs (see tools/trainer_bench.py --grad-stats)
+
+
 def run_trainer_bench(steps: int):
     """cfg5 (BASELINE configs[4]): the simple_trainer.py loop on both backends of the installed reference package,
     default and MCMC strategies (tools/trainer_bench.py, one subprocess per run).  Returns the `trainer` object."""
@@ -303,33 +356,42 @@ def run_trainer_bench(steps: int):
 
     tool = os.path.join(ROOT, "tools", "trainer_bench.py")
     out = {}
+    arms = (("ref", ["--backend", "reference"]), ("ours", ["--backend", "b200"]),
+            ("ours_raster_only", ["--backend", "b200", "--no-fused-losses"]),
+            ("ref_with_our_fused_ssim", ["--backend", "reference", "--fused-ssim-only"]))
     for strat in ("default", "mcmc"):
         runs = {}
-        for backend in ("reference", "b200"):
+        for name, flags in arms:
             try:
-                r = sp.run([sys.executable, tool, "--backend", backend, "--strategy", strat, "--steps", str(steps), "--breakdown"],
+                extra = ["--grow-grad2d", str(TRAINER_GROW_GRAD2D)] if strat == "default" else []
+                r = sp.run([sys.executable, tool, *flags, "--strategy", strat, "--steps", str(steps), "--breakdown", *extra],
                            capture_output=True, text=True, timeout=900)
                 line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-                runs[backend] = json.loads(line[-1]) if line else {"error": (r.stderr or r.stdout)[-400:]}
+                runs[name] = json.loads(line[-1]) if line else {"error": (r.stderr or r.stdout)[-400:]}
             except Exception as e:  # noqa: BLE001
-                runs[backend] = {"error": f"{type(e).__name__}: {e}"[:300]}
-        ours, ref = runs["b200"], runs["reference"]
-        ok = "error" not in ours and "error" not in ref
+                runs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        ref = runs["ref"]
+
+        def ratio(key, a):
+            return (a[key] / ref[key]) if ("error" not in a and "error" not in ref and a.get(key) and ref.get(key)) else None
+
+        pick = lambda key: {k: v.get(key) for k, v in runs.items()}  # noqa: E731
         out[strat] = {
-            "it_per_s": {"ours": ours.get("it_per_s_total"), "ref": ref.get("it_per_s_total")},
-            "it_per_s_at_1M": {"ours": ours.get("it_per_s_at_1M"), "ref": ref.get("it_per_s_at_1M")},
-            "speedup_total": (ours["it_per_s_total"] / ref["it_per_s_total"]) if ok else None,
-            "speedup_at_1M": (ours["it_per_s_at_1M"] / ref["it_per_s_at_1M"]) if ok and ours.get("it_per_s_at_1M") and ref.get("it_per_s_at_1M") else None,
-            "n_gaussians_end": {"ours": ours.get("n_gaussians_end"), "ref": ref.get("n_gaussians_end")},
-            "n_isects_last": {"ours": ours.get("n_isects_last"), "ref": ref.get("n_isects_last")},
-            "breakdown_ms": {"ours": ours.get("breakdown_ms"), "ref": ref.get("breakdown_ms")},
-            "final_loss": {"ours": (ours.get("loss_hist") or [[None, None]])[-1][1], "ref": (ref.get("loss_hist") or [[None, None]])[-1][1]},
-            "steps": steps, "schedule": ours.get("schedule"),
+            "it_per_s": pick("it_per_s_total"), "it_per_s_at_1M": pick("it_per_s_at_1M"),
+            "speedup_total": {k: ratio("it_per_s_total", v) for k, v in runs.items() if k != "ref"},
+            "speedup_at_1M": {k: ratio("it_per_s_at_1M", v) for k, v in runs.items() if k != "ref"},
+            "n_gaussians_end": pick("n_gaussians_end"), "n_isects_last": pick("n_isects_last"),
+            "breakdown_ms": pick("breakdown_ms"),
+            "final_loss": {k: (v.get("loss_hist") or [[None, None]])[-1][1] for k, v in runs.items()},
+            "steps": steps, "untimed_warm_steps": ref.get("untimed_warm_steps"), "schedule": runs["ours"].get("schedule"),
             "errors": {k: v["error"] for k, v in runs.items() if "error" in v} or None,
         }
     out["what"] = ("examples/simple_trainer.py:795-1198 restated on synthetic 1080p targets (tools/trainer_bench.py): 1M -> 3M "
-                   "Gaussians, L1 + SSIM, 6 fused Adam, reference strategies; `ref` = unmodified package, `ours` = same package "
-                   "after gsplat_b200.dropin.apply()")
+                   "Gaussians, L1 + SSIM, 6 fused Adam, reference strategies; `ref` = unmodified package (no third-party fused_ssim "
+                   "in this image: its ssim_loss runs the torch conv2d path), `ours` = same package after gsplat_b200.dropin.apply() "
+                   "(rasterization + fused SSIM), `ours_raster_only` = drop-in with the package's own torch SSIM kept, "
+                   "`ref_with_our_fused_ssim` = the reference's rasterization with only the fused SSIM swapped in (what the reference "
+                   "would do with its third-party fused_ssim hook): ours / ref_with_our_fused_ssim isolates the rasterizer")
     return out
 
 
@@ -342,7 +404,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-trainer", action="store_true", help="skip the cfg5 trainer-loop runs (about 2 minutes)")
-    ap.add_argument("--trainer-steps", type=int, default=400)
+    ap.add_argument("--trainer-steps", type=int, default=700)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -521,6 +583,33 @@ def main():
         mine = torch.tensor([sorted(comp)[2], sorted(comm)[2], sorted(nccl)[2]], device=dev)
         allr = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
+        # ---- correctness of the N > 1 data plane, checked in the run the driver times
+        checks = {}
+        for p in params.values():
+            p.grad = None
+        rc, _, _ = gsplat_b200.rasterization(
+            params["means"], params["quats"], params["scales"], params["opacities"], params["sh"], vm_dev, K_dev, W_IMG, H_IMG,
+            sh_degree=SH_DEGREE, packed=False,
+        )
+        gsplat_b200.l1_loss(rc, target_dev).backward()
+        want = {k: params[k].grad.detach().clone() for k in grad_names}
+        for w in want.values():
+            dist.all_reduce(w, op=dist.ReduceOp.SUM)  # NCCL on copies of the very same per-rank gradients
+        if arena is not None:
+            arena.stats.zero_() if getattr(arena, "stats", None) is not None else None
+        all_reduce_grads()
+        torch.cuda.synchronize()
+        err = torch.tensor([max(float((params[k].grad - want[k]).abs().max()) for k in grad_names)], device=dev)
+        mag = torch.tensor([max(float(want[k].abs().max()) for k in grad_names)], device=dev)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        dist.all_reduce(mag, op=dist.ReduceOp.MAX)
+        checks["own_allreduce_vs_nccl_max_abs"] = float(err.item())
+        checks["grad_max_abs"] = float(mag.item())
+        if arena is not None and getattr(arena, "stats", None) is not None:
+            moved = arena.stats.clone()
+            dist.all_reduce(moved)
+            checks["allreduce_payload_fraction_moved"] = float(moved.item()) * 16 / float(sum(params[k].numel() for k in grad_names) * 4)
+        del want
         ops.set_gradient_allocator(None)
         bounds = [int(round(i * N / world)) for i in range(world + 1)]
         shard = {k: params[k].detach()[bounds[rank] : bounds[rank + 1]].clone().requires_grad_(True) for k in params}
@@ -534,6 +623,20 @@ def main():
             )
             gsplat_b200.l1_loss(rc, target_dev).backward()
 
+        # gaussian-sharded render of this rank's camera must equal the single-GPU render of all gaussians, bit for bit
+        with torch.no_grad():
+            rc_full, ra_full, _ = gsplat_b200.rasterization(
+                params["means"], params["quats"], params["scales"], params["opacities"], params["sh"], vm_dev, K_dev, W_IMG, H_IMG,
+                sh_degree=SH_DEGREE, packed=False,
+            )
+            rc_sh, ra_sh, _ = gsplat_b200.rasterization(
+                shard["means"], shard["quats"], shard["scales"], shard["opacities"], shard["sh"], vm_dev, K_dev, W_IMG, H_IMG,
+                sh_degree=SH_DEGREE, packed=False, distributed=True,
+            )
+            same = torch.tensor([int(torch.equal(rc_full, rc_sh) and torch.equal(ra_full, ra_sh))], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            checks["sharded_vs_single_bitexact"] = bool(same.item())
+            del rc_full, ra_full, rc_sh, ra_sh
         sharded = {}
         for packed in (False, True):
             for _ in range(3):
@@ -556,7 +659,10 @@ def main():
             "per_rank_compute_ms": [round(float(t[0]), 3) for t in allr],
             "per_rank_allreduce_ms": [round(float(t[1]), 3) for t in allr],
             "per_rank_nccl_allreduce_ms": [round(float(t[2]), 3) for t in allr],
-            "allreduce": allreduce_kind,
+            "allreduce": allreduce_kind + (f" [{arena.last_kind}]" if arena is not None and getattr(arena, "last_kind", None) else ""),
+            "exposed_allreduce_ms": round(ms_dev / args.steps - max(float(t[0]) for t in allr), 3),
+            "compute_skew_ms": round(max(float(t[0]) for t in allr) - min(float(t[0]) for t in allr), 3),
+            "checks": checks,
             "allreduce_bytes_per_rank": int(sum(params[k].numel() for k in grad_names) * 4),
             "gaussian_sharded": dict(
                 what="same job with rasterization(distributed=True): Gaussians sharded, all-to-all of the projected rows "
@@ -630,10 +736,14 @@ def main():
     }
 
     if rank == 0:
-        cpu_base, ref_cuda, ref_stock, trainer = None, None, None, None
+        cpu_base, ref_cuda, ref_stock, trainer, big_s = None, None, None, None, None
         if n_gpus == 1:
             ref_cuda = run_ref_cuda(params, vm_dev, K_dev, target_dev, args.steps)
             ref_stock = run_ref_cuda_stock(params, vm_dev, K_dev, target_dev, args.steps)
+            try:
+                big_s = run_big_s(params, vm_dev, K_dev, target_dev, max(5, args.steps // 2))
+            except Exception as e:  # noqa: BLE001
+                big_s = {"error": f"{type(e).__name__}: {e}"[:300]}
             if not args.no_trainer:
                 del colors, opac, rc_keep, det
                 torch.cuda.empty_cache()
@@ -654,7 +764,7 @@ def main():
             # made by the library are not counted); timed region = `steps` device-resident + `steps` e2e steps
             "gpu_launches": args.steps * 2 * (13 + (1 if arena is not None else 0)),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "ref_cuda_stock": ref_stock,
-            "ref_cuda": ref_cuda, "trainer": trainer, "dp": dp_info,
+            "ref_cuda": ref_cuda, "big_s": big_s, "trainer": trainer, "dp": dp_info,
         }
         print(json.dumps(line))
     if world > 1:

@@ -136,6 +136,118 @@ __global__ void __launch_bounds__(kNvlsThreads) p2p_allreduce_kernel(
     __threadfence_system();
     rank_barrier<Order::AcqRel>(pads, rank, world);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Row-sparse variants.  In the view-parallel step most gaussians are culled in a rank's view (71 % at BASELINE
+// configs[3]): their gradient rows are zeros on that rank, and a row that NO rank touched needs no traffic at all.
+// The fused backward (project_sh_bwd) publishes one bit per gaussian ("seen in some view of this rank") in the
+// symmetric buffer; here a warp takes a group of 32 rows, ORs the ranks' bitmap words (in the switch:
+// multimem.ld_reduce.or, or one peer load at two ranks) and moves only the rows whose bit is set.  The buffer is
+// a structure of arrays: segment k holds N rows of w_k floats (means 3, quats 4, scales 3, opacities 1, SH 48);
+// a group's slice of a segment is 8 w_k float4, always 16-byte aligned.  Exact: skipped rows are zero everywhere.
+constexpr int kMaxSegs = 8;
+struct RowSegs
+{
+    int n;
+    int64_t vec_off[kMaxSegs]; // first float4 of the segment
+    int32_t width[kMaxSegs];   // floats per row
+    int64_t n_vec[kMaxSegs];   // float4 in the segment (rows * width / 4, rounded up)
+};
+
+__device__ __forceinline__ uint32_t multimem_ld_reduce_or(const uint32_t *mc)
+{
+    uint32_t v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.or.b32 %0, [%1];" : "=r"(v) : "l"(mc) : "memory");
+    return v;
+}
+
+// does float4 `v` of a 32-row group (rows of `w` floats) contain a row whose bit is set?
+__device__ __forceinline__ bool vec_touched(uint32_t word, int v, int w)
+{
+    const int r0 = (4 * v) / w, r1 = (4 * v + 3) / w; // first / last row the vector overlaps (r1 may be 32: next group's row 0 never)
+    const uint32_t span = (r1 >= 31 ? 0xffffffffu : ((2u << r1) - 1u)) & ~((1u << r0) - 1u);
+    return (word & span) != 0u;
+}
+
+template<bool NVLS>
+__global__ void __launch_bounds__(kNvlsThreads) rows_allreduce_kernel(
+    float4 *__restrict__ mc, float4 *const *__restrict__ bufs, const RowSegs segs, int64_t n_rows, int64_t bitmap_off_words,
+    int rank, int world, uint32_t *const *__restrict__ pads, unsigned long long *__restrict__ stats
+)
+{
+    rank_barrier<Order::Relaxed>(pads, rank, world);
+    const int64_t groups = (n_rows + 31) / 32;
+    const int64_t per    = (groups + world - 1) / world;
+    const int64_t glo = (int64_t)rank * per, ghi = (glo + per < groups) ? glo + per : groups;
+    const int lane   = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kNvlsThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarp = (int64_t)gridDim.x * (kNvlsThreads / 32);
+    unsigned long long moved = 0;
+    for(int64_t g = glo + warp0; g < ghi; g += nwarp)
+    {
+        uint32_t word;
+        if constexpr(NVLS)
+            word = multimem_ld_reduce_or(reinterpret_cast<const uint32_t *>(mc) + bitmap_off_words + g);
+        else
+        {
+            word = 0u;
+            for(int p = 0; p < world; ++p)
+                word |= __ldcv(reinterpret_cast<const uint32_t *>(bufs[p]) + bitmap_off_words + g);
+        }
+        if(word == 0u)
+            continue;
+#pragma unroll 1
+        for(int k = 0; k < segs.n; ++k)
+        {
+            const int w        = segs.width[k];
+            const int64_t base = segs.vec_off[k] + g * 8 * (int64_t)w;
+            const int64_t lim  = segs.vec_off[k] + segs.n_vec[k];
+            // four vectors in flight per lane: all loads of a round are issued before its stores
+            for(int v0 = lane; v0 < 8 * w; v0 += 32 * kNvlsUnroll)
+            {
+                float4 x[kNvlsUnroll];
+                bool on[kNvlsUnroll];
+#pragma unroll
+                for(int u = 0; u < kNvlsUnroll; ++u)
+                {
+                    const int v     = v0 + 32 * u;
+                    const int64_t i = base + v;
+                    on[u]           = v < 8 * w && i < lim && vec_touched(word, v, w);
+                    if(on[u])
+                    {
+                        if constexpr(NVLS)
+                            x[u] = multimem_ld_reduce_add(mc + i);
+                        else
+                        {
+                            x[u] = bufs[rank][i];
+                            for(int p = 1; p < world; ++p)
+                            {
+                                const float4 y = __ldcv(bufs[(rank + p) % world] + i);
+                                x[u].x += y.x, x[u].y += y.y, x[u].z += y.z, x[u].w += y.w;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for(int u = 0; u < kNvlsUnroll; ++u)
+                    if(on[u])
+                    {
+                        const int64_t i = base + v0 + 32 * u;
+                        if constexpr(NVLS)
+                            multimem_st(mc + i, x[u]);
+                        else
+                            for(int p = 0; p < world; ++p)
+                                bufs[(rank + p) % world][i] = x[u];
+                        ++moved;
+                    }
+            }
+        }
+    }
+    if(stats != nullptr && moved != 0)
+        atomicAdd(stats, moved); // float4 actually reduced by this rank (diagnostics)
+    __threadfence_system();
+    rank_barrier<Order::AcqRel>(pads, rank, world);
+}
 } // namespace gsb
 
 extern "C" int gsb200_p2p_allreduce_f32(
@@ -173,5 +285,49 @@ extern "C" int gsb200_nvls_allreduce_f32(
     gsb::nvls_allreduce_kernel<<<blocks, gsb::kNvlsThreads, 0, (cudaStream_t)stream>>>(
         static_cast<float4 *>(multicast_ptr), n_floats / 4, rank, world, reinterpret_cast<uint32_t *const *>(signal_pads_dev)
     );
+    return gsb::check_launch();
+}
+
+// Row-sparse all-reduce of a structure-of-arrays gradient buffer (see rows_allreduce_kernel).  seg_vec_offsets /
+// seg_widths describe n_segs segments of n_rows rows; bitmap_offset_floats locates the per-rank "row touched" bitmap
+// (ceil(n_rows / 32) 32-bit words) inside the same symmetric buffer.  multicast_ptr != NULL selects the in-switch
+// reduction, otherwise peer loads / stores through buffers_dev.  stats (optional, device u64) accumulates the number of
+// 16-byte vectors this rank reduced.
+extern "C" int gsb200_rows_allreduce_f32(
+    void *multicast_ptr, void *const *buffers_dev, int n_segs, const int64_t *seg_offsets_floats, const int32_t *seg_widths,
+    int64_t n_rows, int64_t bitmap_offset_floats, int rank, int world, void *const *signal_pads_dev, int64_t signal_pad_bytes,
+    int blocks, void *stats, void *stream
+)
+{
+    if(n_rows < 0 || world < 1 || rank < 0 || rank >= world || blocks < 1 || world > gsb::kNvlsThreads || n_segs < 1
+       || n_segs > gsb::kMaxSegs || !seg_offsets_floats || !seg_widths)
+        return GSB200_E_INVALID;
+    if(n_rows == 0 || world == 1)
+        return GSB200_OK;
+    if((!multicast_ptr && !buffers_dev) || !signal_pads_dev || bitmap_offset_floats < 0)
+        return GSB200_E_INVALID;
+    if((int64_t)blocks * world * (int64_t)sizeof(uint32_t) > signal_pad_bytes)
+        return GSB200_E_WORKSPACE;
+    gsb::RowSegs segs;
+    segs.n = n_segs;
+    for(int k = 0; k < n_segs; ++k)
+    {
+        if(seg_widths[k] < 1 || seg_widths[k] > 4096 || (seg_offsets_floats[k] & 3))
+            return GSB200_E_INVALID;
+        segs.vec_off[k] = seg_offsets_floats[k] / 4;
+        segs.width[k]   = seg_widths[k];
+        segs.n_vec[k]   = (n_rows * seg_widths[k] + 3) / 4;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if(multicast_ptr)
+        gsb::rows_allreduce_kernel<true><<<blocks, gsb::kNvlsThreads, 0, st>>>(
+            static_cast<float4 *>(multicast_ptr), nullptr, segs, n_rows, bitmap_offset_floats, rank, world,
+            reinterpret_cast<uint32_t *const *>(signal_pads_dev), static_cast<unsigned long long *>(stats)
+        );
+    else
+        gsb::rows_allreduce_kernel<false><<<blocks, gsb::kNvlsThreads, 0, st>>>(
+            nullptr, reinterpret_cast<float4 *const *>(buffers_dev), segs, n_rows, bitmap_offset_floats, rank, world,
+            reinterpret_cast<uint32_t *const *>(signal_pads_dev), static_cast<unsigned long long *>(stats)
+        );
     return gsb::check_launch();
 }

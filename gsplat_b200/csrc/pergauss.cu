@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 2) project_sh_bwd_kernel(
     const float *__restrict__ v_means2d, int64_t s_m2, const float *__restrict__ v_depths, int64_t s_d,
     const float *__restrict__ v_conics, int64_t s_c, const float *__restrict__ v_colors, int64_t s_col,
     const float *__restrict__ v_compensations, float *__restrict__ v_means, float *__restrict__ v_quats,
-    float *__restrict__ v_scales, float *__restrict__ v_sh
+    float *__restrict__ v_scales, float *__restrict__ v_sh, uint32_t *__restrict__ seen_bits
 )
 {
     const int64_t n     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -669,6 +669,12 @@ __global__ void __launch_bounds__(kThreads, 2) project_sh_bwd_kernel(
     }
     // zero rows of v_sh, warp-cooperatively: lane l writes chunk l, l + 32, ... of the warp's 32-row block
     const unsigned zero_rows = __ballot_sync(0xffffffffu, n < N && !seen);
+    if(seen_bits != nullptr)
+    { // one bit per gaussian: "has a non-trivial gradient row on this rank" (input of the row-sparse all-reduce)
+        const unsigned seen_rows = __ballot_sync(0xffffffffu, seen);
+        if(lane == 0 && n < N)
+            seen_bits[n >> 5] = seen_rows;
+    }
     if(zero_rows != 0u)
     {
         const int64_t row0 = n - lane; // first row of this warp
@@ -1024,6 +1030,219 @@ __global__ void __launch_bounds__(kThreads) isect_emit_kernel(
     });
 }
 
+// ---- warp-cooperative emit.  One thread per gaussian with a loop over ITS tiles (isect_emit_kernel) leaves a warp
+// waiting for its largest gaussian and writes 8 + 4 byte records at lane-dependent strides: at S = 20 M (large
+// screen-space gaussians) it took 444 us for 240 MB of output.  Here a gaussian with more than kSmallTiles tiles is
+// handed to its whole warp: the tile interval of every tile row is a closed form of the row index (the incremental
+// scheme of tiles_of_gaussian only carries the previous row's far line over as the next row's near line), so lane r
+// computes row ru0 + r, a warp scan places the rows, and the lanes then write the tiles round-robin -- consecutive
+// lanes, consecutive addresses -- in the same order as the sequential enumeration.
+constexpr int kSmallTiles = 6;
+
+struct AccuGauss
+{
+    float mx, my, A, Bc, Cc, disc, t, ts;
+    float bminu, bmaxu, bminv, bmaxv, amin_v, amax_v, pu, pv, coeff;
+    int ru0, ru1, rv0, rv1;
+    bool isY, accu, empty;
+    int x0, x1; // AABB path
+};
+
+__device__ __forceinline__ AccuGauss accu_setup(
+    float mx, float my, int rx, int ry, bool accu, float A, float Bc, float Cc, float opacity, uint32_t tile_size,
+    uint32_t tw, uint32_t th
+)
+{
+    AccuGauss g;
+    g.mx = mx, g.my = my, g.A = A, g.Bc = Bc, g.Cc = Cc, g.accu = accu, g.ts = (float)tile_size;
+    g.empty     = rx <= 0 || ry <= 0;
+    g.ru0 = g.ru1 = g.rv0 = g.rv1 = g.x0 = g.x1 = 0;
+    g.isY                                        = false;
+    auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    if(g.empty)
+        return g;
+    const float ts = g.ts;
+    if(accu)
+    {
+        g.disc          = Bc * Bc - A * Cc;
+        float t         = 2.f * exact_log(opacity / kAlphaThreshold);
+        const float cap = kGaussianExtend * kGaussianExtend;
+        g.t             = t < cap ? t : cap;
+        const float ntd = -g.t / g.disc;
+        const float xe = sqrtf(ntd * Cc), ye = sqrtf(ntd * A);
+        const float bminx = mx - xe, bminy = my - ye, bmaxx = mx + xe, bmaxy = my + ye;
+        const float BxC = Bc * xe / Cc, ByA = Bc * ye / A;
+        const float argminx = my + BxC, argminy = mx + ByA, argmaxx = my - BxC, argmaxy = mx - ByA;
+        const int rminx = clampi((int)(bminx / ts), 0, (int)tw), rminy = clampi((int)(bminy / ts), 0, (int)th);
+        const int rmaxx = clampi((int)(bmaxx / ts + 1.f), 0, (int)tw), rmaxy = clampi((int)(bmaxy / ts + 1.f), 0, (int)th);
+        const int ys = rmaxy - rminy, xs = rmaxx - rminx;
+        if(ys * xs == 0)
+        {
+            g.empty = true;
+            return g;
+        }
+        g.isY = ys < xs;
+        g.ru0 = g.isY ? rminy : rminx, g.ru1 = g.isY ? rmaxy : rmaxx, g.rv0 = g.isY ? rminx : rminy, g.rv1 = g.isY ? rmaxx : rmaxy;
+        g.bminu = g.isY ? bminy : bminx, g.bmaxu = g.isY ? bmaxy : bmaxx;
+        g.bminv = g.isY ? bminx : bminy, g.bmaxv = g.isY ? bmaxx : bmaxy;
+        g.amin_v = g.isY ? argminx : argminy, g.amax_v = g.isY ? argmaxx : argmaxy;
+        g.pu = g.isY ? my : mx, g.pv = g.isY ? mx : my, g.coeff = g.isY ? A : Cc;
+    }
+    else
+    {
+        const float trx = (float)rx / ts, try_ = (float)ry / ts, tx = mx / ts, ty = my / ts;
+        g.x0 = clampi((int)floorf(tx - trx), 0, (int)tw), g.ru0 = clampi((int)floorf(ty - try_), 0, (int)th);
+        g.x1 = clampi((int)ceilf(tx + trx), 0, (int)tw), g.ru1 = clampi((int)ceilf(ty + try_), 0, (int)th);
+        g.isY = true; // rows are tile rows
+        if(g.ru1 <= g.ru0 || g.x1 <= g.x0)
+            g.empty = true;
+    }
+    return g;
+}
+
+// tile interval [v0, v1) of row u (ru0 <= u < ru1); identical, bit for bit, to what tiles_of_gaussian enumerates
+__device__ __forceinline__ void accu_row(const AccuGauss &g, int u, int &v0, int &v1)
+{
+    if(!g.accu)
+    {
+        v0 = g.x0, v1 = g.x1;
+        return;
+    }
+    const float ts = g.ts;
+    auto line = [&](float coord, float &lo, float &hi) {
+        const float h  = coord - g.pu;
+        const float sq = sqrtf(g.disc * h * h + g.t * g.coeff);
+        lo             = (-g.Bc * h - sq) / g.coeff + g.pv;
+        hi             = (-g.Bc * h + sq) / g.coeff + g.pv;
+    };
+    const float min_line = (float)u * ts, max_line = min_line + ts;
+    float minlo = g.bmaxv, minhi = g.bminv; // the sequential scheme's initial values
+    if(u > g.ru0 || g.bminu <= min_line)
+        line(min_line, minlo, minhi);
+    float maxlo, maxhi;
+    if(max_line <= g.bmaxu)
+        line(max_line, maxlo, maxhi);
+    else if(u > g.ru0)
+        maxlo = minlo, maxhi = minhi; // the far line was not computed: the previous one is kept
+    else
+        maxlo = g.bmaxv, maxhi = g.bminv;
+    const float emin = (min_line <= g.amin_v && g.amin_v < max_line) ? g.bminv : (minlo < maxlo ? minlo : maxlo);
+    const float emax = (min_line <= g.amax_v && g.amax_v < max_line) ? g.bmaxv : (minhi > maxhi ? minhi : maxhi);
+    const int e0 = (int)(emin / ts), e1 = (int)(emax / ts + 1.f);
+    v0 = e0 < g.rv1 ? e0 : g.rv1;
+    v0 = v0 > g.rv0 ? v0 : g.rv0;
+    v1 = e1 > g.rv0 ? e1 : g.rv0;
+    v1 = v1 < g.rv1 ? v1 : g.rv1;
+    if(v1 < v0)
+        v1 = v0;
+}
+
+__global__ void __launch_bounds__(kThreads) isect_emit_coop_kernel(
+    int64_t total, int64_t N, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
+    const float *__restrict__ depths, const float *__restrict__ conics, const float *__restrict__ opacities,
+    const int64_t *__restrict__ cum_tiles, const int64_t *__restrict__ image_ids, const int32_t *__restrict__ order,
+    uint32_t tile_size, uint32_t tw, uint32_t th, uint32_t tile_n_bits, int64_t *__restrict__ isect_ids,
+    int32_t *__restrict__ flatten_ids
+)
+{
+    const int64_t j     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    const bool active   = j < total;
+    const int64_t i     = active ? (order ? (int64_t)order[j] : j) : 0;
+    int2 r              = make_int2(0, 0);
+    float2 m            = make_float2(0.f, 0.f);
+    float cn0 = 0.f, cn1 = 0.f, cn2 = 0.f, op = 0.f;
+    const bool accu = conics != nullptr && opacities != nullptr;
+    int64_t cur = 0, hi = 0, dbits = 0;
+    int cnt = 0;
+    if(active)
+    {
+        r = reinterpret_cast<const int2 *>(radii)[i];
+        if(r.x > 0 && r.y > 0)
+        {
+            m = reinterpret_cast<const float2 *>(means2d)[i];
+            if(accu)
+                cn0 = conics[i * 3], cn1 = conics[i * 3 + 1], cn2 = conics[i * 3 + 2], op = opacities[i];
+            cur   = (j == 0) ? 0 : cum_tiles[j - 1];
+            cnt   = (int)(cum_tiles[j] - cur);
+            hi    = (image_ids ? image_ids[i] : (i / N)) << (32 + tile_n_bits);
+            dbits = (int64_t)__float_as_uint(depths[i]);
+        }
+    }
+    // small gaussians: the owning lane writes its few tiles
+    if(cnt > 0 && cnt <= kSmallTiles)
+    {
+        float cn[3] = {cn0, cn1, cn2};
+        tiles_of_gaussian(m.x, m.y, r.x, r.y, accu ? cn : nullptr, accu ? &op : nullptr, tile_size, tw, th, [&](int64_t tile) {
+            isect_ids[cur]   = hi | (tile << 32) | dbits;
+            flatten_ids[cur] = (int32_t)i;
+            ++cur;
+        });
+    }
+    // large gaussians: one at a time, the whole warp
+    uint32_t big = __ballot_sync(0xffffffffu, cnt > kSmallTiles);
+    while(big)
+    {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const float bmx = __shfl_sync(0xffffffffu, m.x, src), bmy = __shfl_sync(0xffffffffu, m.y, src);
+        const int brx = __shfl_sync(0xffffffffu, r.x, src), bry = __shfl_sync(0xffffffffu, r.y, src);
+        const float b0 = __shfl_sync(0xffffffffu, cn0, src), b1 = __shfl_sync(0xffffffffu, cn1, src);
+        const float b2 = __shfl_sync(0xffffffffu, cn2, src), bop = __shfl_sync(0xffffffffu, op, src);
+        const int64_t bcur = __shfl_sync(0xffffffffu, cur, src), bhi = __shfl_sync(0xffffffffu, hi, src);
+        const int64_t bdb = __shfl_sync(0xffffffffu, dbits, src);
+        const int32_t bi  = (int32_t)__shfl_sync(0xffffffffu, i, src);
+        const AccuGauss g = accu_setup(bmx, bmy, brx, bry, accu, b0, b1, b2, bop, tile_size, tw, th);
+        if(g.empty)
+            continue;
+        int64_t base = bcur;
+        for(int u0 = g.ru0; u0 < g.ru1; u0 += 32)
+        {
+            const int u = u0 + (int)lane;
+            int v0 = 0, v1 = 0;
+            if(u < g.ru1)
+                accu_row(g, u, v0, v1);
+            const int len = v1 - v0;
+            int incl      = len;
+#pragma unroll
+            for(int o = 1; o < 32; o <<= 1)
+            {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if((int)lane >= o)
+                    incl += up;
+            }
+            const int excl  = incl - len;
+            const int chunk = __shfl_sync(0xffffffffu, incl, 31);
+            // tile k of this 32-row chunk: row = the last row with excl <= k (binary search over the lanes; the loop is
+            // warp-uniform so that every shuffle sees all 32 lanes, only the stores are predicated)
+            for(int k0 = 0; k0 < chunk; k0 += 32)
+            {
+                const int k = k0 + (int)lane;
+                int row     = 0;
+#pragma unroll
+                for(int step = 16; step > 0; step >>= 1)
+                {
+                    const int probe = row + step; // <= 31
+                    const int pe    = __shfl_sync(0xffffffffu, excl, probe);
+                    if(pe <= k)
+                        row = probe;
+                }
+                const int rex = __shfl_sync(0xffffffffu, excl, row);
+                const int rv0 = __shfl_sync(0xffffffffu, v0, row);
+                if(k < chunk)
+                {
+                    const int v        = rv0 + (k - rex);
+                    const int uu       = u0 + row;
+                    const int64_t tile = g.isY ? (int64_t)uu * tw + v : (int64_t)v * tw + uu;
+                    isect_ids[base + k]   = bhi | (tile << 32) | bdb;
+                    flatten_ids[base + k] = bi;
+                }
+            }
+            base += chunk;
+        }
+    }
+}
+
 // offsets[(image, tile)] = first sorted index of that tile's run.  One thread per sorted
 // intersection; a thread that starts a new run also fills the empty tiles before it.
 __global__ void __launch_bounds__(kThreads) isect_offsets_kernel(
@@ -1319,7 +1538,7 @@ extern "C" int gsb200_project_sh_bwd(
     float eps2d, const int32_t *radii, const float *conics, const float *compensations, const float *colors,
     const float *v_means2d, int64_t v_means2d_stride, const float *v_depths, int64_t v_depths_stride,
     const float *v_conics, int64_t v_conics_stride, const float *v_colors, int64_t v_colors_stride,
-    const float *v_compensations, float *v_means, float *v_quats, float *v_scales, float *v_sh_coeffs, void *stream
+    const float *v_compensations, float *v_means, float *v_quats, float *v_scales, float *v_sh_coeffs, uint32_t *seen_bits, void *stream
 )
 {
     if(C < 0 || N < 0 || K <= 0 || degrees_to_use < 0 || degrees_to_use > 4
@@ -1337,7 +1556,7 @@ extern "C" int gsb200_project_sh_bwd(
     project_sh_bwd_kernel<d><<<grid_for(N, kThreads), kThreads, 0, st>>>(                                          \
         C, N, K, means, quats, scales, sh_coeffs, viewmats, Ks, image_width, image_height, eps2d, radii, conics,   \
         compensations, colors, v_means2d, v_means2d_stride, v_depths, v_depths_stride, v_conics, v_conics_stride,  \
-        v_colors, v_colors_stride, v_compensations, v_means, v_quats, v_scales, v_sh_coeffs                        \
+        v_colors, v_colors_stride, v_compensations, v_means, v_quats, v_scales, v_sh_coeffs, seen_bits             \
     )
     GSB_DEG_SWITCH(degrees_to_use, CALL)
 #undef CALL
@@ -1402,10 +1621,20 @@ extern "C" int gsb200_isect_emit(
     const uint32_t tile_bits = bits_for_count((int64_t)tile_width * tile_height);
     if(bits_for_count(I) + tile_bits > 32)
         return GSB200_E_KEYBITS;
-    isect_emit_kernel<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        total, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
-        tile_bits, isect_ids, flatten_ids
-    );
+    static const bool coop = [] {
+        const char *e = std::getenv("GSB200_EMIT");
+        return !(e && e[0] == 's'); // GSB200_EMIT=serial selects the one-thread-per-gaussian kernel (measurements)
+    }();
+    if(coop)
+        isect_emit_coop_kernel<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+            total, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
+            tile_bits, isect_ids, flatten_ids
+        );
+    else
+        isect_emit_kernel<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+            total, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
+            tile_bits, isect_ids, flatten_ids
+        );
     return check_launch();
 }
 

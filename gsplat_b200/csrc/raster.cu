@@ -1031,15 +1031,14 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
+// record streams + tile dispatch order of one view batch (the first stage of the forward; also callable on its own,
+// gsb200_raster_pack, for bindings that rebuild the records in their backward instead of keeping them alive)
 template<int CDIM>
-static int launch_fwd(
-    int64_t I, int64_t N, const float *means2d, const float *conics, const float *colors, const float *opacities,
-    const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tw, uint32_t th,
-    const int32_t *offsets, const int32_t *flatten_ids, int64_t S, void *records, float *render_colors,
-    float *render_alphas, int32_t *last_ids, cudaStream_t st
+static int launch_pack(
+    const float *means2d, const float *conics, const float *colors, const float *opacities, const int32_t *offsets,
+    const int32_t *flatten_ids, int64_t S, unsigned n_tiles, void *records, cudaStream_t st
 )
 {
-    (void)N;
     RecordStreams r = carve_records(records, S, RecLayout<CDIM>::kColorVec4);
     if(S > 0)
     {
@@ -1049,17 +1048,32 @@ static int launch_fwd(
         if(int rc = check_launch())
             return rc;
     }
-    const size_t smem = ring_smem_bytes<CDIM>();
-    GSB_CUDA_TRY(cudaFuncSetAttribute(raster_fwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned n_tiles = (unsigned)(I * tw * th);
-    const int32_t *order = nullptr;
     if(S > 0 && n_tiles >= 2 * 148)
     { // enough tiles for dispatch order to matter
         tile_order_kernel<<<1, 1024, 0, st>>>(offsets, (int32_t)n_tiles, (int32_t)S, r.order);
         if(int rc = check_launch())
             return rc;
-        order = r.order;
     }
+    return GSB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+template<int CDIM>
+static int launch_fwd(
+    int64_t I, int64_t N, const float *means2d, const float *conics, const float *colors, const float *opacities,
+    const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tw, uint32_t th,
+    const int32_t *offsets, const int32_t *flatten_ids, int64_t S, void *records, float *render_colors,
+    float *render_alphas, int32_t *last_ids, cudaStream_t st
+)
+{
+    (void)N;
+    const unsigned n_tiles = (unsigned)(I * tw * th);
+    if(int rc = launch_pack<CDIM>(means2d, conics, colors, opacities, offsets, flatten_ids, S, n_tiles, records, st))
+        return rc;
+    RecordStreams r      = carve_records(records, S, RecLayout<CDIM>::kColorVec4);
+    const size_t smem    = ring_smem_bytes<CDIM>();
+    const int32_t *order = (S > 0 && n_tiles >= 2 * 148) ? r.order : nullptr;
+    GSB_CUDA_TRY(cudaFuncSetAttribute(raster_fwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     raster_fwd_kernel<CDIM><<<n_tiles, kWarps * 32, smem, st>>>(
         (uint32_t)I, S, r.cull, r.geom, r.color, order, backgrounds, masks, W, H, tw, th, offsets, render_colors,
         render_alphas, last_ids
@@ -1201,6 +1215,32 @@ extern "C" size_t gsb200_raster_records_bytes(int64_t n_isects, int D, int64_t n
     const size_t cv = (size_t)((D + 3) / 4);
     return 3 * gsb::align256((size_t)n_isects * 16) + gsb::align256((size_t)n_isects * 16 * cv)
          + gsb::align256((size_t)(n_tiles + 1) * 4) + 256;
+}
+
+extern "C" int gsb200_raster_pack(
+    int64_t I, int D, const float *means2d, const float *conics, const float *colors, const float *opacities,
+    uint32_t tile_width, uint32_t tile_height, const int32_t *offsets, const int32_t *flatten_ids, int64_t n_isects,
+    void *records, void *stream
+)
+{
+    if(I < 0 || n_isects < 0 || !offsets)
+        return GSB200_E_INVALID;
+    if(n_isects == 0 || I == 0)
+        return GSB200_OK;
+    if(!means2d || !conics || !colors || !opacities || !flatten_ids || !records)
+        return GSB200_E_INVALID;
+    const unsigned n_tiles = (unsigned)(I * tile_width * tile_height);
+    cudaStream_t st        = (cudaStream_t)stream;
+    switch(D)
+    {
+#define X(n)                                                                                                         \
+    case n:                                                                                                          \
+        return gsb::launch_pack<n>(means2d, conics, colors, opacities, offsets, flatten_ids, n_isects, n_tiles, records, st);
+        GSB_FOR_CHANNELS(X)
+#undef X
+    default:
+        return GSB200_E_UNSUPPORTED;
+    }
 }
 
 extern "C" int gsb200_raster_fwd(

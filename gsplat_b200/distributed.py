@@ -128,7 +128,10 @@ class NvlsGradArena:
 
     ALIGN = 64  # floats (256 B) between segment starts
 
-    def __init__(self, named_params: Dict[str, Tensor], group=None, blocks: Optional[int] = None, algo: Optional[str] = None):
+    def __init__(
+        self, named_params: Dict[str, Tensor], group=None, blocks: Optional[int] = None, algo: Optional[str] = None,
+        row_sparse: Optional[bool] = None,
+    ):
         import torch.distributed._symmetric_memory as symm_mem
 
         from ._cabi import lib
@@ -137,6 +140,8 @@ class NvlsGradArena:
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.params = dict(named_params)
         self.blocks = int(os.environ.get("GSB200_NVLS_BLOCKS", "64")) if blocks is None else int(blocks)
+        if row_sparse is None:
+            row_sparse = os.environ.get("GSB200_ALLREDUCE_ROWS", "1") != "0"
         dev = next(iter(self.params.values())).device
         self.offsets, o = {}, 0
         for k, p in self.params.items():
@@ -144,6 +149,14 @@ class NvlsGradArena:
                 raise TypeError("NvlsGradArena holds float32 gradients")
             self.offsets[k] = o
             o += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        # row-sparse mode: every parameter is [N, ...] over the same N gaussians; one bit per gaussian and rank
+        # ("its gradient rows are not all zero here") lives in the same symmetric buffer, behind the gradients
+        rows = {int(p.shape[0]) for p in self.params.values() if p.dim() >= 1}
+        self.n_rows = rows.pop() if len(rows) == 1 and all(p.dim() >= 1 for p in self.params.values()) else None
+        self.row_sparse = bool(row_sparse) and self.n_rows is not None and self.n_rows > 0
+        self.bitmap_off = o
+        if self.row_sparse:
+            o += ((self.n_rows + 31) // 32 + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.numel = max(o, self.ALIGN)
         need_pad = self.blocks * self.world * 4
         if symm_mem.get_signal_pad_size() < need_pad:
@@ -162,8 +175,23 @@ class NvlsGradArena:
         self.views = {k: self.flat[self.offsets[k] : self.offsets[k] + p.numel()].view(p.shape) for k, p in self.params.items()}
         self._handed_out = set()  # segments given to a backward kernel since the last all_reduce() / reset()
         self._lib = lib()
+        self.bits, self._bits_requests = None, 0
+        if self.row_sparse:
+            import ctypes
 
-    def allocator(self, name: str, like: Tensor) -> Optional[Tensor]:
+            nw = (self.n_rows + 31) // 32
+            self.bits = self.flat[self.bitmap_off : self.bitmap_off + nw].view(torch.int32)
+            names = list(self.params)
+            self._seg_off = (ctypes.c_int64 * len(names))(*[self.offsets[k] for k in names])
+            self._seg_w = (ctypes.c_int32 * len(names))(*[self.params[k].numel() // self.n_rows for k in names])
+            self.stats = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def allocator(self, name: str, like: Optional[Tensor]) -> Optional[Tensor]:
+        if name == "seen_bits":
+            # asked for once per fused backward: the bitmap describes the gradients only if exactly one backward
+            # wrote into the arena since the last all_reduce()
+            self._bits_requests += 1
+            return self.bits
         v = self.views.get(name)
         if v is None or v.shape != like.shape:
             return None
@@ -186,12 +214,17 @@ class NvlsGradArena:
         """Forget which segments were handed out (call after optimizer.zero_grad() when a step is abandoned
         without all_reduce())."""
         self._handed_out.clear()
+        self._bits_requests = 0
 
     def all_reduce(self) -> None:
         """Sums the .grad of all registered parameters over the ranks, in place in the arena."""
         from ._cabi import check
 
         self._handed_out.clear()
+        # the row bitmap is trustworthy only when ONE fused backward produced every gradient that was written in place;
+        # gradients that arrive from elsewhere (e.g. opacities through torch) are zero on unseen rows by construction
+        sparse = self.row_sparse and self._bits_requests == 1
+        self._bits_requests = 0
         for k, p in self.params.items():
             v = self.views[k]
             if p.grad is None:
@@ -201,7 +234,14 @@ class NvlsGradArena:
             p.grad = v
         st = torch.cuda.current_stream().cuda_stream
         pads, pad_bytes = int(self.hdl.signal_pad_ptrs_dev), int(self.hdl.signal_pad_size)
-        if self.algo == "nvls":
+        self.last_kind = ("rows-" if sparse else "") + self.algo
+        if sparse:
+            rc = self._lib.gsb200_rows_allreduce_f32(
+                int(self.hdl.multicast_ptr) if self.algo == "nvls" else None, int(self.hdl.buffer_ptrs_dev), len(self.params),
+                self._seg_off, self._seg_w, self.n_rows, self.bitmap_off, self.rank, self.world, pads, pad_bytes, self.blocks,
+                self.stats.data_ptr(), st,
+            )
+        elif self.algo == "nvls":
             rc = self._lib.gsb200_nvls_allreduce_f32(
                 int(self.hdl.multicast_ptr), self.numel, self.rank, self.world, pads, pad_bytes, self.blocks, st
             )
@@ -209,7 +249,7 @@ class NvlsGradArena:
             rc = self._lib.gsb200_p2p_allreduce_f32(
                 int(self.hdl.buffer_ptrs_dev), self.numel, self.rank, self.world, pads, pad_bytes, self.blocks, st
             )
-        check(rc, f"{self.algo}_allreduce")
+        check(rc, f"{self.last_kind}_allreduce")
 
 
 def render_views_dp(

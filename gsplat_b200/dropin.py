@@ -45,13 +45,23 @@ def applied() -> bool:
     return bool(_saved)
 
 
-def apply(losses: bool = True) -> Dict[str, object]:
-    """Rebind the hot-path names of the importable ``gsplat`` package to gsplat_b200.  Idempotent."""
+def apply(losses: bool = True, ops: bool = True) -> Dict[str, object]:
+    """Rebind the hot-path names of the importable ``gsplat`` package to gsplat_b200.  Idempotent.
+    ``ops=False`` leaves the rasterization path alone and only installs the fused SSIM (used by the trainer bench to
+    separate the two effects)."""
     if _saved:
         return {"already": True}
     import gsplat_b200 as B
 
     G = importlib.import_module("gsplat")
+    if ops:
+        _apply_ops(B, G)
+    if losses:
+        _apply_losses(G)
+    return {"package": G.__file__, "ops": (list(_OPS) + ["adam", "rasterization", "compute_relocation"]) if ops else [], "losses": losses}
+
+
+def _apply_ops(B, G) -> None:
     W = importlib.import_module("gsplat.cuda._wrapper")
     R = importlib.import_module("gsplat.rendering")
     for name in _OPS:
@@ -84,7 +94,10 @@ def apply(losses: bool = True) -> Dict[str, object]:
     _set(opt, "SelectiveAdam", B.SelectiveAdam)
     if hasattr(G, "SelectiveAdam"):
         _set(G, "SelectiveAdam", B.SelectiveAdam)
-    if losses:
+
+
+def _apply_losses(G) -> None:
+    if True:  # (block kept flat for the diff; always taken)
         # the reference's l1_loss is element-wise (the trainer reduces it), so only the SSIM term has a fused
         # replacement: same semantics as the torch fallback the reference runs when the third-party
         # ``fused_ssim`` package is absent (losses.py:190-201: zero padding, mean over B*C*H*W)
@@ -108,7 +121,6 @@ def apply(losses: bool = True) -> Dict[str, object]:
         _set(Ls, "ssim_loss", ssim_loss)
         if hasattr(G, "ssim_loss"):
             _set(G, "ssim_loss", ssim_loss)
-    return {"package": G.__file__, "ops": list(_OPS) + ["adam", "rasterization", "compute_relocation"], "losses": losses}
 
 
 def undo() -> None:

@@ -531,7 +531,9 @@ _grad_allocator = None
 
 
 def set_gradient_allocator(fn) -> None:
-    """fn(name, like) -> Tensor | None with name in {"means", "quats", "scales", "sh"}; None = default."""
+    """fn(name, like) -> Tensor | None with name in {"means", "quats", "scales", "sh"}; None = default.
+    The fused backward also asks for ``fn("seen_bits", None)``: an int32 [ceil(N / 32)] tensor that receives the
+    row bitmap of the row-sparse all-reduce, or None."""
     global _grad_allocator
     _grad_allocator = fn
 
@@ -598,13 +600,17 @@ class _ProjectSH(torch.autograd.Function):
         v_comps = None if (v_comps is None or comps is None) else v_comps.contiguous()
         v_means, v_quats, v_scales = _alloc_grad("means", means), _alloc_grad("quats", quats), _alloc_grad("scales", scales)
         v_sh = _alloc_grad("sh", sh_coeffs)
+        # optional row bitmap for the row-sparse gradient all-reduce (distributed.NvlsGradArena): int32 [ceil(N / 32)]
+        seen_bits = _grad_allocator("seen_bits", None) if _grad_allocator is not None else None
+        if seen_bits is not None and (seen_bits.dtype != torch.int32 or seen_bits.numel() < (N + 31) // 32 or not seen_bits.is_contiguous()):
+            raise RuntimeError("gradient allocator returned a mismatching tensor for 'seen_bits'")
         with _Ctx(dev) as st:
             check(
                 lib().gsb200_project_sh_bwd(
                     C, N, K, sh_degree, ptr(means), ptr(quats), ptr(scales), ptr(sh_coeffs), ptr(viewmats), ptr(Ks),
                     width, height, eps2d, ptr(radii), ptr(conics), ptr(comps), ptr(colors), ptr(v_means2d), s_m2,
                     ptr(v_depths), s_d, ptr(v_conics), s_c, ptr(v_colors), s_col, ptr(v_comps), ptr(v_means),
-                    ptr(v_quats), ptr(v_scales), ptr(v_sh), st,
+                    ptr(v_quats), ptr(v_scales), ptr(v_sh), ptr(seen_bits), st,
                 ),
                 "project_sh_bwd",
             )

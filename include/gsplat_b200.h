@@ -107,7 +107,9 @@ extern "C"
         float *compensations, float *colors, void *stream
     );
     /* Backward of the fused pass.  v_colors is the gradient w.r.t. the post-activation colours
-     * (the relu mask is re-derived).  All outputs fully written; deterministic. */
+     * (the relu mask is re-derived).  All outputs fully written; deterministic.  seen_bits (optional,
+     * ceil(N / 32) words): bit n%32 of word n/32 = gaussian n is visible in some camera of this call, i.e. its
+     * gradient rows are not all zero -- the row bitmap gsb200_rows_allreduce_f32 consumes. */
     int gsb200_project_sh_bwd(
         int64_t C, int64_t N, int64_t K, int degrees_to_use, const float *means, const float *quats,
         const float *scales, const float *sh_coeffs, const float *viewmats, const float *Ks, uint32_t image_width,
@@ -115,7 +117,7 @@ extern "C"
         const float *colors, const float *v_means2d, int64_t v_means2d_stride, const float *v_depths,
         int64_t v_depths_stride, const float *v_conics, int64_t v_conics_stride, const float *v_colors,
         int64_t v_colors_stride, const float *v_compensations, float *v_means, float *v_quats, float *v_scales,
-        float *v_sh_coeffs, void *stream
+        float *v_sh_coeffs, uint32_t *seen_bits, void *stream
     );
 
     /* ---- spherical harmonics on packed rows (reference: spherical_harmonics with batch_ids / camera_ids /
@@ -210,6 +212,15 @@ extern "C"
         int32_t *offsets, void *stream
     );
 
+    /* Stage 1 of gsb200_raster_fwd on its own: gathers the depth-sorted per-intersection records into `records`
+     * (gsb200_raster_records_bytes) and writes the longest-list-first tile order.  gsb200_raster_fwd does this itself; a
+     * binding that does not keep `records` alive between forward and backward calls this
+     * in its backward, then gsb200_raster_bwd. */
+    int gsb200_raster_pack(
+        int64_t I, int D, const float *means2d, const float *conics, const float *colors, const float *opacities,
+        uint32_t tile_width, uint32_t tile_height, const int32_t *offsets, const int32_t *flatten_ids, int64_t n_isects,
+        void *records, void *stream
+    );
     /* ---- rasterize_to_pixels_3dgs / _bwd : ext.cpp:1079-1089, _wrapper.py:1497-1562, 2010-2117 ----
      * Dense layout: means2d [I,N,2] conics [I,N,3] colors [I,N,D] opacities [I,N]
      * backgrounds [I,D] or NULL, masks [I,th,tw] bool bytes or NULL, offsets [I,th,tw], flatten_ids [n_isects].
@@ -291,12 +302,25 @@ extern "C"
         void *multicast_ptr, int64_t n_floats, int rank, int world, void *const *signal_pads_dev,
         int64_t signal_pad_bytes, int blocks, void *stream
     );
+
     /* Same contract without the switch reduction (plain peer loads / stores over NVLink): buffers_dev = device
      * array of `world` pointers, entry r = rank r's symmetric buffer.  Moves less than the multicast scheme
      * only for world == 2. */
     int gsb200_p2p_allreduce_f32(
         void *const *buffers_dev, int64_t n_floats, int rank, int world, void *const *signal_pads_dev,
         int64_t signal_pad_bytes, int blocks, void *stream
+    );
+
+    /* Row-sparse all-reduce of a structure-of-arrays gradient buffer: n_segs segments of n_rows rows (segment k starts
+     * seg_offsets_floats[k] floats into the buffer, seg_widths[k] floats per row); the buffer also holds, at
+     * bitmap_offset_floats, every rank's "row touched" bitmap (ceil(n_rows / 32) words, written by
+     * gsb200_project_sh_bwd).  A group of 32 rows is moved only if some rank touched it, inside it only the touched
+     * rows.  multicast_ptr != NULL: in-switch reduction (multimem.ld_reduce / multimem.st); else peer loads / stores
+     * through buffers_dev.  stats (optional device u64) += number of 16-byte vectors this rank reduced. */
+    int gsb200_rows_allreduce_f32(
+        void *multicast_ptr, void *const *buffers_dev, int n_segs, const int64_t *seg_offsets_floats,
+        const int32_t *seg_widths, int64_t n_rows, int64_t bitmap_offset_floats, int rank, int world,
+        void *const *signal_pads_dev, int64_t signal_pad_bytes, int blocks, void *stats, void *stream
     );
 
 #ifdef __cplusplus

@@ -64,6 +64,56 @@ def main():
             print(f"nvls check ok: world={world} algo={algo} blocks={blocks} payload={mb:.1f} MB  nvls {res['nvls']:.3f} ms  nccl {res['nccl']:.3f} ms", flush=True)
         del arena
 
+    # row-sparse variants (rows-nvls / rows-p2p): every rank marks a different random 30 % of the rows as touched, its
+    # other rows are zero; the result must equal the dense NCCL sum, and only the union's rows may have moved
+    for algo in ("nvls", "p2p"):
+        arena = D.NvlsGradArena(params, blocks=64, algo=algo, row_sparse=True)
+        assert arena.row_sparse and arena.bits is not None
+        g = torch.Generator(device=dev).manual_seed(99 + rank)
+        for it in range(2):
+            seen = torch.rand(N, device=dev, generator=g) < 0.3
+            words = torch.zeros(((N + 31) // 32) * 32, dtype=torch.int64, device=dev)
+            words[:N] = seen.long()
+            packed = (words.view(-1, 32) << torch.arange(32, device=dev)).sum(1)
+            arena.bits.copy_(torch.where(packed >= 2**31, packed - 2**32, packed).to(torch.int32))
+            want = {}
+            for k, p in params.items():
+                src = torch.randn(p.shape, device=dev, generator=g) * seen.view((N,) + (1,) * (p.dim() - 1))
+                arena.views[k].copy_(src)
+                p.grad = arena.views[k]
+                w = src.clone()
+                dist.all_reduce(w)
+                want[k] = w
+            arena.stats.zero_()
+            arena._bits_requests = 1
+            arena.all_reduce()
+            torch.cuda.synchronize()
+            assert arena.last_kind == "rows-" + algo
+            for k, p in params.items():
+                if world == 2:
+                    assert torch.equal(p.grad, want[k]), f"{k}: rows-{algo} differs from NCCL"
+                else:
+                    torch.testing.assert_close(p.grad, want[k], rtol=1e-5, atol=1e-5)
+            moved = torch.tensor([int(arena.stats.item())], device=dev)
+            dist.all_reduce(moved)
+            dense_vec = sum(p.numel() for p in params.values()) // 4
+            frac = float(moved) / dense_vec
+            assert frac < 1.0 - 0.7**world + 0.05, f"rows-{algo} moved {frac:.3f} of the payload"
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            arena._bits_requests = 1
+            arena.all_reduce()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 10], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"nvls check ok: world={world} rows-{algo} moved {frac * 100:.1f} % of the dense payload, {float(t):.3f} ms", flush=True)
+        del arena
+
     # end to end: the fused backward writes its gradients INTO the arena (no staging copy), and the reduced
     # gradients equal those of the NCCL path
     import numpy as np
@@ -100,8 +150,9 @@ def main():
             rel = float((p.grad - want[k]).norm() / want[k].norm().clamp_min(1e-30))
             assert rel < 1e-5, f"{k}: rel error {rel:.3e} vs the NCCL path"
     ops.set_gradient_allocator(None)
+    assert arena.last_kind.startswith("rows-"), arena.last_kind  # the fused backward published its row bitmap
     if rank == 0:
-        print(f"nvls check ok: end-to-end gradients in the arena ({arena.algo})", flush=True)
+        print(f"nvls check ok: end-to-end gradients in the arena ({arena.last_kind})", flush=True)
     dist.destroy_process_group()
 
 

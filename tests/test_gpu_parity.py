@@ -317,6 +317,28 @@ def test_isect_accutile_exact_on_scene(gs):
     assert offn[0] == 0 and (np.diff(offn) >= 0).all() and offn[-1] <= len(ids)
 
 
+@pytest.mark.parametrize("accu", [True, False])
+def test_isect_large_gaussians_cooperative_emit(gs, accu):
+    """Gaussians that cover many tiles take the warp-cooperative emit path (row intervals in closed form, rows
+    placed by a warp scan): counts, unsorted emission order and the sorted lists must stay EXACTLY the oracle's."""
+    sc = scene.make_scene(n_max=20000)
+    sc["scales"] = sc["scales"] * 6.0
+    W, H = 640, 360
+    Ks = scene.rescale_K(sc["Ks"], sc["width"], sc["height"], W, H)
+    radii, m2, dep, con, _ = _project_scene(sc, W, H, Ks, C=2)
+    op = np.ascontiguousarray(np.broadcast_to(sc["opacities"][None], dep.shape))
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    kw_o = (con, op) if accu else (None, None)
+    kw = dict(conics=_t(con), opacities=_t(op)) if accu else {}
+    for sort in (False, True):
+        o = gso.isect_tiles(m2, radii, dep, 16, tw, th, sort, *kw_o)
+        r = gs.isect_tiles(_t(m2), _t(radii), _t(dep), 16, tw, th, sort=sort, **kw)
+        assert o[1].shape[0] > 200000 and _n(r[0]).max() > 100, "the case must contain many-tile gaussians"
+        assert np.array_equal(_n(r[0]), o[0]), "tiles_per_gauss"
+        assert np.array_equal(_n(r[1]), o[1]), f"isect_ids (sort={sort})"
+        assert np.array_equal(_n(r[2]), o[2]), f"flatten_ids (sort={sort})"
+
+
 def test_isect_sorted_equals_stable_sort_of_unsorted(gs):
     """The two-level sort (rows by depth, then intersections by (image, tile) bits only) must give exactly what
     one stable sort of the reference's unsorted emission gives (csrc/Intersect.cpp:283-326)."""

@@ -78,7 +78,10 @@ def main():
     ap.add_argument("--gt-scale", type=float, default=2.0)
     ap.add_argument("--sh-degree-interval", type=int, default=20)
     ap.add_argument("--no-fused-losses", action="store_true", help="b200 backend: keep the package's torch SSIM")
+    ap.add_argument("--fused-ssim-only", action="store_true", help="reference backend + ONLY the fused SSIM of gsplat_b200 (isolates the loss)")
     ap.add_argument("--breakdown", action="store_true", help="CUDA-event phase times of a few steady steps (after the run)")
+    ap.add_argument("--warm", type=int, default=20, help="untimed first steps (allocator / cuDNN autotune / lazy init)")
+    ap.add_argument("--grad-stats", action="store_true", help="default strategy: print quantiles of the densification statistic")
     args = ap.parse_args()
 
     from oracle import refcuda
@@ -116,6 +119,10 @@ def main():
         from gsplat_b200 import dropin
 
         applied = dropin.apply(losses=not args.no_fused_losses)
+    elif args.fused_ssim_only:
+        from gsplat_b200 import dropin
+
+        applied = dropin.apply(losses=True, ops=False)
     rasterization = gsplat.rendering.rasterization
 
     # ---- trainable splats, trainer-style init (simple_trainer.py:292-349) from perturbed ground truth
@@ -216,45 +223,51 @@ def main():
         return loss_val, info
 
     # ---- run
-    n_hist, loss_hist = [], []
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    t_first_refine, steps_1m = None, 0
+    n_hist, loss_hist, grad_stats = [], [], None
+    t0 = t_first_refine = None
+    steps_1m = 0
     for step in range(args.steps):
-        n_before = len(splats["means"])
-        if n_before != N0 and t_first_refine is None:
+        if step == args.warm:
             torch.cuda.synchronize()
-            t_first_refine, steps_1m = time.perf_counter(), step
+            t0 = time.perf_counter()
+        n_before = len(splats["means"])
+        if n_before != N0 and t_first_refine is None and t0 is not None:
+            torch.cuda.synchronize()
+            t_first_refine, steps_1m = time.perf_counter(), step - args.warm
+        if args.grad_stats and not mcmc and grad_stats is None and step == args.refine_start and state.get("grad2d") is not None:
+            gstat = (state["grad2d"] / state["count"].clamp_min(1))[state["count"] > 0]
+            qs = torch.tensor([0.5, 0.8, 0.9, 0.95, 0.98, 0.99], device=gstat.device)
+            grad_stats = {"quantiles": dict(zip(qs.tolist(), torch.quantile(gstat[:: max(1, gstat.numel() // 1_000_000)], qs).tolist())),
+                          "n_seen": int(gstat.numel())}
         loss_val, info = train_step(step)
         if step % 25 == 0 or step == args.steps - 1:
             n_hist.append((step, len(splats["means"])))
             loss_hist.append((step, round(loss_val, 5)))
     torch.cuda.synchronize()
     t1 = time.perf_counter()
+    timed_steps = args.steps - args.warm
     if t_first_refine is None:
-        t_first_refine, steps_1m = t1, args.steps
-    warm = min(20, steps_1m // 4)  # the first steps include allocator warm-up / cuDNN autotune
+        t_first_refine, steps_1m = t1, timed_steps
 
     out = {
         "tool": "trainer_bench", "backend": args.backend, "strategy": args.strategy, "steps": args.steps,
-        "it_per_s_total": args.steps / (t1 - t0),
+        "it_per_s_total": timed_steps / (t1 - t0),
         "steps_at_1M": steps_1m,
-        "it_per_s_at_1M": (steps_1m / (t_first_refine - t0)) if steps_1m else None,
-        "ms_per_step_total": (t1 - t0) / args.steps * 1e3,
+        "it_per_s_at_1M": (steps_1m / (t_first_refine - t0)) if steps_1m > 0 else None,
+        "ms_per_step_total": (t1 - t0) / timed_steps * 1e3,
+        "untimed_warm_steps": args.warm, "grad_stats": grad_stats,
         "n_gaussians_start": N0, "n_gaussians_end": len(splats["means"]), "n_hist": n_hist, "loss_hist": loss_hist,
         "n_isects_last": int(info["flatten_ids"].numel()) if info.get("flatten_ids") is not None else None,
         "path": "gsplat.rasterization() (stock: torch.ops.gsplat.rasterization_3dgs)" if args.backend == "reference"
         else "gsplat.rasterization() after gsplat_b200.dropin.apply()",
-        "dropin": applied, "warm_steps_note": warm,
+        "dropin": applied,
         "schedule": {"refine_start": args.refine_start, "refine_every": args.refine_every, "cap": args.cap,
                      "grow_grad2d": args.grow_grad2d, "views": args.views, "gt_scale": args.gt_scale},
         "max_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
     }
     if args.breakdown:
         # freeze the structure (no refinement) and time the phases of 10 steady steps with CUDA events
-        strategy.refine_stop_iter = 0
-        if mcmc:
-            strategy.refine_start_iter = 10**9
+        strategy.refine_start_iter = 10**9  # keeps the per-step bookkeeping (DefaultStrategy._update_state, MCMC noise)
         acc = {k: 0.0 for k in ("fwd", "loss", "bwd", "opt", "post")}
         reps = 10
         for i in range(3 + reps):
