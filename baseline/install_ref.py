@@ -36,16 +36,28 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 DST = os.path.join(HERE, "_ref")
 
-NERFACC_SHIM = '''"""Minimal stand-in for the two nerfacc (>=0.5.3) functions gsplat's torch compositing twin uses
-(gsplat/cuda/_torch_impl.py:763-766).  Written for the reference's own tests; not part of gsplat_b200."""
+NERFACC_SHIM = '''"""Minimal stand-in for the nerfacc (>=0.5.3) functions gsplat's torch compositing twins use
+(gsplat/cuda/_torch_impl.py:763-766, _torch_impl_eval3d.py:418-469).  Written for the reference's own tests; not part of gsplat_b200."""
 import torch
 
 
-def render_weight_from_alpha(alphas, ray_indices=None, n_rays=None, **_):
+def pack_info(ray_indices, n_rays=None):
+    """[n_rays, 2] = (first sample, sample count) of every ray; ray_indices sorted (nerfacc.pack_info)."""
+    if n_rays is None:
+        n_rays = int(ray_indices.max().item()) + 1 if ray_indices.numel() else 0
+    counts = torch.bincount(ray_indices, minlength=n_rays)
+    starts = torch.cumsum(counts, 0) - counts
+    return torch.stack([starts, counts], dim=-1)
+
+
+def render_weight_from_alpha(alphas, packed_info=None, ray_indices=None, n_rays=None, **_):
     """w_i = alpha_i * prod_{j<i, same ray} (1 - alpha_j); samples of a ray are contiguous and ordered.
     Returns (weights, transmittance) like nerfacc.render_weight_from_alpha (prefix='exclusive')."""
     if alphas.numel() == 0:
         return alphas, alphas
+    if ray_indices is None:
+        counts = packed_info[:, 1]
+        ray_indices = torch.repeat_interleave(torch.arange(counts.numel(), device=alphas.device), counts)
     logt = torch.log1p(-alphas.double())  # float64 prefix sums; autograd flows through the casts
     csum = torch.cumsum(logt, 0) - logt  # exclusive
     first = torch.ones_like(ray_indices, dtype=torch.bool)

@@ -151,6 +151,7 @@ struct RowSegs
     int n;
     int64_t vec_off[kMaxSegs]; // first float4 of the segment
     int32_t width[kMaxSegs];   // floats per row
+    uint32_t magic[kMaxSegs];  // floor(2^32 / width) + 1: n / width == __umulhi(n, magic) for n * width < 2^32
     int64_t n_vec[kMaxSegs];   // float4 in the segment (rows * width / 4, rounded up)
 };
 
@@ -162,9 +163,12 @@ __device__ __forceinline__ uint32_t multimem_ld_reduce_or(const uint32_t *mc)
 }
 
 // does float4 `v` of a 32-row group (rows of `w` floats) contain a row whose bit is set?
-__device__ __forceinline__ bool vec_touched(uint32_t word, int v, int w)
+__device__ __forceinline__ bool vec_touched(uint32_t word, int v, uint32_t magic)
 {
-    const int r0 = (4 * v) / w, r1 = (4 * v + 3) / w; // first / last row the vector overlaps (r1 may be 32: next group's row 0 never)
+    // first / last row of the 32-row group the vector overlaps (4 v + 3 < 32 w, so r1 <= 31)
+    // magic == 0 marks width 1 (2^32 / 1 + 1 does not fit 32 bits): the row index is the float index
+    const int r0 = magic ? (int)__umulhi((uint32_t)(4 * v), magic) : 4 * v;
+    const int r1 = magic ? (int)__umulhi((uint32_t)(4 * v + 3), magic) : 4 * v + 3;
     const uint32_t span = (r1 >= 31 ? 0xffffffffu : ((2u << r1) - 1u)) & ~((1u << r0) - 1u);
     return (word & span) != 0u;
 }
@@ -200,6 +204,7 @@ __global__ void __launch_bounds__(kNvlsThreads) rows_allreduce_kernel(
         for(int k = 0; k < segs.n; ++k)
         {
             const int w        = segs.width[k];
+            const uint32_t magic = segs.magic[k];
             const int64_t base = segs.vec_off[k] + g * 8 * (int64_t)w;
             const int64_t lim  = segs.vec_off[k] + segs.n_vec[k];
             // four vectors in flight per lane: all loads of a round are issued before its stores
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(kNvlsThreads) rows_allreduce_kernel(
                 {
                     const int v     = v0 + 32 * u;
                     const int64_t i = base + v;
-                    on[u]           = v < 8 * w && i < lim && vec_touched(word, v, w);
+                    on[u]           = v < 8 * w && i < lim && vec_touched(word, v, magic);
                     if(on[u])
                     {
                         if constexpr(NVLS)
@@ -316,6 +321,7 @@ extern "C" int gsb200_rows_allreduce_f32(
             return GSB200_E_INVALID;
         segs.vec_off[k] = seg_offsets_floats[k] / 4;
         segs.width[k]   = seg_widths[k];
+        segs.magic[k]   = seg_widths[k] == 1 ? 0u : (uint32_t)(0x100000000ULL / (uint64_t)seg_widths[k]) + 1u;
         segs.n_vec[k]   = (n_rows * seg_widths[k] + 3) / 4;
     }
     cudaStream_t st = (cudaStream_t)stream;

@@ -1037,7 +1037,7 @@ __global__ void __launch_bounds__(kThreads) isect_emit_kernel(
 // scheme of tiles_of_gaussian only carries the previous row's far line over as the next row's near line), so lane r
 // computes row ru0 + r, a warp scan places the rows, and the lanes then write the tiles round-robin -- consecutive
 // lanes, consecutive addresses -- in the same order as the sequential enumeration.
-constexpr int kSmallTiles = 6;
+constexpr int kSmallTiles = 64; // measured: below ~2 warps' worth of tiles the per-gaussian warp hand-over costs more than it saves
 
 struct AccuGauss
 {

@@ -25,6 +25,10 @@
 
 namespace gsb
 {
+// geom stream: (a, c) * -0.5 log2(e), b * -log2(e)  ->  -sigma * log2(e) = A dx^2 + C dy^2 + B dx dy
+constexpr float kLog2e        = 1.4426950408889634f;
+constexpr float kConicScaleAC = -0.5f * kLog2e, kConicScaleB = -kLog2e;
+constexpr float kConicUnscaleAC = 1.0f / kConicScaleAC, kConicUnscaleB = 1.0f / kConicScaleB;
 constexpr int kBatch  = 128; // gaussians per ring stage
 constexpr int kStages = 2;
 constexpr int kWarps  = 8;
@@ -170,7 +174,8 @@ __global__ void __launch_bounds__(256) pack_records_kernel(
     }
     cull[s] = make_float4(m.x, m.y, ex, ey);
     axis[s] = make_float4(ux, uy, lu, lv);
-    geom[s] = make_float4(a, b, c, op);
+    // the conic is stored pre-multiplied so that the exponent of 2 falls out of three FMAs: vis = 2^(A dx^2 + C dy^2 + B dx dy)
+    geom[s] = make_float4(a * kConicScaleAC, b * kConicScaleB, c * kConicScaleAC, op);
     constexpr int CV = RecLayout<CDIM>::kColorVec4;
     float cbuf[CV * 4];
 #pragma unroll
@@ -279,9 +284,12 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
     Ring<CDIM> ring;
     ring.carve(smem_raw);
 
+    __shared__ int32_t s_surv[kWarps][32];
     const TileGeom tg   = decode_tile(order, tw, th);
     const unsigned tid  = threadIdx.x;
     const unsigned warp = tid >> 5, lane = tid & 31;
+    int32_t *surv       = s_surv[warp];
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
     // warp -> 8x4 pixel block inside the 16x16 tile
     const int bx0 = tg.tile_x * kTile + (warp & 1) * 8;
     const int by0 = tg.tile_y * kTile + (warp >> 1) * 4;
@@ -356,27 +364,31 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
             const float4 *scol  = ring.color(stage);
             for(int c0 = 0; c0 < count; c0 += 32)
             {
-                // Each lane tests one gaussian's extent box against this warp's pixel block.  Lane L looks at
-                // record c0 + 31 - L so that the HIGHEST set ballot bit is the FRONT-most survivor (one FLO,
-                // no bit reversal, to walk the survivors front to back).
-                const int mine = c0 + 31 - (int)lane;
+                // Each lane tests one gaussian's extent box against this warp's pixel block; the survivors' batch-local
+                // indices are compacted, front to back, into a per-warp list (walking the ballot mask bit by bit cost 10
+                // instructions per survivor: FLO, shift, xor, index and address arithmetic; the list costs one LDS)
+                const int mine = c0 + (int)lane;
                 bool hit       = false;
                 if(mine < count)
                     hit = block_may_touch(scull[mine], saxis[mine], cx, cy);
-                uint32_t mask = __ballot_sync(0xffffffffu, hit);
-                while(mask)
+                const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                if(mask == 0u)
+                    continue;
+                if(hit)
+                    surv[__popc(mask & lanemask_lt)] = mine;
+                __syncwarp();
+                const int n_surv = __popc(mask);
+                for(int i = 0; i < n_surv; ++i)
                 {
-                    const int j = 31 - __clz(mask);
-                    mask ^= 1u << j;
-                    const int t     = c0 + 31 - j;
+                    const int t     = surv[i];
                     const float4 q  = scull[t];
                     const float4 g  = sgeom[t];
                     const float4 cc = scol[t * CV];
                     const float dx = q.x - px, dy = q.y - py;
-                    const float sigma = 0.5f * (g.x * dx * dx + g.z * dy * dy) + g.y * dx * dy;
-                    const float vis   = fast_exp(-sigma);
+                    const float e2    = fmaf(g.x * dx, dx, fmaf(g.z * dy, dy, (g.y * dx) * dy)); // = -sigma * log2(e)
+                    const float vis   = fast_ex2(e2);
                     const float alpha = fminf(kMaxAlpha, g.w * vis);
-                    if(done == 0u && sigma >= 0.f && alpha >= kAlphaThreshold)
+                    if(done == 0u && e2 <= 0.f && alpha >= kAlphaThreshold)
                     {
                         const float next_T = T * (1.0f - alpha);
                         if(next_T <= kTransmittanceThreshold)
@@ -408,6 +420,7 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
                         }
                     }
                 }
+                __syncwarp(); // the list is rewritten by the next chunk
                 if(__all_sync(0xffffffffu, done != 0u))
                     break; // every pixel of this warp is saturated: drop out of the list
             }
@@ -617,11 +630,11 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd_kernel(
                     const float4 q = scull[t];
                     const float4 g = sgeom[t];
                     const float dx = q.x - px, dy = q.y - py;
-                    const float sigma = 0.5f * (g.x * dx * dx + g.z * dy * dy) + g.y * dx * dy;
-                    const float vis   = fast_exp(-sigma);
+                    const float e2    = fmaf(g.x * dx, dx, fmaf(g.z * dy, dy, (g.y * dx) * dy)); // = -sigma * log2(e)
+                    const float vis   = fast_ex2(e2);
                     const float ov    = g.w * vis;
                     const float alpha = fminf(kMaxAlpha, ov);
-                    const bool valid  = (t <= lim) && sigma >= 0.f && alpha >= kAlphaThreshold;
+                    const bool valid  = (t <= lim) && e2 <= 0.f && alpha >= kAlphaThreshold;
                     if(!__any_sync(0xffffffffu, valid))
                         continue;
                     float col[CV * 4];
@@ -652,8 +665,9 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd_kernel(
                         if(ov <= kMaxAlpha)
                         {
                             const float v_sigma = -ov * v_alpha;
-                            part[0]             = v_sigma * (g.x * dx + g.y * dy);
-                            part[1]             = v_sigma * (g.y * dx + g.z * dy);
+                            const float ca = g.x * kConicUnscaleAC, cb = g.y * kConicUnscaleB, cc2 = g.z * kConicUnscaleAC;
+                            part[0]             = v_sigma * (ca * dx + cb * dy);
+                            part[1]             = v_sigma * (cb * dx + cc2 * dy);
                             part[2]             = 0.5f * v_sigma * dx * dx;
                             part[3]             = v_sigma * dx * dy;
                             part[4]             = 0.5f * v_sigma * dy * dy;
@@ -721,7 +735,7 @@ struct Bwd2Smem
     static constexpr size_t rbuf     = (size_t)kRound * kRowF2 * sizeof(float2);
     static constexpr size_t meta     = (size_t)kRound * 2 * sizeof(float4);
     static constexpr size_t pixc     = (size_t)32 * CV * sizeof(float4);
-    static constexpr size_t slot_t   = (size_t)kRound * sizeof(int32_t);
+    static constexpr size_t slot_t   = (size_t)(kRound + 32) * sizeof(int32_t); // slot -> record index, + the chunk's survivor list
     static constexpr size_t per_warp = rbuf + meta + pixc + slot_t;
     static constexpr size_t total    = ring_al + kWarps * per_warp;
 };
@@ -806,6 +820,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
     float4 *meta         = reinterpret_cast<float4 *>(wbase + SM::rbuf);
     float4 *pixc         = reinterpret_cast<float4 *>(wbase + SM::rbuf + SM::meta);
     int32_t *slot_t      = reinterpret_cast<int32_t *>(wbase + SM::rbuf + SM::meta + SM::pixc); // batch-local record index per slot
+    int32_t *surv        = slot_t + kRound;                                                     // survivors of the current 32-record chunk
+    const uint32_t lanemask_gt = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
 #pragma unroll
     for(int v = 0; v < CV; ++v)
         pixc[lane * CV + v] = make_float4(v_render_c[4 * v], v_render_c[4 * v + 1], v_render_c[4 * v + 2], v_render_c[4 * v + 3]);
@@ -840,8 +856,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
             const int t      = slot_t[sl];
             const float4 q   = scull[t];
             const float4 g   = sgeom[t];
-            meta[sl * 2]     = make_float4(q.x, q.y, g.x, g.y);
-            meta[sl * 2 + 1] = make_float4(g.z, g.w, __int_as_float(sid[t]), 0.f);
+            meta[sl * 2]     = make_float4(q.x, q.y, g.x * kConicUnscaleAC, g.y * kConicUnscaleB);
+            meta[sl * 2 + 1] = make_float4(g.z * kConicUnscaleAC, g.w, __int_as_float(sid[t]), 0.f);
         }
         ncopied = nslots;
     };
@@ -968,20 +984,25 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
                 bool hit       = false;
                 if(mine >= 0 && mine <= warp_lim)
                     hit = block_may_touch(scull[mine], saxis[mine], cx, cy);
-                uint32_t mask = __ballot_sync(0xffffffffu, hit);
-                while(mask)
+                const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                if(mask == 0u)
+                    continue;
+                // survivors compacted back to front into the per-warp list (one LDS per survivor instead of walking the mask)
+                if(hit)
+                    surv[__popc(mask & lanemask_gt)] = mine;
+                __syncwarp();
+                const int n_surv = __popc(mask);
+                for(int si = 0; si < n_surv; ++si)
                 {
-                    const int j = 31 - __clz(mask); // back to front
-                    mask ^= 1u << j;
-                    const int t    = c0 + j;
+                    const int t    = surv[si];
                     const float4 q = scull[t];
                     const float4 g = sgeom[t];
                     const float dx = q.x - px, dy = q.y - py;
-                    const float sigma = 0.5f * (g.x * dx * dx + g.z * dy * dy) + g.y * dx * dy;
-                    const float vis   = fast_exp(-sigma);
+                    const float e2    = fmaf(g.x * dx, dx, fmaf(g.z * dy, dy, (g.y * dx) * dy)); // = -sigma * log2(e)
+                    const float vis   = fast_ex2(e2);
                     const float ov    = g.w * vis;
                     const float alpha = fminf(kMaxAlpha, ov);
-                    const bool valid  = (t <= lim) && sigma >= 0.f && alpha >= kAlphaThreshold;
+                    const bool valid  = (t <= lim) && e2 <= 0.f && alpha >= kAlphaThreshold;
                     if(!__any_sync(0xffffffffu, valid))
                         continue;
                     float f = 0.f, o = 0.f;
@@ -1014,6 +1035,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
                         nslots = ncopied = 0;
                     }
                 }
+                __syncwarp(); // the list is rewritten by the next chunk
             }
             if(nslots > ncopied) // pending survivors of this batch: keep their data before the stage is recycled
                 materialise(nslots, scull, sgeom, sid);

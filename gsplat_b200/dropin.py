@@ -10,6 +10,11 @@ executable form).  ``apply()`` rebinds, in place, the names the reference's call
   gsplat.optimizers.SelectiveAdam                                            (optimizers/selective_adam.py)
   gsplat.losses.ssim_loss when ``losses=True``                               (losses.py:154)
 
+Calls the b200 path does not implement (3DGUT / eval3d, lidar, extra signals, float64 inputs, tile_size != 16, ...)
+and calls with invalid arguments are handed to the package's own implementation -- gsplat_b200 raises
+NotImplementedError / ValueError / TypeError before launching anything -- so upstream behaviour and error messages are
+preserved; ``stats`` counts per name how many calls ran on the b200 kernels and how many were handed over (and why).
+
 Nothing else of the package is touched: strategies, exporters, the Python reference implementations
 (``_rasterization``, ``_torch_impl``) keep running the package's own code -- which is what lets the reference's
 own tests compare the b200 kernels with the reference's Python twins (tests/test_reference_suite.py) and lets
@@ -34,6 +39,33 @@ _OPS = (
 )
 
 _saved: List[Tuple[object, str, object]] = []
+
+# per rebound name: how many calls ran on the b200 kernels, how many were handed to the package's own implementation
+# (and why).  The policy of the drop-in: anything the b200 path does not implement -- 3DGUT / eval3d, lidar, extra
+# signals, float64 inputs, tile_size != 16, ... -- and every argument error is the STOCK implementation's business
+# (same results, same messages as upstream); gsplat_b200 declines BEFORE launching anything, so the hand-over is clean.
+stats: Dict[str, Dict[str, object]] = {}
+
+
+def _delegating(name: str, ours, stock):
+    import functools
+
+    st = stats.setdefault(name, {"b200": 0, "stock": 0, "reasons": {}})
+
+    @functools.wraps(stock)
+    def wrapper(*args, **kwargs):
+        try:
+            out = ours(*args, **kwargs)
+        except (NotImplementedError, TypeError, ValueError) as e:
+            st["stock"] += 1
+            key = f"{type(e).__name__}: {str(e)[:90]}"
+            st["reasons"][key] = st["reasons"].get(key, 0) + 1
+            return stock(*args, **kwargs)
+        st["b200"] += 1
+        return out
+
+    wrapper.__gsb200_ours__ = ours
+    return wrapper
 
 
 def _set(mod, name: str, value) -> None:
@@ -65,18 +97,20 @@ def _apply_ops(B, G) -> None:
     W = importlib.import_module("gsplat.cuda._wrapper")
     R = importlib.import_module("gsplat.rendering")
     for name in _OPS:
-        fn = getattr(B, name)
+        fn = _delegating(name, getattr(B, name), getattr(W, name))
         _set(W, name, fn)
         if hasattr(G, name):
             _set(G, name, fn)
-    _set(W, "adam", B.adam)
-    _set(R, "rasterization", B.rasterization)
-    _set(G, "rasterization", B.rasterization)
+    _set(W, "adam", _delegating("adam", B.adam, W.adam))
+    rast = _delegating("rasterization", B.rasterization, R.rasterization)
+    _set(R, "rasterization", rast)
+    _set(G, "rasterization", rast)
 
     rel = importlib.import_module("gsplat.relocation")
-    _set(rel, "compute_relocation", B.compute_relocation)
+    reloc = _delegating("compute_relocation", B.compute_relocation, rel.compute_relocation)
+    _set(rel, "compute_relocation", reloc)
     sops = importlib.import_module("gsplat.strategy.ops")
-    _set(sops, "compute_relocation", B.compute_relocation)
+    _set(sops, "compute_relocation", reloc)
 
     def _b200_fused_mcmc_perturb(positions, quats, scales, opacities, noise_scale=None, *, scaler=None, t=0.005, k=100.0):
         # same contract as strategy/ops.py:405-461: True when the fused kernel ran

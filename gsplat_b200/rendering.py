@@ -132,10 +132,14 @@ def rasterization(
         ("rays", rays), ("radial_coeffs", radial_coeffs), ("tangential_coeffs", tangential_coeffs),
         ("thin_prism_coeffs", thin_prism_coeffs), ("ftheta_coeffs", ftheta_coeffs), ("lidar_coeffs", lidar_coeffs),
         ("external_distortion_coeffs", external_distortion_coeffs), ("viewmats_rs", viewmats_rs),
-        ("ut_params", ut_params), ("extra_signals", extra_signals), ("renderer_config", renderer_config),
+        ("ut_params", ut_params), ("extra_signals", extra_signals),
     ):
         if val is not None:
             _unsupported(name)
+    # renderer_config selects the implementation of the eval3d rasterizer (reference rendering.py:548-556); the classic
+    # path only admits the default RendererConfig_MixedBatch, which changes nothing here
+    if renderer_config is not None and type(renderer_config).__name__ != "RendererConfig_MixedBatch":
+        _unsupported(f"renderer_config={type(renderer_config).__name__}", "eval3d renderer variants are out of scope")
     if return_normals:
         _unsupported("return_normals")
     if rolling_shutter is not None and getattr(rolling_shutter, "name", str(rolling_shutter)) not in ("GLOBAL", "RollingShutterType.GLOBAL"):

@@ -25,3 +25,18 @@ def pytest_configure(config):
 
         info = dropin.apply(losses=True)
         print(f"[gsb200] drop-in applied: {info}")
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """How many calls of every rebound name ran on the b200 kernels / were handed to the stock implementation."""
+    if os.environ.get("GSB200_DROPIN", "0") != "1":
+        return
+    import json
+
+    from gsplat_b200 import dropin
+
+    out = os.environ.get("GSB200_DROPIN_STATS")
+    if out:
+        with open(out, "w") as f:
+            json.dump(dropin.stats, f, indent=1, sort_keys=True)
+    print("[gsb200] drop-in call statistics:", {k: (v["b200"], v["stock"]) for k, v in dropin.stats.items()})

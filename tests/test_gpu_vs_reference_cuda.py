@@ -89,7 +89,7 @@ def test_projection_and_sh_vs_reference(ref, gs):
     rc = L.gsb200_project_sh_bwd(
         C, len(means), 16, 3, ptr(means), ptr(quats), ptr(scales), ptr(sh), ptr(vm), ptr(Ks), W, H, 0.3, ptr(r_radii),
         ptr(r_con), None, ptr(r_col.contiguous()), ptr(v_m2), 2, ptr(v_dep), 1, ptr(v_con), 3, ptr(v_col), 3, None,
-        ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_sh), stream(),
+        ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_sh), None, stream(),
     )
     assert rc == 0
     assert _rel(v_means, rb[0] + r_vmeans_sh) < 1e-4

@@ -37,6 +37,24 @@ def main():
                 i = hdr.index(k)
                 vals[k] = (r[i], units[i])
                 lines.append(f"| {k} | {r[i]} | {units[i]} |")
+        # the eight largest warp-stall reasons (warps stalled per issue-active cycle)
+        stalls = []
+        for i, h in enumerate(hdr):
+            if "issue_stalled" in h and h.endswith("_per_issue_active.ratio"):
+                try:
+                    stalls.append((float(r[i].replace(",", "")), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
+                except ValueError:
+                    pass
+        for v, h in sorted(stalls, reverse=True)[:8]:
+            lines.append(f"| stall: {h} | {v:.3f} | warps / issue-active cycle |")
+        for k in ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum",
+                  "lts__t_sectors_op_atom.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_active",
+                  "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum", "smsp__inst_executed_op_global_red.sum",
+                  "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+                  "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"):
+            if k in hdr:
+                i = hdr.index(k)
+                lines.append(f"| {k} | {r[i]} | {units[i]} |")
         lines.append("")
         try:
             def to_bytes(k):

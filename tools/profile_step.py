@@ -94,7 +94,7 @@ if args.breakdown:
     def pb():
         return L.gsb200_project_sh_bwd(1, N, 16, 3, ptr(P["means"]), ptr(P["quats"]), ptr(P["scales"]), ptr(P["sh"]), ptr(vm), ptr(K), W, H, 0.3,
                                       ptr(radii), ptr(con), None, ptr(col), g[0].data_ptr(), g[0].stride(-2), ptr(vd), 1, g[1].data_ptr(), g[1].stride(-2),
-                                      g[2].data_ptr(), g[2].stride(-2), None, ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), stream())
+                                      g[2].data_ptr(), g[2].stride(-2), None, ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), None, stream())
     ms_pb, _ = t(pb)
     ms_step, _ = t(step, 10)
     print(f"BREAKDOWN ms: project_sh_fwd {ms_p:.3f} | isect(order+count+scan+sync+emit+sort) {ms_i:.3f} (unsorted {ms_in:.3f}) | offsets {ms_o:.3f} | "

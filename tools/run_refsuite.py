@@ -20,6 +20,7 @@ def run(backend: str, select, extra, out_dir: str, timeout: int):
     xml = os.path.join(out_dir, f"refsuite_{backend}.xml")
     env = dict(os.environ)
     env["GSB200_DROPIN"] = "1" if backend == "b200" else "0"
+    env["GSB200_DROPIN_STATS"] = os.path.join(out_dir, f"refsuite_{backend}_dropin_stats.json")
     env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "refsuite"), os.path.join(ROOT, "baseline", "_ref"), env.get("PYTHONPATH", "")])
     cmd = [sys.executable, "-m", "pytest", "-p", "gsb200_refsuite_plugin", "-q", "-p", "no:cacheprovider", f"--junitxml={xml}",
            "-o", "junit_family=xunit1"] + list(select) + list(extra)
