@@ -1000,6 +1000,45 @@ __global__ void __launch_bounds__(kThreads) isect_count_kernel(
         counts_in_order[j] = cnt;
 }
 
+// row-order count + the two totals the host reads once: [0] = number of intersections, [1] = rows with tiles
+__global__ void __launch_bounds__(kThreads) isect_count_totals_kernel(
+    int64_t total, const float *__restrict__ means2d, const int32_t *__restrict__ radii, const float *__restrict__ conics,
+    const float *__restrict__ opacities, uint32_t tile_size, uint32_t tw, uint32_t th, int32_t *__restrict__ tiles_per_gauss,
+    unsigned long long *__restrict__ totals
+)
+{
+    __shared__ unsigned long long s_tot[2];
+    if(threadIdx.x < 2)
+        s_tot[threadIdx.x] = 0ull;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt         = 0;
+    if(i < total)
+    {
+        const int2 r = reinterpret_cast<const int2 *>(radii)[i];
+        if(r.x > 0 && r.y > 0)
+        {
+            const float2 m = reinterpret_cast<const float2 *>(means2d)[i];
+            float cn[3] = {0.f, 0.f, 0.f}, op = 0.f;
+            const bool accu = conics != nullptr && opacities != nullptr;
+            if(accu)
+                cn[0] = conics[i * 3], cn[1] = conics[i * 3 + 1], cn[2] = conics[i * 3 + 2], op = opacities[i];
+            cnt = tiles_of_gaussian(m.x, m.y, r.x, r.y, accu ? cn : nullptr, accu ? &op : nullptr, tile_size, tw, th, [](int64_t) {});
+        }
+        tiles_per_gauss[i] = cnt;
+    }
+    const int wsum         = __reduce_add_sync(0xffffffffu, cnt);
+    const unsigned nonzero = __ballot_sync(0xffffffffu, cnt > 0);
+    if((threadIdx.x & 31) == 0 && nonzero != 0u)
+    {
+        atomicAdd(&s_tot[0], (unsigned long long)wsum);
+        atomicAdd(&s_tot[1], (unsigned long long)__popc(nonzero));
+    }
+    __syncthreads();
+    if(threadIdx.x < 2 && s_tot[threadIdx.x] != 0ull)
+        atomicAdd(&totals[threadIdx.x], s_tot[threadIdx.x]);
+}
+
 __global__ void __launch_bounds__(kThreads) isect_emit_kernel(
     int64_t total, int64_t N, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
     const float *__restrict__ depths, const float *__restrict__ conics, const float *__restrict__ opacities,
@@ -1635,6 +1674,51 @@ extern "C" int gsb200_isect_emit(
             total, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
             tile_bits, isect_ids, flatten_ids
         );
+    return check_launch();
+}
+
+extern "C" int gsb200_isect_count_totals(
+    int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *conics, const float *opacities,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int32_t *tiles_per_gauss, int64_t *totals, void *stream
+)
+{
+    if(I < 0 || N < 0 || tile_size == 0 || !totals)
+        return GSB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    GSB_CUDA_TRY(cudaMemsetAsync(totals, 0, 2 * sizeof(int64_t), st));
+    const int64_t total = I * N;
+    if(total == 0)
+        return GSB200_OK;
+    if(!means2d || !radii || !tiles_per_gauss || total > 0x7fffffffLL)
+        return GSB200_E_INVALID;
+    if(bits_for_count(I) + bits_for_count((int64_t)tile_width * tile_height) > 32)
+        return GSB200_E_KEYBITS;
+    isect_count_totals_kernel<<<grid_for(total, kThreads), kThreads, 0, st>>>(
+        total, means2d, radii, conics, opacities, tile_size, tile_width, tile_height, tiles_per_gauss,
+        reinterpret_cast<unsigned long long *>(totals)
+    );
+    return check_launch();
+}
+
+extern "C" int gsb200_isect_emit_ordered(
+    int64_t I, int64_t N, int64_t n_order, const float *means2d, const int32_t *radii, const float *depths,
+    const float *conics, const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids, const int32_t *order,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids, int32_t *flatten_ids, void *stream
+)
+{
+    if(I < 0 || N < 0 || n_order < 0 || tile_size == 0)
+        return GSB200_E_INVALID;
+    if(n_order == 0)
+        return GSB200_OK;
+    if(!means2d || !radii || !depths || !cum_tiles || !order || !isect_ids || !flatten_ids)
+        return GSB200_E_INVALID;
+    const uint32_t tile_bits = bits_for_count((int64_t)tile_width * tile_height);
+    if(bits_for_count(I) + tile_bits > 32)
+        return GSB200_E_KEYBITS;
+    isect_emit_coop_kernel<<<grid_for(n_order, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        n_order, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
+        tile_bits, isect_ids, flatten_ids
+    );
     return check_launch();
 }
 

@@ -5,6 +5,10 @@
 // once over the N projected rows on (image, depth) and once over the S intersections on the (image, tile)
 // bits only -- see gsb200_isect_depth_order below.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include "common.cuh"
 
@@ -90,6 +94,21 @@ __global__ void __launch_bounds__(256) depth_key_kernel(
     rows[i] = (int32_t)i;
 }
 
+// single image: the key is the depth's bit pattern alone (culled rows 0xffffffff sort last; a visible depth is a
+// positive finite float, never that pattern) -- 8 instead of 12 bytes per row and pass
+__global__ void __launch_bounds__(256) depth_key32_kernel(
+    int64_t total, const int32_t *__restrict__ radii, const float *__restrict__ depths, uint32_t *__restrict__ keys,
+    int32_t *__restrict__ rows
+)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= total)
+        return;
+    const int2 r = reinterpret_cast<const int2 *>(radii)[i];
+    keys[i]      = (r.x > 0 && r.y > 0) ? __float_as_uint(depths[i]) : 0xffffffffu;
+    rows[i]      = (int32_t)i;
+}
+
 struct DepthOrderLayout
 {
     size_t keys_in, keys_out, rows_in, cub, total;
@@ -139,11 +158,138 @@ extern "C" int gsb200_isect_depth_order(
     uint64_t *k_in   = reinterpret_cast<uint64_t *>(ws + L.keys_in), *k_out = reinterpret_cast<uint64_t *>(ws + L.keys_out);
     int32_t *rows_in = reinterpret_cast<int32_t *>(ws + L.rows_in);
     cudaStream_t st  = (cudaStream_t)stream;
+    size_t cub_bytes = L.total - L.cub;
+    if(I == 1 && image_ids == nullptr)
+    { // 32-bit keys in the (larger) 64-bit key buffers; the CUB temp storage sized for 64-bit keys is ample
+        uint32_t *k32_in = reinterpret_cast<uint32_t *>(k_in), *k32_out = reinterpret_cast<uint32_t *>(k_out);
+        gsb::depth_key32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, radii, depths, k32_in, rows_in);
+        if(int rc = gsb::check_launch())
+            return rc;
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs((void *)nullptr, need, k32_in, k32_out, rows_in, order, total, 0, 32, st);
+        if(need > cub_bytes)
+            return GSB200_E_WORKSPACE;
+        GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws + L.cub, need, k32_in, k32_out, rows_in, order, total, 0, 32, st));
+        return GSB200_OK;
+    }
     gsb::depth_key_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, N, radii, depths, image_ids, k_in, rows_in);
     if(int rc = gsb::check_launch())
         return rc;
-    size_t cub_bytes = L.total - L.cub;
     GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, k_in, k_out, rows_in, order, total, 0, end_bit, st));
     return GSB200_OK;
 }
 
+
+// ---- depth order of the rows that HAVE tiles (round 2).  gsb200_isect_depth_order sorts every projected row, culled
+// ones included (71 % at BASELINE configs[2]; in a trainer with 3 M gaussians that is 2 M dead rows through four radix
+// passes).  Once the per-row tile counts are known (gsb200_isect_count_totals) and the host has read the two totals,
+// the rows with tiles are compacted (stable: ascending row index), only those are sorted by (image, depth), and the
+// counts are scanned in that order -- same final order as before (both steps are stable), a third of the rows.
+namespace gsb
+{
+struct HasTiles
+{
+    const int32_t *tiles;
+    __host__ __device__ bool operator()(const int32_t &i) const { return tiles[i] > 0; }
+};
+struct CountOf
+{
+    const int32_t *tiles;
+    __host__ __device__ int64_t operator()(const int32_t &row) const { return (int64_t)tiles[row]; }
+};
+
+__global__ void __launch_bounds__(256) depth_key_rows_kernel(
+    int64_t n_rows, int64_t N, const int32_t *__restrict__ rows, const float *__restrict__ depths,
+    const int64_t *__restrict__ image_ids, bool single_image, void *__restrict__ keys
+)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(j >= n_rows)
+        return;
+    const int64_t i  = rows[j];
+    const uint32_t d = __float_as_uint(depths[i]);
+    if(single_image)
+        static_cast<uint32_t *>(keys)[j] = d;
+    else
+        static_cast<uint64_t *>(keys)[j] = ((uint64_t)(image_ids ? image_ids[i] : i / N) << 32) | (uint64_t)d;
+}
+
+struct VisibleOrderLayout
+{
+    size_t rows_in, keys_in, keys_out, n_sel, cub, total;
+};
+static VisibleOrderLayout visible_order_layout(int64_t total_rows, int64_t n_vis, int end_bit)
+{
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    VisibleOrderLayout L;
+    size_t a = 0, b = 0, c = 0;
+    cub::DeviceSelect::If((void *)nullptr, a, cub::CountingInputIterator<int32_t>(0), (int32_t *)nullptr, (int32_t *)nullptr, total_rows, HasTiles{nullptr});
+    cub::DeviceRadixSort::SortPairs(
+        (void *)nullptr, b, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const int32_t *)nullptr, (int32_t *)nullptr, n_vis, 0, end_bit
+    );
+    cub::TransformInputIterator<int64_t, CountOf, const int32_t *> it((const int32_t *)nullptr, CountOf{nullptr});
+    cub::DeviceScan::InclusiveSum((void *)nullptr, c, it, (int64_t *)nullptr, n_vis);
+    const size_t cub_bytes = a > b ? (a > c ? a : c) : (b > c ? b : c);
+    L.rows_in  = 0;
+    L.keys_in  = L.rows_in + al(sizeof(int32_t) * (size_t)n_vis);
+    L.keys_out = L.keys_in + al(sizeof(uint64_t) * (size_t)n_vis);
+    L.n_sel    = L.keys_out + al(sizeof(uint64_t) * (size_t)n_vis);
+    L.cub      = L.n_sel + 256;
+    L.total    = L.cub + al(cub_bytes) + 256;
+    return L;
+}
+} // namespace gsb
+
+extern "C" size_t gsb200_isect_order_visible_workspace_bytes(int64_t I, int64_t total_rows, int64_t n_vis)
+{
+    if(total_rows <= 0 || I <= 0 || n_vis <= 0)
+        return 0;
+    return gsb::visible_order_layout(total_rows, n_vis, 32 + (int)gsb::bits_for_count(I)).total;
+}
+
+extern "C" int gsb200_isect_order_visible(
+    int64_t I, int64_t N, int64_t n_vis, const int32_t *tiles_per_gauss, const float *depths, const int64_t *image_ids,
+    int32_t *order, int64_t *cum_tiles, void *workspace, size_t workspace_bytes, void *stream
+)
+{
+    if(I < 0 || N < 0 || n_vis < 0)
+        return GSB200_E_INVALID;
+    const int64_t total = image_ids ? N : I * N;
+    if(total == 0 || n_vis == 0)
+        return GSB200_OK;
+    if(!tiles_per_gauss || !depths || !order || !cum_tiles || !workspace || total > 0x7fffffffLL || n_vis > total)
+        return GSB200_E_INVALID;
+    const bool single = (I == 1 && image_ids == nullptr);
+    const int end_bit = single ? 32 : 32 + (int)gsb::bits_for_count(I);
+    const auto L      = gsb::visible_order_layout(total, n_vis, 32 + (int)gsb::bits_for_count(I));
+    if(L.total > workspace_bytes)
+        return GSB200_E_WORKSPACE;
+    char *ws         = static_cast<char *>(workspace);
+    int32_t *rows_in = reinterpret_cast<int32_t *>(ws + L.rows_in);
+    void *k_in = ws + L.keys_in, *k_out = ws + L.keys_out;
+    int32_t *n_sel   = reinterpret_cast<int32_t *>(ws + L.n_sel);
+    cudaStream_t st  = (cudaStream_t)stream;
+    size_t cub_bytes = L.total - L.cub;
+    // 1. rows with tiles, ascending (n_vis of them: the caller read that total from gsb200_isect_count_totals)
+    GSB_CUDA_TRY(cub::DeviceSelect::If(
+        ws + L.cub, cub_bytes, cub::CountingInputIterator<int32_t>(0), rows_in, n_sel, total, gsb::HasTiles{tiles_per_gauss}, st
+    ));
+    // 2. (image, depth) keys of those rows, stable sort
+    gsb::depth_key_rows_kernel<<<(unsigned)((n_vis + 255) / 256), 256, 0, st>>>(n_vis, N, rows_in, depths, image_ids, single, k_in);
+    if(int rc = gsb::check_launch())
+        return rc;
+    cub_bytes = L.total - L.cub;
+    if(single)
+        GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(
+            ws + L.cub, cub_bytes, static_cast<const uint32_t *>(k_in), static_cast<uint32_t *>(k_out), rows_in, order, n_vis, 0, 32, st
+        ));
+    else
+        GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(
+            ws + L.cub, cub_bytes, static_cast<const uint64_t *>(k_in), static_cast<uint64_t *>(k_out), rows_in, order, n_vis, 0, end_bit, st
+        ));
+    // 3. inclusive scan of the tile counts taken in that order
+    cub::TransformInputIterator<int64_t, gsb::CountOf, const int32_t *> it(order, gsb::CountOf{tiles_per_gauss});
+    cub_bytes = L.total - L.cub;
+    GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(ws + L.cub, cub_bytes, it, cum_tiles, n_vis, st));
+    return GSB200_OK;
+}

@@ -704,6 +704,49 @@ def isect_tiles(
     if total == 0:
         return (tiles_per_gauss, torch.empty(0, device=dev, dtype=torch.int64), torch.empty(0, device=dev, dtype=torch.int32))
     accu = conics is not None and opacities is not None
+    if sort and not packed:
+        # dense, sorted (the rasterization() path): count first, read both totals with ONE host sync, then order and
+        # scan only the rows that have tiles (a third of the rows at BASELINE configs[2]: the culled ones never enter
+        # the four radix passes of the depth order)
+        totals = torch.empty(2, device=dev, dtype=torch.int64)
+        with _Ctx(dev) as st:
+            check(
+                L.gsb200_isect_count_totals(
+                    I, N, ptr(means2d), ptr(radii), ptr(conics) if accu else None, ptr(opacities) if accu else None, tile_size,
+                    tile_width, tile_height, ptr(tiles_per_gauss), ptr(totals), st,
+                ),
+                "intersect_tile (count)",
+            )
+            n_isects, n_vis = (int(v) for v in totals.tolist())  # the one host sync of the forward (reference: csrc/Intersect.cpp:259)
+            isect_ids = torch.empty(n_isects, device=dev, dtype=torch.int64)
+            flatten_ids = torch.empty(n_isects, device=dev, dtype=torch.int32)
+            if n_isects == 0:
+                return tiles_per_gauss, isect_ids, flatten_ids
+            order = torch.empty(n_vis, device=dev, dtype=torch.int32)
+            cum = torch.empty(n_vis, device=dev, dtype=torch.int64)
+            ws = _scratch_buffer(dev, "vorder", L.gsb200_isect_order_visible_workspace_bytes(I, total, n_vis))
+            check(
+                L.gsb200_isect_order_visible(I, N, n_vis, ptr(tiles_per_gauss), ptr(depths), None, ptr(order), ptr(cum), ptr(ws), ws.numel(), st),
+                "intersect_tile (order)",
+            )
+            check(
+                L.gsb200_isect_emit_ordered(
+                    I, N, n_vis, ptr(means2d), ptr(radii), ptr(depths), ptr(conics) if accu else None,
+                    ptr(opacities) if accu else None, ptr(cum), None, ptr(order), tile_size, tile_width, tile_height,
+                    ptr(isect_ids), ptr(flatten_ids), st,
+                ),
+                "intersect_tile (emit)",
+            )
+            begin_bit, end_bit = 32, 32 + tile_bits + image_bits
+            keys_out, vals_out = torch.empty_like(isect_ids), torch.empty_like(flatten_ids)
+            ws = _scratch_buffer(dev, "sort", L.gsb200_sort_workspace_bytes(n_isects, begin_bit, end_bit))
+            check(
+                L.gsb200_sort_pairs(
+                    n_isects, begin_bit, end_bit, ptr(isect_ids), ptr(flatten_ids), ptr(keys_out), ptr(vals_out), ptr(ws), ws.numel(), st,
+                ),
+                "intersect_tile (sort)",
+            )
+        return tiles_per_gauss, keys_out, vals_out
     cum = torch.empty(total, device=dev, dtype=torch.int64)
     with _Ctx(dev) as st:
         order = None

@@ -199,6 +199,28 @@ extern "C"
         uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids, int32_t *flatten_ids,
         void *stream
     );
+    /* Faster pass 0 / 1 for the sorted dense layout (round 2): count first, in row order, and hand the host BOTH totals
+     * -- totals[0] = n_isects, totals[1] = rows that have tiles -- in one read; then order ONLY those rows:
+     * gsb200_isect_order_visible compacts them (stable), sorts them by (image, depth) and scans their counts in that
+     * order (order int32 [n_vis], cum_tiles int64 [n_vis]); gsb200_isect_emit_ordered emits from the n_vis ordered rows.
+     * Same intersections in the same final order as gsb200_isect_depth_order + gsb200_isect_count + gsb200_isect_emit. */
+    int gsb200_isect_count_totals(
+        int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *conics, const float *opacities,
+        uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int32_t *tiles_per_gauss, int64_t *totals,
+        void *stream
+    );
+    size_t gsb200_isect_order_visible_workspace_bytes(int64_t I, int64_t total_rows, int64_t n_vis);
+    int gsb200_isect_order_visible(
+        int64_t I, int64_t N, int64_t n_vis, const int32_t *tiles_per_gauss, const float *depths,
+        const int64_t *image_ids, int32_t *order, int64_t *cum_tiles, void *workspace, size_t workspace_bytes,
+        void *stream
+    );
+    int gsb200_isect_emit_ordered(
+        int64_t I, int64_t N, int64_t n_order, const float *means2d, const int32_t *radii, const float *depths,
+        const float *conics, const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids,
+        const int32_t *order, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids,
+        int32_t *flatten_ids, void *stream
+    );
     /* Stable radix sort of (isect_ids, flatten_ids) on key bits [begin_bit, end_bit)
      * (cub::DeviceRadixSort::SortPairs, csrc/IntersectTile.cu:1078-1121); begin_bit = 32 after pass 0. */
     size_t gsb200_sort_workspace_bytes(int64_t n_isects, int begin_bit, int end_bit);
