@@ -211,7 +211,7 @@ __device__ __forceinline__ const float4 *gaxis_from(const float4 *gcull, const f
 }
 
 // shared-memory ring: per stage [cull | axis | geom | color] + one full-barrier per stage
-template<int CDIM, int BATCH = kBatch>
+template<int CDIM, int BATCH = kBatch, int STAGES = kStages>
 struct Ring
 {
     static constexpr int CV = RecLayout<CDIM>::kColorVec4;
@@ -228,11 +228,11 @@ struct Ring
     __device__ __forceinline__ float4 *color(int s) const { return cull(s) + 3 * BATCH; }
     __device__ __forceinline__ uint64_t *full(int s) const
     {
-        return reinterpret_cast<uint64_t *>(base + (size_t)kStages * kStageBytes) + s;
+        return reinterpret_cast<uint64_t *>(base + (size_t)STAGES * kStageBytes) + s;
     }
     __device__ __forceinline__ int32_t *ids(int s) const
     {
-        return reinterpret_cast<int32_t *>(base + (size_t)kStages * kStageBytes + kStages * sizeof(uint64_t)) + s * BATCH;
+        return reinterpret_cast<int32_t *>(base + (size_t)STAGES * kStageBytes + STAGES * sizeof(uint64_t)) + s * BATCH;
     }
     // one thread: arm the barrier and launch the four bulk copies of records [first, first+count)
     __device__ __forceinline__ void issue(
@@ -249,12 +249,12 @@ struct Ring
     }
 };
 
-template<int CDIM, int BATCH = kBatch>
+template<int CDIM, int BATCH = kBatch, int STAGES = kStages>
 constexpr size_t ring_smem_bytes()
 {
     // stages | full barriers | per-stage gaussian ids (backward only)
-    return (size_t)kStages * RecLayout<CDIM, BATCH>::kStageBytes + kStages * sizeof(uint64_t)
-         + (size_t)kStages * BATCH * sizeof(int32_t);
+    return (size_t)STAGES * RecLayout<CDIM, BATCH>::kStageBytes + STAGES * sizeof(uint64_t)
+         + (size_t)STAGES * BATCH * sizeof(int32_t);
 }
 
 // Can the gaussian reach alpha >= 1/255 anywhere in the 8x4 pixel block centred at (cx, cy)?  Conservative:
@@ -727,11 +727,14 @@ constexpr int kBwdBatch = 64; // records per ring stage (smaller than the forwar
 constexpr int kRound    = 16; // survivors per reduction round of a warp
 constexpr int kRowF2    = 33; // row stride of the round buffer in float2 units (odd: conflict-free in both phases)
 
-template<int CDIM>
+constexpr int kPipeStages = 3; // ring depth of the barrier-free variant (warps may drift two batches apart)
+
+template<int CDIM, bool PIPE = false>
 struct Bwd2Smem
 {
     static constexpr int CV          = RecLayout<CDIM>::kColorVec4;
-    static constexpr size_t ring_al  = (ring_smem_bytes<CDIM, kBwdBatch>() + 15) & ~size_t(15);
+    static constexpr int KS          = PIPE ? kPipeStages : kStages;
+    static constexpr size_t ring_al  = (ring_smem_bytes<CDIM, kBwdBatch, KS>() + 15) & ~size_t(15);
     static constexpr size_t rbuf     = (size_t)kRound * kRowF2 * sizeof(float2);
     static constexpr size_t meta     = (size_t)kRound * 2 * sizeof(float4);
     static constexpr size_t pixc     = (size_t)32 * CV * sizeof(float4);
@@ -745,7 +748,12 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template<int CDIM, bool ABS, int MINB>
+// PIPE = true: no CTA barrier in the batch loop.  Every warp waits for the stage's TMA barrier, works through the
+// batch at its own pace and then counts itself off on the stage; the LAST warp to do so re-arms the barrier and issues
+// the bulk copies of the batch three ahead.  Warps of a tile differ a lot in survivors per 64-record batch, and with
+// two CTA barriers per batch every warp ran at the pace of the slowest one.  The gaussian ids are read from global
+// memory when a survivor's data is materialised (no per-batch staging, hence no barrier for it either).
+template<int CDIM, bool ABS, int MINB, bool PIPE = false>
 __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
     const uint32_t I, const int64_t n_isects, const float4 *__restrict__ gcull, const float4 *__restrict__ ggeom,
     const float4 *__restrict__ gcolor, const int32_t *__restrict__ order, const int32_t *__restrict__ flatten_ids,
@@ -758,11 +766,13 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
     constexpr int CV  = RecLayout<CDIM>::kColorVec4;
     constexpr int NV  = 6 + CDIM + (ABS ? 2 : 0); // [v_xy 2 | v_conic 3 | v_opacity 1 | v_rgb CDIM | abs 2]
     constexpr int NV4 = (NV + 3) / 4;
-    using SM          = Bwd2Smem<CDIM>;
+    using SM          = Bwd2Smem<CDIM, PIPE>;
+    constexpr int KS  = SM::KS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Ring<CDIM, kBwdBatch> ring;
+    Ring<CDIM, kBwdBatch, KS> ring;
     ring.carve(smem_raw);
     __shared__ int32_t s_tile_bin;
+    __shared__ int32_t s_done[kPipeStages]; // PIPE: warps that have finished with the stage's current batch
 
     const TileGeom tg      = decode_tile(order, tw, th);
     const unsigned tid     = threadIdx.x;
@@ -802,8 +812,11 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
     {
         s_tile_bin = -1;
 #pragma unroll
-        for(int s = 0; s < kStages; ++s)
+        for(int s = 0; s < KS; ++s)
+        {
             mbar_init(ring.full(s), 1);
+            s_done[s < kPipeStages ? s : 0] = 0;
+        }
         fence_mbar_init();
     }
     __syncthreads();
@@ -835,7 +848,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
     if(tid == 0)
     {
 #pragma unroll
-        for(int s = 0; s < kStages; ++s)
+        for(int s = 0; s < KS; ++s)
             if(s < num_batches)
                 ring.issue(s, gcull, ggeom, gcolor, batch_first(s), batch_count(s));
     }
@@ -857,7 +870,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
             const float4 q   = scull[t];
             const float4 g   = sgeom[t];
             meta[sl * 2]     = make_float4(q.x, q.y, g.x * kConicUnscaleAC, g.y * kConicUnscaleB);
-            meta[sl * 2 + 1] = make_float4(g.z * kConicUnscaleAC, g.w, __int_as_float(sid[t]), 0.f);
+            meta[sl * 2 + 1] = make_float4(g.z * kConicUnscaleAC, g.w, __int_as_float(sid[t]), 0.f); // PIPE: sid = flatten_ids + first
         }
         ncopied = nslots;
     };
@@ -960,21 +973,27 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
     int nslots = 0;
     for(int b = 0; b < num_batches; ++b)
     {
-        const int stage       = b % kStages;
-        const uint32_t parity = (uint32_t)(b / kStages) & 1u;
+        const int stage       = b % KS;
+        const uint32_t parity = (uint32_t)(b / KS) & 1u;
         const int32_t first   = (int32_t)batch_first(b);
         const int count       = batch_count(b);
-        if((int)tid < count)
-            ring.ids(stage)[tid] = flatten_ids[first + tid];
-        __syncthreads();
+        if constexpr(!PIPE)
+        {
+            if((int)tid < count)
+                ring.ids(stage)[tid] = flatten_ids[first + tid];
+            __syncthreads();
+        }
+        else
+            mbar_wait(ring.full(stage), parity); // every warp, also one that skips the batch: keeps the stage counters in step
         if(first <= warp_bin_final)
         {
-            mbar_wait(ring.full(stage), parity);
+            if constexpr(!PIPE)
+                mbar_wait(ring.full(stage), parity);
             const float4 *scull = ring.cull(stage);
             const float4 *saxis = ring.axis(stage);
             const float4 *sgeom = ring.geom(stage);
             const float4 *scol  = ring.color(stage);
-            const int32_t *sid  = ring.ids(stage);
+            const int32_t *sid  = PIPE ? flatten_ids + first : ring.ids(stage);
             const int lim       = bin_final - first;      // local index of this pixel's last contributor
             const int warp_lim  = warp_bin_final - first; // ... of the warp's
             for(int c1 = count; c1 > 0; c1 -= 32)
@@ -1040,12 +1059,30 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
             if(nslots > ncopied) // pending survivors of this batch: keep their data before the stage is recycled
                 materialise(nslots, scull, sgeom, sid);
         }
-        __syncthreads(); // stage (records + ids) fully consumed
-        if(tid == 0)
+        if constexpr(!PIPE)
         {
-            mbar_wait(ring.full(stage), parity); // landed even if every warp skipped it
-            if(b + kStages < num_batches)
-                ring.issue(stage, gcull, ggeom, gcolor, batch_first(b + kStages), batch_count(b + kStages));
+            __syncthreads(); // stage (records + ids) fully consumed
+            if(tid == 0)
+            {
+                mbar_wait(ring.full(stage), parity); // landed even if every warp skipped it
+                if(b + KS < num_batches)
+                    ring.issue(stage, gcull, ggeom, gcolor, batch_first(b + KS), batch_count(b + KS));
+            }
+        }
+        else
+        {
+            __syncwarp();
+            if(lane == 0)
+            {
+                __threadfence_block(); // this warp's reads of the stage are done before it is counted off
+                if(atomicAdd(&s_done[stage], 1) == kWarps - 1)
+                { // last warp out: the stage is free -- re-arm it and fetch the batch KS ahead
+                    s_done[stage] = 0;
+                    __threadfence_block();
+                    if(b + KS < num_batches)
+                        ring.issue(stage, gcull, ggeom, gcolor, batch_first(b + KS), batch_count(b + KS));
+                }
+            }
         }
     }
     if(nslots > 0)
@@ -1131,31 +1168,43 @@ static int launch_bwd(
            && dst.conics == dst.means2d + 2 && dst.opacities == dst.means2d + 5 && dst.colors == dst.means2d + 6
            && (!absg || (dst.s_abs == P && dst.abs == dst.means2d + 6 + CDIM)) && (reinterpret_cast<uintptr_t>(dst.means2d) & 15) == 0)
             packed = (uint32_t)P;
-        const size_t smem2 = Bwd2Smem<CDIM>::total;
-#define GSB_BWD2_LAUNCH(ABSV, MINBV)                                                                                    \
+        // GSB200_BWD_PIPE=0 keeps the two CTA barriers per batch (measurements); default: barrier-free ring
+        static const bool pipe = [] {
+            const char *e = std::getenv("GSB200_BWD_PIPE");
+            return !(e && e[0] == '0');
+        }();
+#define GSB_BWD2_LAUNCH(ABSV, MINBV, PIPEV)                                                                             \
     do                                                                                                                  \
     {                                                                                                                   \
+        const size_t smem2 = Bwd2Smem<CDIM, PIPEV>::total;                                                              \
         GSB_CUDA_TRY(cudaFuncSetAttribute(                                                                              \
-            raster_bwd2_kernel<CDIM, ABSV, MINBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2              \
+            raster_bwd2_kernel<CDIM, ABSV, MINBV, PIPEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2       \
         ));                                                                                                             \
-        raster_bwd2_kernel<CDIM, ABSV, MINBV><<<n_tiles, kWarps * 32, smem2, st>>>(                                      \
+        raster_bwd2_kernel<CDIM, ABSV, MINBV, PIPEV><<<n_tiles, kWarps * 32, smem2, st>>>(                               \
             (uint32_t)I, S, r.cull, r.geom, r.color, order, flatten_ids, backgrounds, masks, W, H, tw, th, offsets,     \
             render_alphas, last_ids, v_render_colors, v_render_alphas, dst, packed                                      \
         );                                                                                                              \
     } while(0)
         if constexpr(CDIM <= 4)
         {
-            if(absg)
-                GSB_BWD2_LAUNCH(true, 4);
+            if(pipe)
+            {
+                if(absg)
+                    GSB_BWD2_LAUNCH(true, 4, true);
+                else
+                    GSB_BWD2_LAUNCH(false, 4, true);
+            }
+            else if(absg)
+                GSB_BWD2_LAUNCH(true, 4, false);
             else
-                GSB_BWD2_LAUNCH(false, 4);
+                GSB_BWD2_LAUNCH(false, 4, false);
         }
         else
         {
             if(absg)
-                GSB_BWD2_LAUNCH(true, 1);
+                GSB_BWD2_LAUNCH(true, 1, false);
             else
-                GSB_BWD2_LAUNCH(false, 1);
+                GSB_BWD2_LAUNCH(false, 1, false);
         }
 #undef GSB_BWD2_LAUNCH
         return check_launch();
