@@ -721,20 +721,20 @@ def main():
             traffic = None
     achieved = bytes_bwd / (ms_rbwd * 1e-3) / 1e9
     roofline = {
-        "kernel": "raster_bwd_kernel<3> (+ zero-init of the gradient records)", "bound": "hbm", "achieved": achieved,
+        "kernel": "raster_bwd2_kernel<3,false,4,pipe> (+ zero-init of the gradient records)", "bound": "hbm", "achieved": achieved,
         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes": bytes_bwd, "ms": ms_rbwd, "n_isects": S,
         "note": "compositing is FP32/MUFU-bound, not HBM-bound (SURVEY.md section 8d): the HBM fraction is reported as "
         "required, pair throughput below is the meaningful figure",
         "raster_fwd": {"ms": ms_rfwd, "achieved": bytes_fwd / (ms_rfwd * 1e-3) / 1e9, "algorithmic_bytes": bytes_fwd},
         # compute-side figure: candidate (pixel, gaussian) pairs = 256 per (tile, gaussian)
-        # intersection; the kernels are instruction-issue bound (profiles/r01_v6_ncu.md: 81 % / 87 % issue-active)
+        # intersection; the kernels are instruction-issue bound (profiles/r02_v1_ncu.md: 77 % / 85 % issue-active)
         "pairs": {
             "candidate_pairs": 256 * S,
             "bwd_gpairs_per_s": 256 * S / (ms_rbwd * 1e-3) / 1e9,
             "fwd_gpairs_per_s": 256 * S / (ms_rfwd * 1e-3) / 1e9,
             "issue_peak_ginst_per_s": 148 * 4 * 1.965,
-            "issue_evidence": "profiles/r01_v6_ncu.md (smsp__issue_active, smsp__inst_executed)",
+            "issue_evidence": "profiles/r02_v1_ncu.md (smsp__issue_active, smsp__inst_executed: 413 M backward, 238 M forward)",
         },
     }
 
@@ -762,9 +762,10 @@ def main():
                 "value": n_gpus * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
             },
-            # our own kernels per step: project_sh_fwd, depth_key, isect_count, isect_emit, isect_offsets,
-            # pack_records, tile_order, raster_fwd, l1 partial/final/bwd, raster_bwd, project_sh_bwd (= 13; cub scan / radix-sort launches
-            # made by the library are not counted); timed region = `steps` device-resident + `steps` e2e steps
+            # our own kernels per step (profiles/r02_v1_launches.csv): project_sh_fwd, isect_count_totals, depth_key_rows,
+            # isect_emit_coop, isect_offsets, pack_records, tile_order, raster_fwd, l1 partial/final/bwd, raster_bwd2,
+            # project_sh_bwd (= 13; the cub select / scan / radix-sort launches made by the library are not counted);
+            # timed region = `steps` device-resident + `steps` e2e steps
             "gpu_launches": args.steps * 2 * (13 + (1 if arena is not None else 0)),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "ref_cuda_stock": ref_stock,
             "ref_cuda": ref_cuda, "big_s": big_s, "trainer": trainer, "dp": dp_info,

@@ -19,6 +19,8 @@ SUITE = os.path.join(ROOT, "baseline", "_ref", "reference_suite")
 def run(backend: str, select, extra, out_dir: str, timeout: int):
     xml = os.path.join(out_dir, f"refsuite_{backend}.xml")
     env = dict(os.environ)
+    for k in ("MASTER_PORT", "MASTER_ADDR", "RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)  # the suite's dist_init fixture picks a free port of its own (a parent test may hold one)
     env["GSB200_DROPIN"] = "1" if backend == "b200" else "0"
     env["GSB200_DROPIN_STATS"] = os.path.join(out_dir, f"refsuite_{backend}_dropin_stats.json")
     env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "refsuite"), os.path.join(ROOT, "baseline", "_ref"), env.get("PYTHONPATH", "")])
