@@ -269,8 +269,14 @@ __device__ __forceinline__ bool block_may_touch(const float4 q, const float4 ax,
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward
-template<int CDIM>
+// forward.  PIPE = true: the batch loop has no CTA barrier (same scheme as raster_bwd2_kernel): every warp waits for the
+// stage's TMA barrier, works through the batch at its own pace, counts itself off on the stage, and the last warp out
+// re-arms the barrier and fetches the batch kPipeStages ahead -- unless every warp of the tile is saturated, in which
+// case it publishes the first batch that will NOT arrive (s_stop) and all warps leave when they reach it (the tile-level
+// early exit of the barrier version).
+constexpr int kPipeStages = 3;
+
+template<int CDIM, bool PIPE = false>
 __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
     const uint32_t I, const int64_t n_isects, const float4 *__restrict__ gcull, const float4 *__restrict__ ggeom,
     const float4 *__restrict__ gcolor, const int32_t *__restrict__ order, const float *__restrict__ backgrounds,
@@ -281,10 +287,14 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
 {
     constexpr int CV = RecLayout<CDIM>::kColorVec4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Ring<CDIM> ring;
+    constexpr int KS = PIPE ? kPipeStages : kStages;
+    Ring<CDIM, kBatch, KS> ring;
     ring.carve(smem_raw);
 
     __shared__ int32_t s_surv[kWarps][32];
+    __shared__ int32_t s_cnt[kPipeStages]; // PIPE: warps that are through with the stage's current batch
+    __shared__ int32_t s_alive;            // PIPE: warps with an unsaturated pixel
+    __shared__ volatile int32_t s_stop;    // PIPE: first batch that will not be fetched
     const TileGeom tg   = decode_tile(order, tw, th);
     const unsigned tid  = threadIdx.x;
     const unsigned warp = tid >> 5, lane = tid & 31;
@@ -320,15 +330,20 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
     if(tid == 0)
     {
 #pragma unroll
-        for(int s = 0; s < kStages; ++s)
+        for(int s = 0; s < KS; ++s)
+        {
             mbar_init(ring.full(s), 1);
+            s_cnt[s < kPipeStages ? s : 0] = 0;
+        }
+        s_alive = kWarps;
+        s_stop  = 0x7fffffff;
         fence_mbar_init();
     }
     __syncthreads();
     if(tid == 0)
     {
 #pragma unroll
-        for(int s = 0; s < kStages; ++s)
+        for(int s = 0; s < KS; ++s)
             if(s < num_batches)
             {
                 const int64_t first = (int64_t)range_start + (int64_t)s * kBatch;
@@ -349,15 +364,29 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
     uint32_t done   = inside ? 0u : 1u;
     int last_b      = num_batches; // batch at which the tile-level early exit happened
 
+    bool warp_alive = true; // PIPE: this warp still has an unsaturated pixel (uniform in the warp)
     for(int b = 0; b < num_batches; ++b)
     {
-        const int stage       = b % kStages;
-        const uint32_t parity = (uint32_t)(b / kStages) & 1u;
+        const int stage       = b % KS;
+        const uint32_t parity = (uint32_t)(b / KS) & 1u;
         const int32_t first   = range_start + b * kBatch;
         const int count       = min(kBatch, (int)(range_end - first));
+        if constexpr(PIPE)
+        {
+            bool stop = false;
+            while(!mbar_try_wait(ring.full(stage), parity))
+                if(b >= s_stop)
+                {
+                    stop = true;
+                    break;
+                }
+            if(stop || b >= s_stop)
+                break;
+        }
         if(!__all_sync(0xffffffffu, done != 0u))
         {
-            mbar_wait(ring.full(stage), parity);
+            if constexpr(!PIPE)
+                mbar_wait(ring.full(stage), parity);
             const float4 *scull = ring.cull(stage);
             const float4 *saxis = ring.axis(stage);
             const float4 *sgeom = ring.geom(stage);
@@ -425,26 +454,60 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
                     break; // every pixel of this warp is saturated: drop out of the list
             }
         }
-        // everyone finished reading this stage; tile-level early exit
-        const int n_done = __syncthreads_count(done != 0u);
-        if(tid == 0)
-            mbar_wait(ring.full(stage), parity); // batch b has landed even if no warp needed it
-        if(n_done == kWarps * 32)
+        if constexpr(!PIPE)
         {
-            last_b = b;
-            break;
+            // everyone finished reading this stage; tile-level early exit
+            const int n_done = __syncthreads_count(done != 0u);
+            if(tid == 0)
+                mbar_wait(ring.full(stage), parity); // batch b has landed even if no warp needed it
+            if(n_done == kWarps * 32)
+            {
+                last_b = b;
+                break;
+            }
+            if(tid == 0 && b + KS < num_batches)
+            {
+                const int64_t nfirst = (int64_t)range_start + (int64_t)(b + KS) * kBatch;
+                const int ncount     = min(kBatch, (int)(range_end - nfirst));
+                ring.issue(stage, gcull, ggeom, gcolor, nfirst, ncount);
+            }
         }
-        if(tid == 0 && b + kStages < num_batches)
+        else
         {
-            const int64_t nfirst = (int64_t)range_start + (int64_t)(b + kStages) * kBatch;
-            const int ncount     = min(kBatch, (int)(range_end - nfirst));
-            ring.issue(stage, gcull, ggeom, gcolor, nfirst, ncount);
+            const bool all_done = __all_sync(0xffffffffu, done != 0u);
+            if(lane == 0)
+            {
+                if(warp_alive && all_done)
+                    atomicSub(&s_alive, 1);
+                __threadfence_block(); // this warp's reads of the stage are done before it is counted off
+                if(atomicAdd(&s_cnt[stage], 1) == kWarps - 1)
+                { // last warp out: the stage is free
+                    s_cnt[stage] = 0;
+                    __threadfence_block();
+                    if(b + KS < num_batches)
+                    {
+                        if(*(volatile int32_t *)&s_alive > 0)
+                        {
+                            const int64_t nfirst = (int64_t)range_start + (int64_t)(b + KS) * kBatch;
+                            const int ncount     = min(kBatch, (int)(range_end - nfirst));
+                            ring.issue(stage, gcull, ggeom, gcolor, nfirst, ncount);
+                        }
+                        else
+                            atomicMin((int32_t *)&s_stop, b + KS); // every warp is saturated: batches >= b + KS never arrive
+                    }
+                }
+            }
+            if(all_done)
+                warp_alive = false;
         }
     }
-    if(tid == 0)
-    { // never retire the CTA with bulk copies still in flight into its shared memory
-        for(int b = last_b + 1; b < num_batches && b < last_b + kStages; ++b)
-            mbar_wait(ring.full(b % kStages), (uint32_t)(b / kStages) & 1u);
+    if constexpr(!PIPE)
+    {
+        if(tid == 0)
+        { // never retire the CTA with bulk copies still in flight into its shared memory
+            for(int b = last_b + 1; b < num_batches && b < last_b + KS; ++b)
+                mbar_wait(ring.full(b % KS), (uint32_t)(b / KS) & 1u);
+        }
     }
 
     if(inside)
@@ -726,8 +789,6 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd_kernel(
 constexpr int kBwdBatch = 64; // records per ring stage (smaller than the forward's: the per-warp buffers need the room)
 constexpr int kRound    = 16; // survivors per reduction round of a warp
 constexpr int kRowF2    = 33; // row stride of the round buffer in float2 units (odd: conflict-free in both phases)
-
-constexpr int kPipeStages = 3; // ring depth of the barrier-free variant (warps may drift two batches apart)
 
 template<int CDIM, bool PIPE = false>
 struct Bwd2Smem
@@ -1130,10 +1191,25 @@ static int launch_fwd(
     if(int rc = launch_pack<CDIM>(means2d, conics, colors, opacities, offsets, flatten_ids, S, n_tiles, records, st))
         return rc;
     RecordStreams r      = carve_records(records, S, RecLayout<CDIM>::kColorVec4);
-    const size_t smem    = ring_smem_bytes<CDIM>();
     const int32_t *order = (S > 0 && n_tiles >= 2 * 148) ? r.order : nullptr;
-    GSB_CUDA_TRY(cudaFuncSetAttribute(raster_fwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    raster_fwd_kernel<CDIM><<<n_tiles, kWarps * 32, smem, st>>>(
+    // GSB200_FWD_PIPE=1 selects the barrier-free ring (CDIM <= 4); default: one CTA barrier per batch
+    static const bool pipe = [] {
+        const char *e = std::getenv("GSB200_FWD_PIPE");
+        return e && e[0] == '1';
+    }();
+    if(pipe && CDIM <= 4)
+    {
+        const size_t smem = ring_smem_bytes<CDIM, kBatch, kPipeStages>();
+        GSB_CUDA_TRY(cudaFuncSetAttribute(raster_fwd_kernel<CDIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        raster_fwd_kernel<CDIM, true><<<n_tiles, kWarps * 32, smem, st>>>(
+            (uint32_t)I, S, r.cull, r.geom, r.color, order, backgrounds, masks, W, H, tw, th, offsets, render_colors,
+            render_alphas, last_ids
+        );
+        return check_launch();
+    }
+    const size_t smem = ring_smem_bytes<CDIM>();
+    GSB_CUDA_TRY(cudaFuncSetAttribute(raster_fwd_kernel<CDIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    raster_fwd_kernel<CDIM, false><<<n_tiles, kWarps * 32, smem, st>>>(
         (uint32_t)I, S, r.cull, r.geom, r.color, order, backgrounds, masks, W, H, tw, th, offsets, render_colors,
         render_alphas, last_ids
     );
