@@ -163,10 +163,17 @@ def rasterization(
         if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
             raise ValueError("distributed=True requires an initialized default torch.distributed process group.")
         world_size, world_rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+        # the reference's distributed-mode rejections (csrc/Rendering.cpp:187-232), same wording
         if len(tuple(means.shape[:-2])) != 0:
             raise ValueError("distributed=True does not support batch dimensions")
-        if world_size > 1 and colors is not None and sh_degree is None and colors.dim() == 3:
-            raise ValueError("distributed=True: per-camera colors [C, N, D] cannot be sharded; pass [N, D] or SH")
+        if absgrad:
+            raise ValueError("distributed=True does not support absgrad=True")
+        if camera_model != "pinhole":
+            raise ValueError("distributed=True only supports camera_model='pinhole'")
+        if not global_z_order:
+            raise ValueError("distributed=True does not support global_z_order=False")
+        if colors is not None and sh_degree is None and colors.dim() == 3:
+            raise ValueError("distributed=True only supports per-Gaussian colors")
     if tile_size is None:
         tile_size = 16
     if tile_size != 16:

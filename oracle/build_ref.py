@@ -65,13 +65,13 @@ def main():
     # --full: the configuration the reference's own hot-path tests need to RUN rather than skip (tests/refsuite):
     #   GSPLAT_BUILD_3DGUT=1          two tests of the 3DGS path (test_basic.py test_isect / the eval3d twins) are gated on it
     #   GSPLAT_BUILD_CAMERA_WRAPPERS  tests/test_rasterization.py imports tests/test_cameras.py, which skips itself without them
-    #   GSPLAT_NUM_CHANNELS + 6, 32   channel counts test_basic.py renders (128 needs tile_size 4: not part of the b200 path)
+    #   GSPLAT_NUM_CHANNELS           the channel counts the reference's pytest.ini builds for its tests (1,3,4,6,8,21,23,24,32,128)
     # None of this changes the 3DGS kernels that get timed; it adds instantiations.  Objects go to obj_full/.
     full = "--full" in sys.argv
     objdir = OBJ
     if full:
         defs += ["-DGSPLAT_BUILD_3DGUT=1", "-DGSPLAT_BUILD_CAMERA_WRAPPERS=1"]
-        channels = "1,3,4,6,32"
+        channels = "1,3,4,6,8,21,23,24,32,128"  # the reference's own test configuration (pytest.ini: NUM_CHANNELS)
         cxx[-1] = f"-DGSPLAT_NUM_CHANNELS={channels}"
         nvcc[nvcc.index("-DGSPLAT_NUM_CHANNELS=" + NUM_CHANNELS.replace(",", "\\,"))] = "-DGSPLAT_NUM_CHANNELS=" + channels.replace(",", "\\,")
         sources.insert(0, os.path.join(REF, "csrc", "CameraWrappers.cu"))
