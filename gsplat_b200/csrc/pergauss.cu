@@ -1000,15 +1000,16 @@ __global__ void __launch_bounds__(kThreads) isect_count_kernel(
         counts_in_order[j] = cnt;
 }
 
-// row-order count + the two totals the host reads once: [0] = number of intersections, [1] = rows with tiles
+// row-order count + the totals the host reads once: [0] = number of intersections, [1] = rows with tiles,
+// [2] = the largest tile count of a row (picks the emit kernel)
 __global__ void __launch_bounds__(kThreads) isect_count_totals_kernel(
     int64_t total, const float *__restrict__ means2d, const int32_t *__restrict__ radii, const float *__restrict__ conics,
     const float *__restrict__ opacities, uint32_t tile_size, uint32_t tw, uint32_t th, int32_t *__restrict__ tiles_per_gauss,
     unsigned long long *__restrict__ totals
 )
 {
-    __shared__ unsigned long long s_tot[2];
-    if(threadIdx.x < 2)
+    __shared__ unsigned long long s_tot[3];
+    if(threadIdx.x < 3)
         s_tot[threadIdx.x] = 0ull;
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1028,15 +1029,19 @@ __global__ void __launch_bounds__(kThreads) isect_count_totals_kernel(
         tiles_per_gauss[i] = cnt;
     }
     const int wsum         = __reduce_add_sync(0xffffffffu, cnt);
+    const int wmax         = __reduce_max_sync(0xffffffffu, cnt);
     const unsigned nonzero = __ballot_sync(0xffffffffu, cnt > 0);
     if((threadIdx.x & 31) == 0 && nonzero != 0u)
     {
         atomicAdd(&s_tot[0], (unsigned long long)wsum);
         atomicAdd(&s_tot[1], (unsigned long long)__popc(nonzero));
+        atomicMax(&s_tot[2], (unsigned long long)wmax);
     }
     __syncthreads();
     if(threadIdx.x < 2 && s_tot[threadIdx.x] != 0ull)
         atomicAdd(&totals[threadIdx.x], s_tot[threadIdx.x]);
+    if(threadIdx.x == 2 && s_tot[2] != 0ull)
+        atomicMax(&totals[2], s_tot[2]);
 }
 
 __global__ void __launch_bounds__(kThreads) isect_emit_kernel(
@@ -1685,7 +1690,7 @@ extern "C" int gsb200_isect_count_totals(
     if(I < 0 || N < 0 || tile_size == 0 || !totals)
         return GSB200_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    GSB_CUDA_TRY(cudaMemsetAsync(totals, 0, 2 * sizeof(int64_t), st));
+    GSB_CUDA_TRY(cudaMemsetAsync(totals, 0, 3 * sizeof(int64_t), st));
     const int64_t total = I * N;
     if(total == 0)
         return GSB200_OK;
@@ -1701,7 +1706,7 @@ extern "C" int gsb200_isect_count_totals(
 }
 
 extern "C" int gsb200_isect_emit_ordered(
-    int64_t I, int64_t N, int64_t n_order, const float *means2d, const int32_t *radii, const float *depths,
+    int64_t I, int64_t N, int64_t n_order, int64_t max_tiles_hint, const float *means2d, const int32_t *radii, const float *depths,
     const float *conics, const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids, const int32_t *order,
     uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids, int32_t *flatten_ids, void *stream
 )
@@ -1715,10 +1720,19 @@ extern "C" int gsb200_isect_emit_ordered(
     const uint32_t tile_bits = bits_for_count((int64_t)tile_width * tile_height);
     if(bits_for_count(I) + tile_bits > 32)
         return GSB200_E_KEYBITS;
-    isect_emit_coop_kernel<<<grid_for(n_order, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        n_order, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
-        tile_bits, isect_ids, flatten_ids
-    );
+    // the cooperative kernel pays off when SOME gaussian covers many tiles (one lane looping over thousands of tiles is the
+    // tail of the whole launch); when even the largest row has few, the plain one-thread-per-gaussian kernel is leaner
+    // (38 vs 45 us at cfg3)
+    if(max_tiles_hint > 0 && max_tiles_hint <= 96)
+        isect_emit_kernel<<<grid_for(n_order, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+            n_order, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
+            tile_bits, isect_ids, flatten_ids
+        );
+    else
+        isect_emit_coop_kernel<<<grid_for(n_order, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+            n_order, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
+            tile_bits, isect_ids, flatten_ids
+        );
     return check_launch();
 }
 

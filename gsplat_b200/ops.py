@@ -708,7 +708,7 @@ def isect_tiles(
         # dense, sorted (the rasterization() path): count first, read both totals with ONE host sync, then order and
         # scan only the rows that have tiles (a third of the rows at BASELINE configs[2]: the culled ones never enter
         # the four radix passes of the depth order)
-        totals = torch.empty(2, device=dev, dtype=torch.int64)
+        totals = torch.empty(3, device=dev, dtype=torch.int64)
         with _Ctx(dev) as st:
             check(
                 L.gsb200_isect_count_totals(
@@ -717,7 +717,7 @@ def isect_tiles(
                 ),
                 "intersect_tile (count)",
             )
-            n_isects, n_vis = (int(v) for v in totals.tolist())  # the one host sync of the forward (reference: csrc/Intersect.cpp:259)
+            n_isects, n_vis, max_tiles = (int(v) for v in totals.tolist())  # the one host sync of the forward (reference: csrc/Intersect.cpp:259)
             isect_ids = torch.empty(n_isects, device=dev, dtype=torch.int64)
             flatten_ids = torch.empty(n_isects, device=dev, dtype=torch.int32)
             if n_isects == 0:
@@ -731,7 +731,7 @@ def isect_tiles(
             )
             check(
                 L.gsb200_isect_emit_ordered(
-                    I, N, n_vis, ptr(means2d), ptr(radii), ptr(depths), ptr(conics) if accu else None,
+                    I, N, n_vis, max_tiles, ptr(means2d), ptr(radii), ptr(depths), ptr(conics) if accu else None,
                     ptr(opacities) if accu else None, ptr(cum), None, ptr(order), tile_size, tile_width, tile_height,
                     ptr(isect_ids), ptr(flatten_ids), st,
                 ),

@@ -200,9 +200,11 @@ extern "C"
         void *stream
     );
     /* Faster pass 0 / 1 for the sorted dense layout (round 2): count first, in row order, and hand the host BOTH totals
-     * -- totals[0] = n_isects, totals[1] = rows that have tiles -- in one read; then order ONLY those rows:
+     * -- totals[0] = n_isects, totals[1] = rows that have tiles, totals[2] = largest tile count of a row -- in one read; then order ONLY those rows:
      * gsb200_isect_order_visible compacts them (stable), sorts them by (image, depth) and scans their counts in that
-     * order (order int32 [n_vis], cum_tiles int64 [n_vis]); gsb200_isect_emit_ordered emits from the n_vis ordered rows.
+     * order (order int32 [n_vis], cum_tiles int64 [n_vis]); gsb200_isect_emit_ordered emits from the n_vis ordered rows
+     * (max_tiles_hint = totals[2], the largest tile count of a row, or 0: picks the one-thread-per-gaussian or the
+     * warp-cooperative kernel).  totals is int64 [3].
      * Same intersections in the same final order as gsb200_isect_depth_order + gsb200_isect_count + gsb200_isect_emit. */
     int gsb200_isect_count_totals(
         int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *conics, const float *opacities,
@@ -216,7 +218,7 @@ extern "C"
         void *stream
     );
     int gsb200_isect_emit_ordered(
-        int64_t I, int64_t N, int64_t n_order, const float *means2d, const int32_t *radii, const float *depths,
+        int64_t I, int64_t N, int64_t n_order, int64_t max_tiles_hint, const float *means2d, const int32_t *radii, const float *depths,
         const float *conics, const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids,
         const int32_t *order, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids,
         int32_t *flatten_ids, void *stream
