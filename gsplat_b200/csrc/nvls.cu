@@ -151,7 +151,7 @@ struct RowSegs
     int n;
     int64_t vec_off[kMaxSegs]; // first float4 of the segment
     int32_t width[kMaxSegs];   // floats per row
-    uint32_t magic[kMaxSegs];  // floor(2^32 / width) + 1: n / width == __umulhi(n, magic) for n * width < 2^32
+    uint32_t magic_vpr[kMaxSegs]; // width % 4 == 0: floor(2^32 / (width / 4)) + 1 (0 for one vector per row): n / vpr by __umulhi
     int64_t n_vec[kMaxSegs];   // float4 in the segment (rows * width / 4, rounded up)
 };
 
@@ -162,17 +162,15 @@ __device__ __forceinline__ uint32_t multimem_ld_reduce_or(const uint32_t *mc)
     return v;
 }
 
-// does float4 `v` of a 32-row group (rows of `w` floats) contain a row whose bit is set?
-__device__ __forceinline__ bool vec_touched(uint32_t word, int v, uint32_t magic)
-{
-    // first / last row of the 32-row group the vector overlaps (4 v + 3 < 32 w, so r1 <= 31)
-    // magic == 0 marks width 1 (2^32 / 1 + 1 does not fit 32 bits): the row index is the float index
-    const int r0 = magic ? (int)__umulhi((uint32_t)(4 * v), magic) : 4 * v;
-    const int r1 = magic ? (int)__umulhi((uint32_t)(4 * v + 3), magic) : 4 * v + 3;
-    const uint32_t span = (r1 >= 31 ? 0xffffffffu : ((2u << r1) - 1u)) & ~((1u << r0) - 1u);
-    return (word & span) != 0u;
-}
+constexpr int kRowsUnroll = 8; // 16-byte vectors in flight per lane and round
 
+// One warp per group of 32 rows; groups are dealt round-robin over the ranks (visibility is spatially correlated with
+// the row index, contiguous halves would leave one rank with most of the touched rows) and grid-stride over the warps.
+// Inside a group the TOUCHED work is flattened -- for segments whose rows are whole vectors (quats: 1, SH: 12 per row)
+// only the vectors of touched rows, found with __fns on the ORed bitmap word; the narrow segments (means, scales,
+// opacities: 56 vectors per group together) as a whole -- so that every lane has a vector in every round: with a third of
+// the rows touched, predicating a dense walk left two thirds of the lanes idle in a latency-bound loop (measured at 2
+// ranks: 0.62 ms for 35 % of the payload, slower than the dense kernel's 0.38 ms for all of it).
 template<bool NVLS>
 __global__ void __launch_bounds__(kNvlsThreads) rows_allreduce_kernel(
     float4 *__restrict__ mc, float4 *const *__restrict__ bufs, const RowSegs segs, int64_t n_rows, int64_t bitmap_off_words,
@@ -181,13 +179,12 @@ __global__ void __launch_bounds__(kNvlsThreads) rows_allreduce_kernel(
 {
     rank_barrier<Order::Relaxed>(pads, rank, world);
     const int64_t groups = (n_rows + 31) / 32;
-    const int64_t per    = (groups + world - 1) / world;
-    const int64_t glo = (int64_t)rank * per, ghi = (glo + per < groups) ? glo + per : groups;
-    const int lane   = threadIdx.x & 31;
-    const int64_t warp0 = (int64_t)blockIdx.x * (kNvlsThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarp = (int64_t)gridDim.x * (kNvlsThreads / 32);
+    const int lane       = threadIdx.x & 31;
+    const int64_t warp0  = (int64_t)blockIdx.x * (kNvlsThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarp  = (int64_t)gridDim.x * (kNvlsThreads / 32);
+    float4 *mine         = NVLS ? nullptr : bufs[rank];
     unsigned long long moved = 0;
-    for(int64_t g = glo + warp0; g < ghi; g += nwarp)
+    for(int64_t g = (int64_t)rank + (int64_t)world * warp0; g < groups; g += (int64_t)world * nwarp)
     {
         uint32_t word;
         if constexpr(NVLS)
@@ -200,52 +197,76 @@ __global__ void __launch_bounds__(kNvlsThreads) rows_allreduce_kernel(
         }
         if(word == 0u)
             continue;
-#pragma unroll 1
-        for(int k = 0; k < segs.n; ++k)
-        {
-            const int w        = segs.width[k];
-            const uint32_t magic = segs.magic[k];
-            const int64_t base = segs.vec_off[k] + g * 8 * (int64_t)w;
-            const int64_t lim  = segs.vec_off[k] + segs.n_vec[k];
-            // four vectors in flight per lane: all loads of a round are issued before its stores
-            for(int v0 = lane; v0 < 8 * w; v0 += 32 * kNvlsUnroll)
-            {
-                float4 x[kNvlsUnroll];
-                bool on[kNvlsUnroll];
+        const int nt = __popc(word);
+        // flattened work list of this group: prefix[k] = first item of segment k
+        int prefix[kMaxSegs + 1];
+        prefix[0] = 0;
 #pragma unroll
-                for(int u = 0; u < kNvlsUnroll; ++u)
+        for(int k = 0; k < kMaxSegs; ++k)
+        {
+            int cnt = 0;
+            if(k < segs.n)
+                cnt = (segs.width[k] & 3) == 0 ? nt * (segs.width[k] >> 2) : 8 * segs.width[k];
+            prefix[k + 1] = prefix[k] + cnt;
+        }
+        const int total = prefix[kMaxSegs];
+        for(int j0 = 0; j0 < total; j0 += 32 * kRowsUnroll)
+        {
+            float4 x[kRowsUnroll];
+            int64_t addr[kRowsUnroll];
+#pragma unroll
+            for(int u = 0; u < kRowsUnroll; ++u)
+            {
+                const int j = j0 + 32 * u + lane;
+                addr[u]     = -1;
+                if(j < total)
                 {
-                    const int v     = v0 + 32 * u;
-                    const int64_t i = base + v;
-                    on[u]           = v < 8 * w && i < lim && vec_touched(word, v, magic);
-                    if(on[u])
+                    int k = 0;
+#pragma unroll
+                    for(int q = 1; q < kMaxSegs; ++q)
+                        if(q < segs.n && j >= prefix[q])
+                            k = q;
+                    const int jl = j - prefix[k];
+                    const int w  = segs.width[k];
+                    int64_t i;
+                    if((w & 3) == 0)
+                    { // whole-vector rows: the r-th touched row of the group
+                        const int vpr = w >> 2;
+                        const int r   = segs.magic_vpr[k] ? (int)__umulhi((uint32_t)jl, segs.magic_vpr[k]) : jl; // 0: one vector per row
+                        const int row = (int)__fns(word, 0, r + 1);
+                        i             = segs.vec_off[k] + (g * 32 + row) * vpr + (jl - r * vpr);
+                    }
+                    else
+                        i = segs.vec_off[k] + g * 8 * (int64_t)w + jl;
+                    if(i < segs.vec_off[k] + segs.n_vec[k])
+                        addr[u] = i;
+                }
+                if(addr[u] >= 0)
+                {
+                    if constexpr(NVLS)
+                        x[u] = multimem_ld_reduce_add(mc + addr[u]);
+                    else
                     {
-                        if constexpr(NVLS)
-                            x[u] = multimem_ld_reduce_add(mc + i);
-                        else
+                        x[u] = mine[addr[u]];
+                        for(int p = 1; p < world; ++p)
                         {
-                            x[u] = bufs[rank][i];
-                            for(int p = 1; p < world; ++p)
-                            {
-                                const float4 y = __ldcv(bufs[(rank + p) % world] + i);
-                                x[u].x += y.x, x[u].y += y.y, x[u].z += y.z, x[u].w += y.w;
-                            }
+                            const float4 y = __ldcv(bufs[(rank + p) % world] + addr[u]);
+                            x[u].x += y.x, x[u].y += y.y, x[u].z += y.z, x[u].w += y.w;
                         }
                     }
                 }
-#pragma unroll
-                for(int u = 0; u < kNvlsUnroll; ++u)
-                    if(on[u])
-                    {
-                        const int64_t i = base + v0 + 32 * u;
-                        if constexpr(NVLS)
-                            multimem_st(mc + i, x[u]);
-                        else
-                            for(int p = 0; p < world; ++p)
-                                bufs[(rank + p) % world][i] = x[u];
-                        ++moved;
-                    }
             }
+#pragma unroll
+            for(int u = 0; u < kRowsUnroll; ++u)
+                if(addr[u] >= 0)
+                {
+                    if constexpr(NVLS)
+                        multimem_st(mc + addr[u], x[u]);
+                    else
+                        for(int p = 0; p < world; ++p)
+                            bufs[(rank + p) % world][addr[u]] = x[u];
+                    ++moved;
+                }
         }
     }
     if(stats != nullptr && moved != 0)
@@ -321,7 +342,8 @@ extern "C" int gsb200_rows_allreduce_f32(
             return GSB200_E_INVALID;
         segs.vec_off[k] = seg_offsets_floats[k] / 4;
         segs.width[k]   = seg_widths[k];
-        segs.magic[k]   = seg_widths[k] == 1 ? 0u : (uint32_t)(0x100000000ULL / (uint64_t)seg_widths[k]) + 1u;
+        const int vpr    = seg_widths[k] / 4;
+        segs.magic_vpr[k] = ((seg_widths[k] & 3) != 0 || vpr <= 1) ? 0u : (uint32_t)(0x100000000ULL / (uint64_t)vpr) + 1u;
         segs.n_vec[k]   = (n_rows * seg_widths[k] + 3) / 4;
     }
     cudaStream_t st = (cudaStream_t)stream;

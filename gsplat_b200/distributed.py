@@ -139,7 +139,7 @@ class NvlsGradArena:
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.params = dict(named_params)
-        self.blocks = int(os.environ.get("GSB200_NVLS_BLOCKS", "64")) if blocks is None else int(blocks)
+        self.blocks = int(os.environ.get("GSB200_NVLS_BLOCKS", "128")) if blocks is None else int(blocks)
         if row_sparse is None:
             row_sparse = os.environ.get("GSB200_ALLREDUCE_ROWS", "1") != "0"
         dev = next(iter(self.params.values())).device
