@@ -98,7 +98,10 @@ def main():
             dist.all_reduce(moved)
             dense_vec = sum(p.numel() for p in params.values()) // 4
             frac = float(moved) / dense_vec
-            assert frac < 1.0 - 0.7**world + 0.05, f"rows-{algo} moved {frac:.3f} of the payload"
+            # whole-vector rows (quats 4 + SH 48 of the 59 floats) move only when touched by some rank (union of `world`
+            # random 30 % sets); the narrow segments (means, scales, opacities: 7 floats) move with their 32-row group
+            bound = (1.0 - 0.7**world) * 52 / 59 + 7 / 59 + 0.03
+            assert frac < bound, f"rows-{algo} moved {frac:.3f} of the payload (bound {bound:.3f})"
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
         torch.cuda.synchronize()
