@@ -184,19 +184,27 @@ __global__ void __launch_bounds__(kNvlsThreads) rows_allreduce_kernel(
     const int64_t nwarp  = (int64_t)gridDim.x * (kNvlsThreads / 32);
     float4 *mine         = NVLS ? nullptr : bufs[rank];
     unsigned long long moved = 0;
-    for(int64_t g = (int64_t)rank + (int64_t)world * warp0; g < groups; g += (int64_t)world * nwarp)
+    // the warp's groups, 32 at a time: lane l fetches the ORed bitmap word of the l-th of them (one round trip for all)
+    const int64_t gstride = (int64_t)world * nwarp;
+    for(int64_t gbase = (int64_t)rank + (int64_t)world * warp0; gbase < groups; gbase += 32 * gstride)
     {
-        uint32_t word;
-        if constexpr(NVLS)
-            word = multimem_ld_reduce_or(reinterpret_cast<const uint32_t *>(mc) + bitmap_off_words + g);
-        else
+        const int64_t myg = gbase + (int64_t)lane * gstride;
+        uint32_t myword   = 0u;
+        if(myg < groups)
         {
-            word = 0u;
-            for(int p = 0; p < world; ++p)
-                word |= __ldcv(reinterpret_cast<const uint32_t *>(bufs[p]) + bitmap_off_words + g);
+            if constexpr(NVLS)
+                myword = multimem_ld_reduce_or(reinterpret_cast<const uint32_t *>(mc) + bitmap_off_words + myg);
+            else
+                for(int p = 0; p < world; ++p)
+                    myword |= __ldcv(reinterpret_cast<const uint32_t *>(bufs[p]) + bitmap_off_words + myg);
         }
-        if(word == 0u)
-            continue;
+        uint32_t todo = __ballot_sync(0xffffffffu, myword != 0u);
+        while(todo)
+        {
+        const int gi = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t word = __shfl_sync(0xffffffffu, myword, gi);
+        const int64_t g     = gbase + (int64_t)gi * gstride;
         const int nt = __popc(word);
         // flattened work list of this group: prefix[k] = first item of segment k
         int prefix[kMaxSegs + 1];
@@ -268,6 +276,7 @@ __global__ void __launch_bounds__(kNvlsThreads) rows_allreduce_kernel(
                     ++moved;
                 }
         }
+        } // groups of this chunk
     }
     if(stats != nullptr && moved != 0)
         atomicAdd(stats, moved); // float4 actually reduced by this rank (diagnostics)
