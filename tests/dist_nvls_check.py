@@ -135,7 +135,7 @@ def main():
     def backward():
         for p in P.values():
             p.grad = None
-        rc, _, _ = gsplat_b200.rasterization(P["means"], P["quats"], P["scales"], P["opacities"], P["sh"], vm, K, W, H, sh_degree=3)
+        rc, _, _ = gsplat_b200.rasterization(P["means"], P["quats"], P["scales"], P["opacities"], P["sh"], vm, K, W, H, sh_degree=3, packed=False)
         (rc - tgt).abs().mean().backward()
 
     backward()
