@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
     __shared__ int32_t s_surv[kWarps][32];
     __shared__ int32_t s_cnt[kPipeStages]; // PIPE: warps that are through with the stage's current batch
     __shared__ int32_t s_alive;            // PIPE: warps with an unsaturated pixel
-    __shared__ volatile int32_t s_stop;    // PIPE: first batch that will not be fetched
+    __shared__ int32_t s_stop;             // PIPE: first batch that will not be fetched (read and written with atomics only)
     const TileGeom tg   = decode_tile(order, tw, th);
     const unsigned tid  = threadIdx.x;
     const unsigned warp = tid >> 5, lane = tid & 31;
@@ -373,15 +373,22 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
         const int count       = min(kBatch, (int)(range_end - first));
         if constexpr(PIPE)
         {
-            bool stop = false;
-            while(!mbar_try_wait(ring.full(stage), parity))
-                if(b >= s_stop)
+            // lane 0 waits for the batch or for the stop flag; the verdict is broadcast so that the warp leaves as one
+            int verdict = 0; // 1 = the batch has landed, 2 = it will never be fetched
+            if(lane == 0)
+            {
+                while(verdict == 0)
                 {
-                    stop = true;
-                    break;
+                    if(mbar_try_wait(ring.full(stage), parity))
+                        verdict = 1;
+                    else if(b >= atomicMin(&s_stop, 0x7fffffff)) // atomic read of the flag
+                        verdict = 2;
                 }
-            if(stop || b >= s_stop)
+            }
+            verdict = __shfl_sync(0xffffffffu, verdict, 0);
+            if(verdict == 2)
                 break;
+            mbar_wait(ring.full(stage), parity); // every lane observes the completed phase itself (returns at once)
         }
         if(!__all_sync(0xffffffffu, done != 0u))
         {
@@ -482,18 +489,18 @@ __global__ void __launch_bounds__(kWarps * 32) raster_fwd_kernel(
                 __threadfence_block(); // this warp's reads of the stage are done before it is counted off
                 if(atomicAdd(&s_cnt[stage], 1) == kWarps - 1)
                 { // last warp out: the stage is free
-                    s_cnt[stage] = 0;
+                    atomicExch(&s_cnt[stage], 0);
                     __threadfence_block();
                     if(b + KS < num_batches)
                     {
-                        if(*(volatile int32_t *)&s_alive > 0)
+                        if(atomicAdd(&s_alive, 0) > 0)
                         {
                             const int64_t nfirst = (int64_t)range_start + (int64_t)(b + KS) * kBatch;
                             const int ncount     = min(kBatch, (int)(range_end - nfirst));
                             ring.issue(stage, gcull, ggeom, gcolor, nfirst, ncount);
                         }
                         else
-                            atomicMin((int32_t *)&s_stop, b + KS); // every warp is saturated: batches >= b + KS never arrive
+                            atomicMin(&s_stop, b + KS); // every warp is saturated: batches >= b + KS never arrive
                     }
                 }
             }
@@ -1107,7 +1114,8 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
                             o = vis * v_alpha;
                     }
                     rbuf[nslots * kRowF2 + lane] = make_float2(f, o);
-                    slot_t[nslots]               = t; // every lane writes the same value: no predicate needed
+                    if(lane == 0)
+                        slot_t[nslots] = t;
                     if(++nslots == kRound)
                     {
                         materialise(kRound, scull, sgeom, sid);
@@ -1138,7 +1146,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
                 __threadfence_block(); // this warp's reads of the stage are done before it is counted off
                 if(atomicAdd(&s_done[stage], 1) == kWarps - 1)
                 { // last warp out: the stage is free -- re-arm it and fetch the batch KS ahead
-                    s_done[stage] = 0;
+                    atomicExch(&s_done[stage], 0);
                     __threadfence_block();
                     if(b + KS < num_batches)
                         ring.issue(stage, gcull, ggeom, gcolor, batch_first(b + KS), batch_count(b + KS));
