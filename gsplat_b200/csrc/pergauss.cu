@@ -1044,11 +1044,34 @@ __global__ void __launch_bounds__(kThreads) isect_count_totals_kernel(
         atomicMax(&totals[2], s_tot[2]);
 }
 
+// Key of one (gaussian, tile) intersection.  int64_t: the reference's isect id, (image | tile) << 32 | depth bits
+// (csrc/IntersectTile.cu:925-988).  uint16_t / uint32_t: the dense tile id image * n_tiles + tile alone -- the rows are
+// emitted in depth order already, so the S-sized sort only needs those bits, and moving 2 + 4 instead of 8 + 4 bytes per
+// intersection and pass halves its traffic (the 64-bit ids are rebuilt on demand: isect_ids_from_tilekeys_kernel).
+template<class KeyT>
+struct IsectKey
+{
+    uint32_t base;
+    __device__ __forceinline__ IsectKey(int64_t image, uint32_t, uint32_t, int64_t n_tiles) : base((uint32_t)(image * n_tiles)) {}
+    __device__ __forceinline__ KeyT operator()(int64_t tile) const { return (KeyT)(base + (uint32_t)tile); }
+};
+template<>
+struct IsectKey<int64_t>
+{
+    int64_t hi_db;
+    __device__ __forceinline__ IsectKey(int64_t image, uint32_t dbits, uint32_t tile_n_bits, int64_t)
+        : hi_db((image << (32 + tile_n_bits)) | (int64_t)dbits)
+    {
+    }
+    __device__ __forceinline__ int64_t operator()(int64_t tile) const { return hi_db | (tile << 32); }
+};
+
+template<class KeyT>
 __global__ void __launch_bounds__(kThreads) isect_emit_kernel(
     int64_t total, int64_t N, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
     const float *__restrict__ depths, const float *__restrict__ conics, const float *__restrict__ opacities,
     const int64_t *__restrict__ cum_tiles, const int64_t *__restrict__ image_ids, const int32_t *__restrict__ order,
-    uint32_t tile_size, uint32_t tw, uint32_t th, uint32_t tile_n_bits, int64_t *__restrict__ isect_ids,
+    uint32_t tile_size, uint32_t tw, uint32_t th, uint32_t tile_n_bits, KeyT *__restrict__ isect_ids,
     int32_t *__restrict__ flatten_ids
 )
 {
@@ -1065,10 +1088,10 @@ __global__ void __launch_bounds__(kThreads) isect_emit_kernel(
     if(accu)
         cn[0] = conics[i * 3], cn[1] = conics[i * 3 + 1], cn[2] = conics[i * 3 + 2], op = opacities[i];
     int64_t cur         = (j == 0) ? 0 : cum_tiles[j - 1];
-    const int64_t hi    = (image_ids ? image_ids[i] : (i / N)) << (32 + tile_n_bits); // packed rows carry their image id
-    const int64_t dbits = (int64_t)__float_as_uint(depths[i]);
+    // packed rows carry their image id
+    const IsectKey<KeyT> key(image_ids ? image_ids[i] : (i / N), __float_as_uint(depths[i]), tile_n_bits, (int64_t)tw * th);
     tiles_of_gaussian(m.x, m.y, r.x, r.y, accu ? cn : nullptr, accu ? &op : nullptr, tile_size, tw, th, [&](int64_t tile) {
-        isect_ids[cur]   = hi | (tile << 32) | dbits;
+        isect_ids[cur]   = key(tile);
         flatten_ids[cur] = (int32_t)i;
         ++cur;
     });
@@ -1181,11 +1204,12 @@ __device__ __forceinline__ void accu_row(const AccuGauss &g, int u, int &v0, int
         v1 = v0;
 }
 
+template<class KeyT>
 __global__ void __launch_bounds__(kThreads) isect_emit_coop_kernel(
     int64_t total, int64_t N, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
     const float *__restrict__ depths, const float *__restrict__ conics, const float *__restrict__ opacities,
     const int64_t *__restrict__ cum_tiles, const int64_t *__restrict__ image_ids, const int32_t *__restrict__ order,
-    uint32_t tile_size, uint32_t tw, uint32_t th, uint32_t tile_n_bits, int64_t *__restrict__ isect_ids,
+    uint32_t tile_size, uint32_t tw, uint32_t th, uint32_t tile_n_bits, KeyT *__restrict__ isect_ids,
     int32_t *__restrict__ flatten_ids
 )
 {
@@ -1197,7 +1221,8 @@ __global__ void __launch_bounds__(kThreads) isect_emit_coop_kernel(
     float2 m            = make_float2(0.f, 0.f);
     float cn0 = 0.f, cn1 = 0.f, cn2 = 0.f, op = 0.f;
     const bool accu = conics != nullptr && opacities != nullptr;
-    int64_t cur = 0, hi = 0, dbits = 0;
+    int64_t cur = 0, img = 0;
+    uint32_t dbits = 0;
     int cnt = 0;
     if(active)
     {
@@ -1209,16 +1234,17 @@ __global__ void __launch_bounds__(kThreads) isect_emit_coop_kernel(
                 cn0 = conics[i * 3], cn1 = conics[i * 3 + 1], cn2 = conics[i * 3 + 2], op = opacities[i];
             cur   = (j == 0) ? 0 : cum_tiles[j - 1];
             cnt   = (int)(cum_tiles[j] - cur);
-            hi    = (image_ids ? image_ids[i] : (i / N)) << (32 + tile_n_bits);
-            dbits = (int64_t)__float_as_uint(depths[i]);
+            img   = image_ids ? image_ids[i] : (i / N);
+            dbits = __float_as_uint(depths[i]);
         }
     }
     // small gaussians: the owning lane writes its few tiles
     if(cnt > 0 && cnt <= kSmallTiles)
     {
         float cn[3] = {cn0, cn1, cn2};
+        const IsectKey<KeyT> key(img, dbits, tile_n_bits, (int64_t)tw * th);
         tiles_of_gaussian(m.x, m.y, r.x, r.y, accu ? cn : nullptr, accu ? &op : nullptr, tile_size, tw, th, [&](int64_t tile) {
-            isect_ids[cur]   = hi | (tile << 32) | dbits;
+            isect_ids[cur]   = key(tile);
             flatten_ids[cur] = (int32_t)i;
             ++cur;
         });
@@ -1233,8 +1259,9 @@ __global__ void __launch_bounds__(kThreads) isect_emit_coop_kernel(
         const int brx = __shfl_sync(0xffffffffu, r.x, src), bry = __shfl_sync(0xffffffffu, r.y, src);
         const float b0 = __shfl_sync(0xffffffffu, cn0, src), b1 = __shfl_sync(0xffffffffu, cn1, src);
         const float b2 = __shfl_sync(0xffffffffu, cn2, src), bop = __shfl_sync(0xffffffffu, op, src);
-        const int64_t bcur = __shfl_sync(0xffffffffu, cur, src), bhi = __shfl_sync(0xffffffffu, hi, src);
-        const int64_t bdb = __shfl_sync(0xffffffffu, dbits, src);
+        const int64_t bcur = __shfl_sync(0xffffffffu, cur, src), bimg = __shfl_sync(0xffffffffu, img, src);
+        const uint32_t bdb = __shfl_sync(0xffffffffu, dbits, src);
+        const IsectKey<KeyT> bkey(bimg, bdb, tile_n_bits, (int64_t)tw * th);
         const int32_t bi  = (int32_t)__shfl_sync(0xffffffffu, i, src);
         const AccuGauss g = accu_setup(bmx, bmy, brx, bry, accu, b0, b1, b2, bop, tile_size, tw, th);
         if(g.empty)
@@ -1278,7 +1305,7 @@ __global__ void __launch_bounds__(kThreads) isect_emit_coop_kernel(
                     const int v        = rv0 + (k - rex);
                     const int uu       = u0 + row;
                     const int64_t tile = g.isY ? (int64_t)uu * tw + v : (int64_t)v * tw + uu;
-                    isect_ids[base + k]   = bhi | (tile << 32) | bdb;
+                    isect_ids[base + k]   = bkey(tile);
                     flatten_ids[base + k] = bi;
                 }
             }
@@ -1670,12 +1697,12 @@ extern "C" int gsb200_isect_emit(
         return !(e && e[0] == 's'); // GSB200_EMIT=serial selects the one-thread-per-gaussian kernel (measurements)
     }();
     if(coop)
-        isect_emit_coop_kernel<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        isect_emit_coop_kernel<int64_t><<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
             total, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
             tile_bits, isect_ids, flatten_ids
         );
     else
-        isect_emit_kernel<<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        isect_emit_kernel<int64_t><<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
             total, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
             tile_bits, isect_ids, flatten_ids
         );
@@ -1705,33 +1732,159 @@ extern "C" int gsb200_isect_count_totals(
     return check_launch();
 }
 
-extern "C" int gsb200_isect_emit_ordered(
+namespace gsb
+{
+template<class KeyT>
+static int emit_ordered(
     int64_t I, int64_t N, int64_t n_order, int64_t max_tiles_hint, const float *means2d, const int32_t *radii, const float *depths,
     const float *conics, const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids, const int32_t *order,
-    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids, int32_t *flatten_ids, void *stream
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, KeyT *keys, int32_t *flatten_ids, void *stream
 )
 {
     if(I < 0 || N < 0 || n_order < 0 || tile_size == 0)
         return GSB200_E_INVALID;
     if(n_order == 0)
         return GSB200_OK;
-    if(!means2d || !radii || !depths || !cum_tiles || !order || !isect_ids || !flatten_ids)
+    if(!means2d || !radii || !depths || !cum_tiles || !order || !keys || !flatten_ids)
         return GSB200_E_INVALID;
     const uint32_t tile_bits = bits_for_count((int64_t)tile_width * tile_height);
     if(bits_for_count(I) + tile_bits > 32)
+        return GSB200_E_KEYBITS;
+    if(sizeof(KeyT) < 8 && bits_for_count(I * (int64_t)tile_width * tile_height) > 8 * sizeof(KeyT))
         return GSB200_E_KEYBITS;
     // the cooperative kernel pays off when SOME gaussian covers many tiles (one lane looping over thousands of tiles is the
     // tail of the whole launch); when even the largest row has few, the plain one-thread-per-gaussian kernel is leaner
     // (38 vs 45 us at cfg3)
     if(max_tiles_hint > 0 && max_tiles_hint <= 96)
-        isect_emit_kernel<<<grid_for(n_order, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        isect_emit_kernel<KeyT><<<grid_for(n_order, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
             n_order, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
-            tile_bits, isect_ids, flatten_ids
+            tile_bits, keys, flatten_ids
         );
     else
-        isect_emit_coop_kernel<<<grid_for(n_order, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        isect_emit_coop_kernel<KeyT><<<grid_for(n_order, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
             n_order, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
-            tile_bits, isect_ids, flatten_ids
+            tile_bits, keys, flatten_ids
+        );
+    return check_launch();
+}
+
+// offsets[(image, tile)] from sorted dense tile ids (narrow keys): same contract as isect_offsets_kernel
+template<class KeyT>
+__global__ void __launch_bounds__(kThreads) isect_offsets_tilekeys_kernel(
+    int64_t n_isects, const KeyT *__restrict__ keys, int64_t total_tiles, int32_t *__restrict__ offsets
+)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(s >= n_isects)
+        return;
+    const int64_t id   = (int64_t)keys[s];
+    const int64_t prev = s > 0 ? (int64_t)keys[s - 1] : -1;
+    for(int64_t k = prev + 1; k <= id; ++k)
+        offsets[k] = (int32_t)s;
+    if(s == n_isects - 1)
+        for(int64_t k = id + 1; k < total_tiles; ++k)
+            offsets[k] = (int32_t)n_isects;
+}
+
+// the reference's 64-bit intersection ids, rebuilt from the sorted tile ids and the rows' depths
+template<class KeyT>
+__global__ void __launch_bounds__(kThreads) isect_ids_from_tilekeys_kernel(
+    int64_t n_isects, const KeyT *__restrict__ keys, const int32_t *__restrict__ flatten_ids, const float *__restrict__ depths,
+    int64_t n_tiles, uint32_t tile_n_bits, int64_t *__restrict__ isect_ids
+)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(s >= n_isects)
+        return;
+    const int64_t id = (int64_t)keys[s];
+    const int64_t image = id / n_tiles, tile = id - image * n_tiles;
+    isect_ids[s] = (((image << tile_n_bits) | tile) << 32) | (int64_t)__float_as_uint(depths[flatten_ids[s]]);
+}
+} // namespace gsb
+
+extern "C" int gsb200_isect_emit_ordered(
+    int64_t I, int64_t N, int64_t n_order, int64_t max_tiles_hint, const float *means2d, const int32_t *radii, const float *depths,
+    const float *conics, const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids, const int32_t *order,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids, int32_t *flatten_ids, void *stream
+)
+{
+    return gsb::emit_ordered<int64_t>(
+        I, N, n_order, max_tiles_hint, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width,
+        tile_height, isect_ids, flatten_ids, stream
+    );
+}
+
+// Narrow-key variant: writes the dense tile id image * n_tiles + tile as a key_bytes-wide (2 or 4) unsigned integer.
+extern "C" int gsb200_isect_emit_tilekeys(
+    int64_t I, int64_t N, int64_t n_order, int64_t max_tiles_hint, const float *means2d, const int32_t *radii, const float *depths,
+    const float *conics, const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids, const int32_t *order,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int key_bytes, void *tile_keys, int32_t *flatten_ids, void *stream
+)
+{
+    if(key_bytes == 2)
+        return gsb::emit_ordered<uint16_t>(
+            I, N, n_order, max_tiles_hint, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size,
+            tile_width, tile_height, static_cast<uint16_t *>(tile_keys), flatten_ids, stream
+        );
+    if(key_bytes == 4)
+        return gsb::emit_ordered<uint32_t>(
+            I, N, n_order, max_tiles_hint, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size,
+            tile_width, tile_height, static_cast<uint32_t *>(tile_keys), flatten_ids, stream
+        );
+    return GSB200_E_INVALID;
+}
+
+extern "C" int gsb200_isect_offsets_tilekeys(
+    int64_t n_isects, int key_bytes, const void *tile_keys, int64_t I, uint32_t tile_width, uint32_t tile_height, int32_t *offsets,
+    void *stream
+)
+{
+    if(n_isects < 0 || I < 0 || (key_bytes != 2 && key_bytes != 4))
+        return GSB200_E_INVALID;
+    const int64_t total = I * (int64_t)tile_width * tile_height;
+    if(total == 0)
+        return GSB200_OK;
+    if(!offsets)
+        return GSB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if(n_isects == 0)
+    {
+        GSB_CUDA_TRY(cudaMemsetAsync(offsets, 0, sizeof(int32_t) * (size_t)total, st));
+        return GSB200_OK;
+    }
+    if(!tile_keys)
+        return GSB200_E_INVALID;
+    if(key_bytes == 2)
+        isect_offsets_tilekeys_kernel<uint16_t><<<grid_for(n_isects, kThreads), kThreads, 0, st>>>(
+            n_isects, static_cast<const uint16_t *>(tile_keys), total, offsets
+        );
+    else
+        isect_offsets_tilekeys_kernel<uint32_t><<<grid_for(n_isects, kThreads), kThreads, 0, st>>>(
+            n_isects, static_cast<const uint32_t *>(tile_keys), total, offsets
+        );
+    return check_launch();
+}
+
+extern "C" int gsb200_isect_ids_from_tilekeys(
+    int64_t n_isects, int key_bytes, const void *tile_keys, const int32_t *flatten_ids, const float *depths, int64_t I,
+    uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids, void *stream
+)
+{
+    if(n_isects < 0 || I < 0 || (key_bytes != 2 && key_bytes != 4))
+        return GSB200_E_INVALID;
+    if(n_isects == 0)
+        return GSB200_OK;
+    if(!tile_keys || !flatten_ids || !depths || !isect_ids)
+        return GSB200_E_INVALID;
+    const int64_t n_tiles = (int64_t)tile_width * tile_height;
+    cudaStream_t st       = (cudaStream_t)stream;
+    if(key_bytes == 2)
+        isect_ids_from_tilekeys_kernel<uint16_t><<<grid_for(n_isects, kThreads), kThreads, 0, st>>>(
+            n_isects, static_cast<const uint16_t *>(tile_keys), flatten_ids, depths, n_tiles, bits_for_count(n_tiles), isect_ids
+        );
+    else
+        isect_ids_from_tilekeys_kernel<uint32_t><<<grid_for(n_isects, kThreads), kThreads, 0, st>>>(
+            n_isects, static_cast<const uint32_t *>(tile_keys), flatten_ids, depths, n_tiles, bits_for_count(n_tiles), isect_ids
         );
     return check_launch();
 }

@@ -71,6 +71,64 @@ extern "C" int gsb200_sort_pairs(
     return GSB200_OK;
 }
 
+// Narrow variant for the (image, tile)-only sort of the depth-ordered intersections: 2- or 4-byte dense tile ids
+// as keys, the row index as value -- 6 (8) instead of 12 bytes per intersection and direction in each radix pass.
+namespace gsb
+{
+template<class KeyT>
+static int sort_tile_pairs(
+    int64_t n, int end_bit, const void *keys_in, const int32_t *vals_in, void *keys_out, int32_t *vals_out, void *workspace,
+    size_t workspace_bytes, cudaStream_t st
+)
+{
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(
+        (void *)nullptr, need, static_cast<const KeyT *>(keys_in), static_cast<KeyT *>(keys_out), vals_in, vals_out, n, 0, end_bit, st
+    );
+    if(need > workspace_bytes)
+        return GSB200_E_WORKSPACE;
+    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(
+        workspace, need, static_cast<const KeyT *>(keys_in), static_cast<KeyT *>(keys_out), vals_in, vals_out, n, 0, end_bit, st
+    ));
+    return GSB200_OK;
+}
+} // namespace gsb
+
+extern "C" size_t gsb200_sort_tile_pairs_workspace_bytes(int64_t n_isects, int key_bytes, int end_bit)
+{
+    if(n_isects <= 0)
+        return 0;
+    size_t bytes = 0;
+    if(key_bytes == 2)
+        cub::DeviceRadixSort::SortPairs(
+            (void *)nullptr, bytes, (const uint16_t *)nullptr, (uint16_t *)nullptr, (const int32_t *)nullptr, (int32_t *)nullptr,
+            n_isects, 0, end_bit
+        );
+    else
+        cub::DeviceRadixSort::SortPairs(
+            (void *)nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int32_t *)nullptr, (int32_t *)nullptr,
+            n_isects, 0, end_bit
+        );
+    return bytes + 256;
+}
+
+extern "C" int gsb200_sort_tile_pairs(
+    int64_t n_isects, int key_bytes, int end_bit, const void *keys_in, const int32_t *vals_in, void *keys_out, int32_t *vals_out,
+    void *workspace, size_t workspace_bytes, void *stream
+)
+{
+    if(n_isects < 0 || (key_bytes != 2 && key_bytes != 4) || end_bit < 0 || end_bit > 8 * key_bytes)
+        return GSB200_E_INVALID;
+    if(n_isects == 0)
+        return GSB200_OK;
+    if(!keys_in || !vals_in || !keys_out || !vals_out || !workspace)
+        return GSB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    if(key_bytes == 2)
+        return gsb::sort_tile_pairs<uint16_t>(n_isects, end_bit, keys_in, vals_in, keys_out, vals_out, workspace, workspace_bytes, st);
+    return gsb::sort_tile_pairs<uint32_t>(n_isects, end_bit, keys_in, vals_in, keys_out, vals_out, workspace, workspace_bytes, st);
+}
+
 // ---- depth order of the projected gaussians (pre-pass of the tile intersection)
 // The reference sorts all S intersections on (image, tile, depth) = 45+ key bits.  Sorting the rows ONCE by
 // (image, depth) and emitting the intersections in that order leaves only the (image, tile) bits for the

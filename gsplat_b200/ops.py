@@ -794,6 +794,132 @@ def isect_tiles(
     return tiles_per_gauss, isect_ids, flatten_ids
 
 
+_MEASURE_NO_SYNC = __import__("os").environ.get("GSB200_MEASURE_NO_SYNC", "0") == "1"
+_last_totals = {}
+
+
+class SortedIntersections:
+    """What the compositing needs from the tile intersection, from the narrow-key pipeline: ``tiles_per_gauss``,
+    ``flatten_ids`` (sorted by (image, tile, depth)), ``isect_offsets`` [I, th, tw].  The reference's sorted int64
+    ``isect_ids`` are rebuilt from the sorted tile ids and the depths only when asked for (``isect_ids()``)."""
+
+    __slots__ = ("tiles_per_gauss", "flatten_ids", "isect_offsets", "_keys", "_key_bytes", "_depths", "_geom", "_ids")
+
+    def __init__(self, tiles_per_gauss, flatten_ids, isect_offsets, keys, key_bytes, depths, geom):
+        self.tiles_per_gauss, self.flatten_ids, self.isect_offsets = tiles_per_gauss, flatten_ids, isect_offsets
+        self._keys, self._key_bytes, self._depths, self._geom, self._ids = keys, key_bytes, depths, geom, None
+
+    def isect_ids(self) -> Tensor:
+        if self._ids is None:
+            I, tw, th = self._geom
+            n = self.flatten_ids.shape[0]
+            ids = torch.empty(n, device=self.flatten_ids.device, dtype=torch.int64)
+            if n > 0:
+                with _Ctx(ids.device) as st:
+                    check(
+                        lib().gsb200_isect_ids_from_tilekeys(
+                            n, self._key_bytes, ptr(self._keys), ptr(self.flatten_ids), ptr(self._depths), I, tw, th, ptr(ids), st,
+                        ),
+                        "intersect_tile (ids)",
+                    )
+            self._ids = ids
+        return self._ids
+
+
+@torch.no_grad()
+def isect_tiles_sorted(
+    means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
+    conics: Optional[Tensor] = None, opacities: Optional[Tensor] = None,
+) -> SortedIntersections:
+    """Dense-layout tile intersection + offsets for rasterization(): same intersections in the same order as
+    ``isect_tiles(sort=True)`` + ``isect_offset_encode`` (reference: csrc/Intersect.cpp:203-326, 330-382), with the
+    S-sized sort done on 2- or 4-byte dense tile ids instead of the 8-byte (image | tile | depth) ids."""
+    dev = require_cuda(means2d, radii, depths)
+    means2d, depths = f32c(means2d, "means2d"), f32c(depths, "depths")
+    conics, opacities = f32c(conics, "conics"), f32c(opacities, "opacities")
+    if radii.dtype != torch.int32:
+        raise TypeError("radii must be int32")
+    radii = radii.contiguous()
+    image_dims = tuple(means2d.shape[:-2])
+    I, N = _prod(image_dims), means2d.shape[-2]
+    L = lib()
+    n_tiles = tile_width * tile_height
+    image_bits, tile_bits = _cabi.bits_for_count(I), _cabi.bits_for_count(n_tiles)
+    if image_bits + tile_bits > 32:
+        raise RuntimeError(
+            f"intersect_tile: (image, tile) id packing needs {image_bits + tile_bits} bits but only 32 are "
+            f"available (I={I}, n_tiles={n_tiles})."
+        )
+    key_bits = _cabi.bits_for_count(I * n_tiles)
+    key_bytes = 2 if key_bits <= 16 else 4
+    key_dtype = torch.int16 if key_bytes == 2 else torch.int32  # raw storage; the kernels read them unsigned
+    total = I * N
+    tiles_per_gauss = torch.empty(image_dims + (N,), device=dev, dtype=torch.int32)
+    offsets = torch.empty((I, tile_height, tile_width), device=dev, dtype=torch.int32)
+    geom = (I, tile_width, tile_height)
+    accu = conics is not None and opacities is not None
+
+    def empty():
+        offsets.zero_()
+        return SortedIntersections(
+            tiles_per_gauss.zero_(), torch.empty(0, device=dev, dtype=torch.int32), offsets,
+            torch.empty(0, device=dev, dtype=key_dtype), key_bytes, depths, geom,
+        )
+
+    if total == 0:
+        return empty()
+    totals = torch.empty(3, device=dev, dtype=torch.int64)
+    with _Ctx(dev) as st:
+        check(
+            L.gsb200_isect_count_totals(
+                I, N, ptr(means2d), ptr(radii), ptr(conics) if accu else None, ptr(opacities) if accu else None, tile_size,
+                tile_width, tile_height, ptr(tiles_per_gauss), ptr(totals), st,
+            ),
+            "intersect_tile (count)",
+        )
+        if _MEASURE_NO_SYNC and (I, N, tile_width, tile_height) in _last_totals:
+            # measurement knob only (GSB200_MEASURE_NO_SYNC=1, static scene): reuse the previous call's totals to see what
+            # the host read below costs in a steady-state step; never set outside bench A/B runs
+            n_isects, n_vis, max_tiles = _last_totals[(I, N, tile_width, tile_height)]
+        else:
+            n_isects, n_vis, max_tiles = (int(v) for v in totals.tolist())  # the one host sync of the forward (reference: csrc/Intersect.cpp:259)
+            if _MEASURE_NO_SYNC:
+                _last_totals[(I, N, tile_width, tile_height)] = (n_isects, n_vis, max_tiles)
+        if n_isects == 0:
+            return empty()
+        keys = torch.empty(n_isects, device=dev, dtype=key_dtype)
+        flatten_ids = torch.empty(n_isects, device=dev, dtype=torch.int32)
+        order = torch.empty(n_vis, device=dev, dtype=torch.int32)
+        cum = torch.empty(n_vis, device=dev, dtype=torch.int64)
+        ws = _scratch_buffer(dev, "vorder", L.gsb200_isect_order_visible_workspace_bytes(I, total, n_vis))
+        check(
+            L.gsb200_isect_order_visible(I, N, n_vis, ptr(tiles_per_gauss), ptr(depths), None, ptr(order), ptr(cum), ptr(ws), ws.numel(), st),
+            "intersect_tile (order)",
+        )
+        check(
+            L.gsb200_isect_emit_tilekeys(
+                I, N, n_vis, max_tiles, ptr(means2d), ptr(radii), ptr(depths), ptr(conics) if accu else None,
+                ptr(opacities) if accu else None, ptr(cum), None, ptr(order), tile_size, tile_width, tile_height, key_bytes,
+                ptr(keys), ptr(flatten_ids), st,
+            ),
+            "intersect_tile (emit)",
+        )
+        keys_out, vals_out = torch.empty_like(keys), torch.empty_like(flatten_ids)
+        end_bit = max(key_bits, 1)
+        ws = _scratch_buffer(dev, "sort", L.gsb200_sort_tile_pairs_workspace_bytes(n_isects, key_bytes, end_bit))
+        check(
+            L.gsb200_sort_tile_pairs(
+                n_isects, key_bytes, end_bit, ptr(keys), ptr(flatten_ids), ptr(keys_out), ptr(vals_out), ptr(ws), ws.numel(), st,
+            ),
+            "intersect_tile (sort)",
+        )
+        check(
+            L.gsb200_isect_offsets_tilekeys(n_isects, key_bytes, ptr(keys_out), I, tile_width, tile_height, ptr(offsets), st),
+            "intersect_offset",
+        )
+    return SortedIntersections(tiles_per_gauss, vals_out, offsets, keys_out, key_bytes, depths, geom)
+
+
 @torch.no_grad()
 def isect_offset_encode(isect_ids: Tensor, n_images: int, tile_width: int, tile_height: int) -> Tensor:
     """Sorted intersection ids -> per-(image, tile) start offsets, int32 [n_images, tile_height, tile_width]."""

@@ -24,6 +24,7 @@ from .ops import (
     fused_project_sh,
     isect_offset_encode,
     isect_tiles,
+    isect_tiles_sorted,
     rasterize_to_pixels,
     spherical_harmonics,
     spherical_harmonics_rows,
@@ -35,6 +36,61 @@ _HIT_DISTANCE_MODES = {"d", "Ed", "RGB-d", "RGB-Ed"}
 _DEPTH_MODES = {"D", "ED", "RGB+D", "RGB+ED"}
 _EXPECTED_MODES = {"Ed", "ED", "RGB-Ed", "RGB+ED"}
 _ALL_MODES = _COLOR_MODES | _HIT_DISTANCE_MODES | _DEPTH_MODES
+
+
+# GSB200_ISECT_WIDE=1 keeps the 64-bit (image | tile | depth) keys through the S-sized sort (round-1 pipeline; A/B runs)
+_ISECT_WIDE = os.environ.get("GSB200_ISECT_WIDE", "0") == "1"
+
+
+class _Lazy:
+    """A meta value that is only computed when somebody reads it."""
+
+    __slots__ = ("fn",)
+
+    def __init__(self, fn):
+        self.fn = fn
+
+
+class _Meta(dict):
+    """The meta dict of rasterization(); ``_Lazy`` values are computed on first access and then stored.  Every read path
+    resolves them (the Python-level ``__iter__`` also keeps ``dict(meta)`` / ``{**meta}`` off CPython's raw-entry fast path)."""
+
+    def _resolve(self, key):
+        v = dict.__getitem__(self, key)
+        if isinstance(v, _Lazy):
+            v = v.fn()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def _resolve_all(self):
+        for k in list(dict.keys(self)):
+            self._resolve(k)
+
+    def __getitem__(self, key):
+        return self._resolve(key)
+
+    def get(self, key, default=None):
+        return self._resolve(key) if dict.__contains__(self, key) else default
+
+    def __iter__(self):
+        return dict.__iter__(self)
+
+    def items(self):
+        self._resolve_all()
+        return dict.items(self)
+
+    def values(self):
+        self._resolve_all()
+        return dict.values(self)
+
+    def copy(self):
+        self._resolve_all()
+        return dict(dict.items(self))
+
+    def pop(self, key, *default):
+        if dict.__contains__(self, key):
+            self._resolve(key)
+        return dict.pop(self, key, *default)
 
 
 def _unsupported(name: str, why: str = "out of scope for the gsplat_b200 hot path (SURVEY.md section 8)"):
@@ -315,17 +371,19 @@ def rasterization(
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
     # reference-shaped op sequence: (depth order,) count, emit, radix sort on the (image, tile) bits, offsets
-    if native_packed:
+    if native_packed or _ISECT_WIDE:
         tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(
-            means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, segmented=segmented, packed=True,
-            n_images=I, image_ids=batch_ids * C + camera_ids, gaussian_ids=gaussian_ids, conics=conics, opacities=opac,
+            means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, segmented=segmented, packed=native_packed,
+            n_images=I, image_ids=batch_ids * C + camera_ids if native_packed else None,
+            gaussian_ids=gaussian_ids if native_packed else None, conics=conics, opacities=opac,
         )
+        isect_offsets = isect_offset_encode(isect_ids, I, tile_width, tile_height)
     else:
-        tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(
-            means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, segmented=segmented, packed=False,
-            n_images=I, conics=conics, opacities=opac,
-        )
-    isect_offsets = isect_offset_encode(isect_ids, I, tile_width, tile_height)
+        # dense rows: the S-sized sort runs on 2- / 4-byte tile ids; meta["isect_ids"] (the reference's 64-bit ids) is
+        # rebuilt from them on first access
+        hits = isect_tiles_sorted(means2d, radii, depths, tile_size, tile_width, tile_height, conics=conics, opacities=opac)
+        tiles_per_gauss, flatten_ids, isect_offsets = hits.tiles_per_gauss, hits.flatten_ids, hits.isect_offsets
+        isect_ids = _Lazy(hits.isect_ids)
     isect_offsets = isect_offsets.reshape(batch_dims + (C, tile_height, tile_width))
 
     # ---- assemble channels: [colour | depth]
@@ -362,7 +420,7 @@ def rasterization(
         depth = render_colors[..., -1:] / render_alphas.clamp(min=1e-10)
         render_colors = torch.cat([render_colors[..., :-1], depth], dim=-1)
 
-    meta = {
+    meta = _Meta({
         "batch_ids": batch_ids,
         "camera_ids": camera_ids,
         "gaussian_ids": gaussian_ids,
@@ -382,5 +440,5 @@ def rasterization(
         "tile_size": tile_size,
         "n_batches": B,
         "n_cameras": C,
-    }
+    })
     return render_colors, render_alphas, meta

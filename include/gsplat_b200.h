@@ -223,6 +223,31 @@ extern "C"
         const int32_t *order, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids,
         int32_t *flatten_ids, void *stream
     );
+    /* Narrow-key variant of the same pipeline (round 2): the rows are emitted in depth order, so the S-sized sort only
+     * needs the dense tile id image * n_tiles + tile.  gsb200_isect_emit_tilekeys writes that id as a key_bytes-wide
+     * (2 when I * n_tiles <= 65536, else 4) unsigned integer next to flatten_ids; gsb200_sort_tile_pairs sorts the pairs
+     * (stable, key bits [0, end_bit)), gsb200_isect_offsets_tilekeys derives offsets int32 [I, th, tw] from the sorted
+     * keys, and gsb200_isect_ids_from_tilekeys rebuilds the reference's sorted int64 isect_ids
+     * ((image << tile_bits | tile) << 32 | depth bits; depths is indexed by flatten_ids) for callers that ask for them. */
+    int gsb200_isect_emit_tilekeys(
+        int64_t I, int64_t N, int64_t n_order, int64_t max_tiles_hint, const float *means2d, const int32_t *radii, const float *depths,
+        const float *conics, const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids,
+        const int32_t *order, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int key_bytes, void *tile_keys,
+        int32_t *flatten_ids, void *stream
+    );
+    size_t gsb200_sort_tile_pairs_workspace_bytes(int64_t n_isects, int key_bytes, int end_bit);
+    int gsb200_sort_tile_pairs(
+        int64_t n_isects, int key_bytes, int end_bit, const void *keys_in, const int32_t *vals_in, void *keys_out,
+        int32_t *vals_out, void *workspace, size_t workspace_bytes, void *stream
+    );
+    int gsb200_isect_offsets_tilekeys(
+        int64_t n_isects, int key_bytes, const void *tile_keys, int64_t I, uint32_t tile_width, uint32_t tile_height,
+        int32_t *offsets, void *stream
+    );
+    int gsb200_isect_ids_from_tilekeys(
+        int64_t n_isects, int key_bytes, const void *tile_keys, const int32_t *flatten_ids, const float *depths, int64_t I,
+        uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids, void *stream
+    );
     /* Stable radix sort of (isect_ids, flatten_ids) on key bits [begin_bit, end_bit)
      * (cub::DeviceRadixSort::SortPairs, csrc/IntersectTile.cu:1078-1121); begin_bit = 32 after pass 0. */
     size_t gsb200_sort_workspace_bytes(int64_t n_isects, int begin_bit, int end_bit);

@@ -339,6 +339,40 @@ def test_isect_large_gaussians_cooperative_emit(gs, accu):
         assert np.array_equal(_n(r[2]), o[2]), f"flatten_ids (sort={sort})"
 
 
+@pytest.mark.parametrize("big_gaussians", [False, True])
+def test_isect_narrow_keys_match_wide_pipeline(gs, big_gaussians):
+    """rasterization()'s narrow-key pipeline (2- / 4-byte dense tile ids through the S-sized sort, int64 ids rebuilt on
+    demand) must give bit for bit what isect_tiles(sort=True) + isect_offset_encode -- and the oracle -- give."""
+    from gsplat_b200.ops import isect_tiles_sorted
+
+    sc = scene.make_scene(n_max=30000)
+    if big_gaussians:
+        sc["scales"] = sc["scales"] * 6.0
+    W, H = 640, 360
+    Ks = scene.rescale_K(sc["Ks"], sc["width"], sc["height"], W, H)
+    radii, m2, dep, con, _ = _project_scene(sc, W, H, Ks, C=3)
+    op = np.ascontiguousarray(np.broadcast_to(sc["opacities"][None], dep.shape))
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    o = gso.isect_tiles(m2, radii, dep, 16, tw, th, True, con, op)
+    hits = isect_tiles_sorted(_t(m2), _t(radii), _t(dep), 16, tw, th, conics=_t(con), opacities=_t(op))
+    assert hits._key_bytes == 2 and o[1].shape[0] > 20000
+    assert np.array_equal(_n(hits.tiles_per_gauss), o[0])
+    assert np.array_equal(_n(hits.flatten_ids), o[2])
+    assert np.array_equal(_n(hits.isect_ids()), o[1])
+    assert np.array_equal(_n(hits.isect_offsets), gso.isect_offset_encode(o[1], 3, tw, th))
+    # 4-byte keys: more than 65536 (image, tile) cells -- checked against the wide pipeline of this library
+    tw4, th4 = 300, 120  # a 4800 x 1920 canvas, 36000 tiles x 3 images
+    m2b = m2 * np.float32(7.5)
+    r = gs.isect_tiles(_t(m2b), _t(radii), _t(dep), 16, tw4, th4, conics=_t(con), opacities=_t(op))
+    hits = isect_tiles_sorted(_t(m2b), _t(radii), _t(dep), 16, tw4, th4, conics=_t(con), opacities=_t(op))
+    assert hits._key_bytes == 4 and r[1].numel() > 20000
+    assert torch.equal(hits.tiles_per_gauss, r[0]) and torch.equal(hits.isect_ids(), r[1]) and torch.equal(hits.flatten_ids, r[2])
+    assert torch.equal(hits.isect_offsets, gs.isect_offset_encode(r[1], 3, tw4, th4))
+    # nothing visible
+    z = isect_tiles_sorted(_t(np.zeros((1, 4, 2), np.float32)), _t(np.zeros((1, 4, 2), np.int32)), _t(np.ones((1, 4), np.float32)), 16, 3, 2)
+    assert z.flatten_ids.numel() == 0 and z.isect_ids().numel() == 0 and (z.isect_offsets == 0).all() and (z.tiles_per_gauss == 0).all()
+
+
 def test_isect_sorted_equals_stable_sort_of_unsorted(gs):
     """The two-level sort (rows by depth, then intersections by (image, tile) bits only) must give exactly what
     one stable sort of the reference's unsorted emission gives (csrc/Intersect.cpp:283-326)."""

@@ -1,9 +1,6 @@
-# round 2, job 9 (8 GPUs): all-reduce kernels vs NCCL, DP bench with checks -- the SCALE configuration
-export NCCL_DEBUG=WARN GSB200_CHECK_FAST=1
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29611 tests/dist_nvls_check.py > gpurun_out/r02_nvls_check_n8.log 2>&1
-grep -n "nvls check ok\|AssertionError" gpurun_out/r02_nvls_check_n8.log | cut -c1-200 | tail -8
-unset NCCL_DEBUG
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r02_v3_bench_n8.json 2> gpurun_out/r02_v3_bench_n8.err
+# round 2, job 9 (8 GPUs): DP bench with checks -- the SCALE configuration
+# (the all-reduce kernels are checked against NCCL inside bench.py: dp.checks)
+timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r02_v3_bench_n8.json 2> gpurun_out/r02_v3_bench_n8.err
 python - <<PY
 import json
 d=json.loads(open("gpurun_out/r02_v3_bench_n8.json").read().strip().splitlines()[-1])
