@@ -27,7 +27,7 @@ UNITS = {
     "nvls.cu": [],
     "loss.cu": [],
 }
-HEADERS = ["common.cuh", "gaussmath.cuh", os.path.join("..", "..", "include", "gsplat_b200.h")]
+HEADERS = ["common.cuh", "gaussmath.cuh", "rowrec.cuh", os.path.join("..", "..", "include", "gsplat_b200.h")]
 
 
 def _nvcc() -> str:

@@ -8,6 +8,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "gaussmath.cuh"
+#include "rowrec.cuh"
 
 namespace gsb
 {
@@ -474,19 +475,39 @@ __global__ void __launch_bounds__(kThreads) sh_rows_bwd_kernel(
 // ------------------------------------------------------------------ fused projection + conic + SH -> RGB
 // One thread per (camera, gaussian).  SH coefficients of a visible gaussian are fetched with 128-bit
 // loads (48 floats = 12 x float4 when K = 16); culled gaussians never touch them.
-template<int DEG>
-__global__ void __launch_bounds__(kThreads) project_sh_fwd_kernel(
+template<class F>
+__device__ __forceinline__ int tiles_of_gaussian(
+    float mx, float my, int rx, int ry, const float *conic, const float *opacity, uint32_t tile_size, uint32_t tw,
+    uint32_t th, F &&f
+); // defined with the tile intersection kernels below
+
+// ROWS: the epilogue also produces what the next two stages would otherwise recompute per row / per intersection --
+// the row's tile count and the three totals of gsb200_isect_count_totals (same device function as the emit pass, so the
+// counts agree bit for bit), and the 64-byte compositing row record {cull | axis | geom | rgb0} of rowrec.cuh, which
+// turns the pack pass into a pure gather.  Only valid when the compositing opacity is the input opacity (no
+// antialiasing compensation) -- the host wrapper checks that.
+template<int DEG, bool ROWS>
+__global__ void __launch_bounds__(kThreads, 4) project_sh_fwd_kernel(
     int64_t C, int64_t N, int64_t K, const float *__restrict__ means, const float *__restrict__ quats,
     const float *__restrict__ scales, const float *__restrict__ opacities, const float *__restrict__ sh,
     const float *__restrict__ viewmats, const float *__restrict__ Ks, uint32_t W, uint32_t H, float eps2d,
     float near_plane, float far_plane, float radius_clip, int32_t *__restrict__ radii, float *__restrict__ means2d,
     float *__restrict__ depths, float *__restrict__ conics, float *__restrict__ compensations,
-    float *__restrict__ colors
+    float *__restrict__ colors, uint32_t tile_size, uint32_t tile_w, uint32_t tile_h, float4 *__restrict__ rows,
+    int32_t *__restrict__ tiles_per_gauss, unsigned long long *__restrict__ totals
 )
 {
+    __shared__ unsigned long long s_tot[3];
+    if constexpr(ROWS)
+    {
+        if(threadIdx.x < 3)
+            s_tot[threadIdx.x] = 0ull;
+        __syncthreads();
+    }
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if(idx >= C * N)
-        return;
+    int cnt           = 0;
+    if(idx < C * N)
+    {
     const int64_t c = idx / N, n = idx % N;
     const float *vm = viewmats + c * 16;
     const Cam cam   = load_cam(vm, Ks + c * 9);
@@ -544,11 +565,47 @@ __global__ void __launch_bounds__(kThreads) project_sh_fwd_kernel(
         }
     }
     colors[idx * 3] = rgb[0], colors[idx * 3 + 1] = rgb[1], colors[idx * 3 + 2] = rgb[2];
+    if constexpr(ROWS)
+    {
+        if(p.rx > 0 && p.ry > 0)
+        {
+            float cn[3] = {p.ca, p.cb, p.cc};
+            cnt         = tiles_of_gaussian(p.mx, p.my, p.rx, p.ry, cn, &op, tile_size, tile_w, tile_h, [](int64_t) {});
+            float4 rc, ra, rg;
+            row_record(p.mx, p.my, p.ca, p.cb, p.cc, op, rc, ra, rg);
+            rows[idx * 4]     = rc;
+            rows[idx * 4 + 1] = ra;
+            rows[idx * 4 + 2] = rg;
+            rows[idx * 4 + 3] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+        }
+        tiles_per_gauss[idx] = cnt;
+    }
+    }
+    if constexpr(ROWS)
+    { // the three totals, as isect_count_totals_kernel forms them
+        const int wsum         = __reduce_add_sync(0xffffffffu, cnt);
+        const int wmax         = __reduce_max_sync(0xffffffffu, cnt);
+        const unsigned nonzero = __ballot_sync(0xffffffffu, cnt > 0);
+        if((threadIdx.x & 31) == 0 && nonzero != 0u)
+        {
+            atomicAdd(&s_tot[0], (unsigned long long)wsum);
+            atomicAdd(&s_tot[1], (unsigned long long)__popc(nonzero));
+            atomicMax(&s_tot[2], (unsigned long long)wmax);
+        }
+        __syncthreads();
+        if(threadIdx.x < 2 && s_tot[threadIdx.x] != 0ull)
+            atomicAdd(&totals[threadIdx.x], s_tot[threadIdx.x]);
+        if(threadIdx.x == 2 && s_tot[2] != 0ull)
+            atomicMax(&totals[2], s_tot[2]);
+    }
 }
 
 // One thread per gaussian, looping over cameras: v_means / v_quats / v_scales / v_sh written once.
-template<int DEG>
-__global__ void __launch_bounds__(kThreads, 2) project_sh_bwd_kernel(
+// ONE_CAM (C == 1: every rank of the view-parallel trainer, any batch-size-1 step): the camera loop is gone at compile
+// time, so the 48 SH accumulators die as soon as they are stored -- 80 registers with 36 bytes of spills instead of 128
+// with 164, three CTAs per SM instead of two.
+template<int DEG, bool ONE_CAM>
+__global__ void __launch_bounds__(kThreads, ONE_CAM ? 3 : 2) project_sh_bwd_kernel(
     int64_t C, int64_t N, int64_t K, const float *__restrict__ means, const float *__restrict__ quats,
     const float *__restrict__ scales, const float *__restrict__ sh, const float *__restrict__ viewmats,
     const float *__restrict__ Ks, uint32_t W, uint32_t H, float eps2d, const int32_t *__restrict__ radii,
@@ -566,7 +623,7 @@ __global__ void __launch_bounds__(kThreads, 2) project_sh_bwd_kernel(
     // warp, coalesced (32 consecutive rows = one contiguous block), and their parameters are never loaded.
     bool seen = false;
     if(n < N)
-        for(int64_t c = 0; c < C; ++c)
+        for(int64_t c = 0; c < (ONE_CAM ? (int64_t)1 : C); ++c)
             seen |= radii[(c * N + n) * 2] > 0 && radii[(c * N + n) * 2 + 1] > 0;
     if(seen)
     {
@@ -585,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, 2) project_sh_bwd_kernel(
         for(int k = 0; k < NB * 3; ++k)
             acc[k] = 0.f;
         const float *cf = sh + n * K * 3;
-        for(int64_t c = 0; c < C; ++c)
+        for(int64_t c = 0; c < (ONE_CAM ? (int64_t)1 : C); ++c)
         {
             const int64_t idx = c * N + n;
             if(!(radii[idx * 2] > 0 && radii[idx * 2 + 1] > 0))
@@ -1594,9 +1651,46 @@ extern "C" int gsb200_project_sh_fwd(
     cudaStream_t st = (cudaStream_t)stream;
     float *comp     = calc_compensations ? compensations : nullptr;
 #define CALL(d)                                                                                                   \
-    project_sh_fwd_kernel<d><<<grid_for(C * N, kThreads), kThreads, 0, st>>>(                                     \
+    project_sh_fwd_kernel<d, false><<<grid_for(C * N, kThreads), kThreads, 0, st>>>(                              \
         C, N, K, means, quats, scales, opacities, sh_coeffs, viewmats, Ks, image_width, image_height, eps2d,      \
-        near_plane, far_plane, radius_clip, radii, means2d, depths, conics, comp, colors                          \
+        near_plane, far_plane, radius_clip, radii, means2d, depths, conics, comp, colors, 0u, 0u, 0u, nullptr,    \
+        nullptr, nullptr                                                                                          \
+    )
+    GSB_DEG_SWITCH(degrees_to_use, CALL)
+#undef CALL
+    return check_launch();
+}
+
+// gsb200_project_sh_fwd (no compensations) + the per-row tile counts / totals of gsb200_isect_count_totals (AccuTile test
+// on the row's conic and INPUT opacity) + the 64-byte compositing row records for gsb200_raster_fwd_rows.
+// row_records: 64 * C * N bytes, 16-byte aligned; only rows with radii > 0 are written.  totals: int64 [3].
+extern "C" int gsb200_project_sh_fwd_rows(
+    int64_t C, int64_t N, int64_t K, int degrees_to_use, const float *means, const float *quats, const float *scales,
+    const float *opacities, const float *sh_coeffs, const float *viewmats, const float *Ks, uint32_t image_width,
+    uint32_t image_height, float eps2d, float near_plane, float far_plane, float radius_clip, uint32_t tile_size,
+    uint32_t tile_width, uint32_t tile_height, int32_t *radii, float *means2d, float *depths, float *conics, float *colors,
+    void *row_records, int32_t *tiles_per_gauss, int64_t *totals, void *stream
+)
+{
+    if(C < 0 || N < 0 || K <= 0 || degrees_to_use < 0 || degrees_to_use > 4 || tile_size == 0 || !totals
+       || (int64_t)(degrees_to_use + 1) * (degrees_to_use + 1) > K)
+        return GSB200_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    GSB_CUDA_TRY(cudaMemsetAsync(totals, 0, 3 * sizeof(int64_t), st));
+    if(C * N == 0)
+        return GSB200_OK;
+    if(!means || !quats || !scales || !opacities || !sh_coeffs || !viewmats || !Ks || !radii || !means2d || !depths
+       || !conics || !colors || !row_records || !tiles_per_gauss || C * N > 0x7fffffffLL
+       || (reinterpret_cast<uintptr_t>(row_records) & 15) != 0)
+        return GSB200_E_INVALID;
+    if(bits_for_count(C) + bits_for_count((int64_t)tile_width * tile_height) > 32)
+        return GSB200_E_KEYBITS;
+#define CALL(d)                                                                                                   \
+    project_sh_fwd_kernel<d, true><<<grid_for(C * N, kThreads), kThreads, 0, st>>>(                               \
+        C, N, K, means, quats, scales, opacities, sh_coeffs, viewmats, Ks, image_width, image_height, eps2d,      \
+        near_plane, far_plane, radius_clip, radii, means2d, depths, conics, nullptr, colors, tile_size,           \
+        tile_width, tile_height, static_cast<float4 *>(row_records), tiles_per_gauss,                             \
+        reinterpret_cast<unsigned long long *>(totals)                                                            \
     )
     GSB_DEG_SWITCH(degrees_to_use, CALL)
 #undef CALL
@@ -1623,14 +1717,18 @@ extern "C" int gsb200_project_sh_bwd(
     if(v_compensations && !compensations)
         return GSB200_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(d)                                                                                                    \
-    project_sh_bwd_kernel<d><<<grid_for(N, kThreads), kThreads, 0, st>>>(                                          \
-        C, N, K, means, quats, scales, sh_coeffs, viewmats, Ks, image_width, image_height, eps2d, radii, conics,   \
+#define CALL_ARGS                                                                                                  \
+    C, N, K, means, quats, scales, sh_coeffs, viewmats, Ks, image_width, image_height, eps2d, radii, conics,       \
         compensations, colors, v_means2d, v_means2d_stride, v_depths, v_depths_stride, v_conics, v_conics_stride,  \
-        v_colors, v_colors_stride, v_compensations, v_means, v_quats, v_scales, v_sh_coeffs, seen_bits             \
-    )
+        v_colors, v_colors_stride, v_compensations, v_means, v_quats, v_scales, v_sh_coeffs, seen_bits
+#define CALL(d)                                                                                                    \
+    if(C == 1)                                                                                                     \
+        project_sh_bwd_kernel<d, true><<<grid_for(N, kThreads), kThreads, 0, st>>>(CALL_ARGS);                     \
+    else                                                                                                           \
+        project_sh_bwd_kernel<d, false><<<grid_for(N, kThreads), kThreads, 0, st>>>(CALL_ARGS)
     GSB_DEG_SWITCH(degrees_to_use, CALL)
 #undef CALL
+#undef CALL_ARGS
     return check_launch();
 }
 

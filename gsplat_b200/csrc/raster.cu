@@ -22,13 +22,10 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "rowrec.cuh"
 
 namespace gsb
 {
-// geom stream: (a, c) * -0.5 log2(e), b * -log2(e)  ->  -sigma * log2(e) = A dx^2 + C dy^2 + B dx dy
-constexpr float kLog2e        = 1.4426950408889634f;
-constexpr float kConicScaleAC = -0.5f * kLog2e, kConicScaleB = -kLog2e;
-constexpr float kConicUnscaleAC = 1.0f / kConicScaleAC, kConicUnscaleB = 1.0f / kConicScaleB;
 constexpr int kBatch  = 128; // gaussians per ring stage
 constexpr int kStages = 2;
 constexpr int kWarps  = 8;
@@ -133,49 +130,11 @@ __global__ void __launch_bounds__(256) pack_records_kernel(
     const float2 m  = *reinterpret_cast<const float2 *>(means2d + g * 2);
     const float a = conics[g * 3], b = conics[g * 3 + 1], c = conics[g * 3 + 2];
     const float op = opacities[g];
-    // conservative half extents of {alpha >= 1/255}: |dx| <= sqrt(t c / det), t = 2 ln(255 op)
-    // and of the box oriented along the ellipse axes (unit u = eigenvector of the larger eigenvalue l1 of
-    // [[a,b],[b,c]], v = (-uy, ux)): |d.u| <= sqrt(t / l1), |d.v| <= sqrt(t / l2).  All bounds inflated.
-    float ex, ey, ux = 1.f, uy = 0.f, lu = 1e30f, lv = 1e30f;
-    const float det = a * c - b * b;
-    if(!(op >= kAlphaThreshold))
-    {
-        ex = ey = -1e30f; // can never reach the alpha threshold (NaN opacity lands here too)
-    }
-    else if(!(det > 0.f) || !(a > 0.f) || !(c > 0.f) || !isfinite(det))
-    {
-        ex = ey = 1e30f; // not a proper ellipse: never cull, let the exact test decide
-    }
-    else
-    {
-        const float t = 2.f * logf(op * 255.f) * 1.0001f + 1e-4f;
-        ex            = sqrtf(t * c / det) * 1.0001f + 0.01f;
-        ey            = sqrtf(t * a / det) * 1.0001f + 0.01f;
-        if(!isfinite(ex) || !isfinite(ey))
-            ex = ey = 1e30f;
-        const float hd = 0.5f * (a - c);
-        const float l1 = 0.5f * (a + c) + sqrtf(hd * hd + b * b);
-        const float l2 = det / l1;
-        float vx1 = b, vy1 = l1 - a, vx2 = l1 - c, vy2 = b;
-        if(vx2 * vx2 + vy2 * vy2 > vx1 * vx1 + vy1 * vy1)
-            vx1 = vx2, vy1 = vy2;
-        const float nn = vx1 * vx1 + vy1 * vy1;
-        if(nn > 1e-30f && l2 > 0.f && isfinite(l1))
-        {
-            const float inv = rsqrtf(nn);
-            ux = vx1 * inv, uy = vy1 * inv;
-            const float ru = sqrtf(t / l1), rv = sqrtf(t / l2);
-            // an axis direction error delta (~1e-6 rad) shifts the far end of the other axis by delta * length
-            lu = ru * 1.0001f + 0.01f + 4e-6f * rv;
-            lv = rv * 1.0001f + 0.01f + 4e-6f * ru;
-            if(!isfinite(lu) || !isfinite(lv))
-                lu = lv = 1e30f;
-        }
-    }
-    cull[s] = make_float4(m.x, m.y, ex, ey);
-    axis[s] = make_float4(ux, uy, lu, lv);
-    // the conic is stored pre-multiplied so that the exponent of 2 falls out of three FMAs: vis = 2^(A dx^2 + C dy^2 + B dx dy)
-    geom[s] = make_float4(a * kConicScaleAC, b * kConicScaleB, c * kConicScaleAC, op);
+    float4 rc, ra, rg;
+    row_record(m.x, m.y, a, b, c, op, rc, ra, rg);
+    cull[s] = rc;
+    axis[s] = ra;
+    geom[s] = rg;
     constexpr int CV = RecLayout<CDIM>::kColorVec4;
     float cbuf[CV * 4];
 #pragma unroll
@@ -184,6 +143,25 @@ __global__ void __launch_bounds__(256) pack_records_kernel(
 #pragma unroll
     for(int v = 0; v < CV; ++v)
         color[s * CV + v] = make_float4(cbuf[4 * v], cbuf[4 * v + 1], cbuf[4 * v + 2], cbuf[4 * v + 3]);
+}
+
+// pack from 64-byte row records {cull | axis | geom | color} written by the fused projection (CDIM <= 4): a pure gather,
+// four lanes per intersection, each moving one float4 -- 64 contiguous bytes read per intersection, 128 contiguous bytes
+// written per stream and warp.
+__global__ void __launch_bounds__(256) pack_rows_kernel(
+    const int64_t S, const int32_t *__restrict__ flatten_ids, const float4 *__restrict__ rows, float4 *__restrict__ cull,
+    float4 *__restrict__ axis, float4 *__restrict__ geom, float4 *__restrict__ color
+)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = t >> 2;
+    if(s >= S)
+        return;
+    const int part  = (int)(t & 3);
+    const int64_t g = flatten_ids[s];
+    const float4 v  = ldg_nc_f4(rows + g * 4 + part);
+    float4 *dst     = part == 0 ? cull : (part == 1 ? axis : (part == 2 ? geom : color));
+    dst[s]          = v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1164,15 +1142,18 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
 template<int CDIM>
 static int launch_pack(
     const float *means2d, const float *conics, const float *colors, const float *opacities, const int32_t *offsets,
-    const int32_t *flatten_ids, int64_t S, unsigned n_tiles, void *records, cudaStream_t st
+    const int32_t *flatten_ids, int64_t S, unsigned n_tiles, void *records, cudaStream_t st, const float4 *rows = nullptr
 )
 {
     RecordStreams r = carve_records(records, S, RecLayout<CDIM>::kColorVec4);
     if(S > 0)
     {
-        pack_records_kernel<CDIM><<<grid_for(S, 256), 256, 0, st>>>(
-            S, flatten_ids, means2d, conics, colors, opacities, r.cull, r.axis, r.geom, r.color
-        );
+        if(rows != nullptr && CDIM <= 4) // 64-byte row records from the fused projection: gather only
+            pack_rows_kernel<<<grid_for(S * 4, 256), 256, 0, st>>>(S, flatten_ids, rows, r.cull, r.axis, r.geom, r.color);
+        else
+            pack_records_kernel<CDIM><<<grid_for(S, 256), 256, 0, st>>>(
+                S, flatten_ids, means2d, conics, colors, opacities, r.cull, r.axis, r.geom, r.color
+            );
         if(int rc = check_launch())
             return rc;
     }
@@ -1191,12 +1172,12 @@ static int launch_fwd(
     int64_t I, int64_t N, const float *means2d, const float *conics, const float *colors, const float *opacities,
     const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tw, uint32_t th,
     const int32_t *offsets, const int32_t *flatten_ids, int64_t S, void *records, float *render_colors,
-    float *render_alphas, int32_t *last_ids, cudaStream_t st
+    float *render_alphas, int32_t *last_ids, cudaStream_t st, const float4 *rows = nullptr
 )
 {
     (void)N;
     const unsigned n_tiles = (unsigned)(I * tw * th);
-    if(int rc = launch_pack<CDIM>(means2d, conics, colors, opacities, offsets, flatten_ids, S, n_tiles, records, st))
+    if(int rc = launch_pack<CDIM>(means2d, conics, colors, opacities, offsets, flatten_ids, S, n_tiles, records, st, rows))
         return rc;
     RecordStreams r      = carve_records(records, S, RecLayout<CDIM>::kColorVec4);
     const int32_t *order = (S > 0 && n_tiles >= 2 * 148) ? r.order : nullptr;
@@ -1426,6 +1407,41 @@ extern "C" int gsb200_raster_fwd(
             tile_height, offsets, flatten_ids, n_isects, records, render_colors, render_alphas, last_ids, st        \
         );
         GSB_FOR_CHANNELS(X)
+#undef X
+    default:
+        return GSB200_E_UNSUPPORTED;
+    }
+}
+
+// Forward from the 64-byte row records {cull | axis | geom | color} that gsb200_project_sh_fwd_rows wrote (D <= 4).
+extern "C" int gsb200_raster_fwd_rows(
+    int64_t I, int64_t N, int D, const void *row_records, const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+    uint32_t image_height, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, const int32_t *offsets,
+    const int32_t *flatten_ids, int64_t n_isects, void *records, float *render_colors, float *render_alphas,
+    int32_t *last_ids, void *stream
+)
+{
+    if(I < 0 || N < 0 || n_isects < 0 || !offsets || !render_colors || !render_alphas || !last_ids)
+        return GSB200_E_INVALID;
+    if(n_isects > 0 && (!row_records || !flatten_ids || !records || (reinterpret_cast<uintptr_t>(row_records) & 15) != 0))
+        return GSB200_E_INVALID;
+    if(tile_size != (uint32_t)gsb::kTile || D > 4)
+        return GSB200_E_UNSUPPORTED;
+    if(I == 0 || image_width == 0 || image_height == 0)
+        return GSB200_OK;
+    if((uint64_t)tile_width * gsb::kTile < image_width || (uint64_t)tile_height * gsb::kTile < image_height)
+        return GSB200_E_INVALID;
+    cudaStream_t st  = (cudaStream_t)stream;
+    const float4 *rr = static_cast<const float4 *>(row_records);
+    switch(D)
+    {
+#define X(n)                                                                                                         \
+    case n:                                                                                                          \
+        return gsb::launch_fwd<n>(                                                                                   \
+            I, N, nullptr, nullptr, nullptr, nullptr, backgrounds, masks, image_width, image_height, tile_width,    \
+            tile_height, offsets, flatten_ids, n_isects, records, render_colors, render_alphas, last_ids, st, rr    \
+        );
+        X(1) X(2) X(3) X(4)
 #undef X
     default:
         return GSB200_E_UNSUPPORTED;

@@ -552,7 +552,7 @@ class _ProjectSH(torch.autograd.Function):
     @staticmethod
     def forward(
         ctx, means, quats, scales, opacities, sh_coeffs, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
-        radius_clip, sh_degree, calc_compensations,
+        radius_clip, sh_degree, calc_compensations, rows_out=None,
     ):
         dev = require_cuda(means, quats, scales, opacities, sh_coeffs, viewmats, Ks)
         means, quats, scales = f32c(means, "means"), f32c(quats, "quats"), f32c(scales, "scales")
@@ -565,14 +565,29 @@ class _ProjectSH(torch.autograd.Function):
         colors = torch.empty((C, N, 3), **o)
         comps = torch.empty((C, N), **o) if calc_compensations else None
         with _Ctx(dev) as st:
-            check(
-                lib().gsb200_project_sh_fwd(
-                    C, N, K, sh_degree, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(sh_coeffs),
-                    ptr(viewmats), ptr(Ks), width, height, eps2d, near_plane, far_plane, radius_clip,
-                    int(calc_compensations), ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(colors), st,
-                ),
-                "project_sh_fwd",
-            )
+            if rows_out is not None and not calc_compensations:
+                # + per-row tile counts / totals and the 64-byte compositing row records (see RowSideOutputs)
+                rows_out.rows = torch.empty((C, N, 16), **o)
+                rows_out.tiles_per_gauss = torch.empty((C, N), device=dev, dtype=torch.int32)
+                rows_out.totals = torch.empty(3, device=dev, dtype=torch.int64)
+                check(
+                    lib().gsb200_project_sh_fwd_rows(
+                        C, N, K, sh_degree, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(sh_coeffs),
+                        ptr(viewmats), ptr(Ks), width, height, eps2d, near_plane, far_plane, radius_clip, rows_out.tile_size,
+                        rows_out.tile_width, rows_out.tile_height, ptr(radii), ptr(means2d), ptr(depths), ptr(conics),
+                        ptr(colors), ptr(rows_out.rows), ptr(rows_out.tiles_per_gauss), ptr(rows_out.totals), st,
+                    ),
+                    "project_sh_fwd_rows",
+                )
+            else:
+                check(
+                    lib().gsb200_project_sh_fwd(
+                        C, N, K, sh_degree, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(sh_coeffs),
+                        ptr(viewmats), ptr(Ks), width, height, eps2d, near_plane, far_plane, radius_clip,
+                        int(calc_compensations), ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(colors), st,
+                    ),
+                    "project_sh_fwd",
+                )
         ctx.save_for_backward(means, quats, scales, sh_coeffs, viewmats, Ks, radii, conics, comps, colors)
         ctx.meta = (width, height, eps2d, sh_degree)
         ctx.mark_non_differentiable(radii)
@@ -615,12 +630,25 @@ class _ProjectSH(torch.autograd.Function):
                 "project_sh_bwd",
             )
         # opacities only steer culling / radius (non-differentiable there)
-        return (v_means, v_quats, v_scales, None, v_sh, None, None) + (None,) * 8
+        return (v_means, v_quats, v_scales, None, v_sh, None, None) + (None,) * 9
+
+
+class RowSideOutputs:
+    """Side outputs of the fused projection for the two stages that follow it in rasterization(): per-row tile counts
+    and their totals (what gsb200_isect_count_totals would compute) and the 64-byte compositing row records
+    {cull | axis | geom | rgb0} that make the pack pass a pure gather.  Valid only while the compositing runs on exactly
+    the projection's means2d / conics / colours and the INPUT opacities (no antialiasing compensation, 3 channels)."""
+
+    __slots__ = ("tile_size", "tile_width", "tile_height", "rows", "tiles_per_gauss", "totals")
+
+    def __init__(self, tile_size: int, tile_width: int, tile_height: int):
+        self.tile_size, self.tile_width, self.tile_height = int(tile_size), int(tile_width), int(tile_height)
+        self.rows = self.tiles_per_gauss = self.totals = None
 
 
 def fused_project_sh(
     means, quats, scales, opacities, sh_coeffs, viewmats, Ks, width, height, sh_degree, eps2d=0.3, near_plane=0.01,
-    far_plane=1e10, radius_clip=0.0, calc_compensations=False,
+    far_plane=1e10, radius_clip=0.0, calc_compensations=False, rows_out: Optional[RowSideOutputs] = None,
 ):
     """One pass over the gaussians: world->camera, covariance->conic, SH->RGB (+0.5, clamped at 0).
     means [N,3] quats [N,4] scales [N,3] opacities [N] sh_coeffs [N,K,3] viewmats [C,4,4] Ks [C,3,3].
@@ -631,7 +659,7 @@ def fused_project_sh(
         raise ValueError(f"sh_degree={sh_degree} needs K >= {(sh_degree + 1) ** 2}")
     return _ProjectSH.apply(
         means, quats, scales, opacities, sh_coeffs, viewmats, Ks, int(width), int(height), float(eps2d),
-        float(near_plane), float(far_plane), float(radius_clip), int(sh_degree), bool(calc_compensations),
+        float(near_plane), float(far_plane), float(radius_clip), int(sh_degree), bool(calc_compensations), rows_out,
     )
 
 
@@ -829,7 +857,7 @@ class SortedIntersections:
 @torch.no_grad()
 def isect_tiles_sorted(
     means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
-    conics: Optional[Tensor] = None, opacities: Optional[Tensor] = None,
+    conics: Optional[Tensor] = None, opacities: Optional[Tensor] = None, precounted: Optional[RowSideOutputs] = None,
 ) -> SortedIntersections:
     """Dense-layout tile intersection + offsets for rasterization(): same intersections in the same order as
     ``isect_tiles(sort=True)`` + ``isect_offset_encode`` (reference: csrc/Intersect.cpp:203-326, 330-382), with the
@@ -854,7 +882,15 @@ def isect_tiles_sorted(
     key_bytes = 2 if key_bits <= 16 else 4
     key_dtype = torch.int16 if key_bytes == 2 else torch.int32  # raw storage; the kernels read them unsigned
     total = I * N
-    tiles_per_gauss = torch.empty(image_dims + (N,), device=dev, dtype=torch.int32)
+    have_counts = (
+        precounted is not None and precounted.totals is not None and total > 0
+        and (precounted.tile_size, precounted.tile_width, precounted.tile_height) == (tile_size, tile_width, tile_height)
+        and precounted.tiles_per_gauss.numel() == total and conics is not None and opacities is not None
+    )
+    if have_counts:  # counted by the fused projection (same device function, same inputs)
+        tiles_per_gauss = precounted.tiles_per_gauss.view(image_dims + (N,))
+    else:
+        tiles_per_gauss = torch.empty(image_dims + (N,), device=dev, dtype=torch.int32)
     offsets = torch.empty((I, tile_height, tile_width), device=dev, dtype=torch.int32)
     geom = (I, tile_width, tile_height)
     accu = conics is not None and opacities is not None
@@ -868,15 +904,16 @@ def isect_tiles_sorted(
 
     if total == 0:
         return empty()
-    totals = torch.empty(3, device=dev, dtype=torch.int64)
+    totals = precounted.totals if have_counts else torch.empty(3, device=dev, dtype=torch.int64)
     with _Ctx(dev) as st:
-        check(
-            L.gsb200_isect_count_totals(
-                I, N, ptr(means2d), ptr(radii), ptr(conics) if accu else None, ptr(opacities) if accu else None, tile_size,
-                tile_width, tile_height, ptr(tiles_per_gauss), ptr(totals), st,
-            ),
-            "intersect_tile (count)",
-        )
+        if not have_counts:
+            check(
+                L.gsb200_isect_count_totals(
+                    I, N, ptr(means2d), ptr(radii), ptr(conics) if accu else None, ptr(opacities) if accu else None, tile_size,
+                    tile_width, tile_height, ptr(tiles_per_gauss), ptr(totals), st,
+                ),
+                "intersect_tile (count)",
+            )
         if _MEASURE_NO_SYNC and (I, N, tile_width, tile_height) in _last_totals:
             # measurement knob only (GSB200_MEASURE_NO_SYNC=1, static scene): reuse the previous call's totals to see what
             # the host read below costs in a steady-state step; never set outside bench A/B runs
@@ -950,7 +987,7 @@ class _RasterizeToPixels(torch.autograd.Function):
     @staticmethod
     def forward(
         ctx, means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size, isect_offsets,
-        flatten_ids, absgrad_holder,
+        flatten_ids, absgrad_holder, row_records=None,
     ):
         dev = require_cuda(means2d, conics, colors, opacities)
         means2d, conics, colors, opacities = f32c(means2d, "means2d"), f32c(conics, "conics"), f32c(colors, "colors"), f32c(opacities, "opacities")
@@ -978,14 +1015,23 @@ class _RasterizeToPixels(torch.autograd.Function):
         render_alphas = torch.empty(image_dims + (height, width, 1), **o)
         last_ids = torch.empty(image_dims + (height, width), device=dev, dtype=torch.int32)
         with _Ctx(dev) as st:
-            check(
-                L.gsb200_raster_fwd(
-                    I, N, D, ptr(means2d), ptr(conics), ptr(colors), ptr(opacities), ptr(backgrounds), ptr(m8), width,
-                    height, tile_size, tw, th, ptr(offsets), ptr(fl), S, ptr(records), ptr(render_colors),
-                    ptr(render_alphas), ptr(last_ids), st,
-                ),
-                "rasterize_to_pixels_3dgs",
-            )
+            if row_records is not None and D <= 4 and row_records.numel() == R * 16:
+                check(
+                    L.gsb200_raster_fwd_rows(
+                        I, N, D, ptr(row_records), ptr(backgrounds), ptr(m8), width, height, tile_size, tw, th, ptr(offsets),
+                        ptr(fl), S, ptr(records), ptr(render_colors), ptr(render_alphas), ptr(last_ids), st,
+                    ),
+                    "rasterize_to_pixels_3dgs (row records)",
+                )
+            else:
+                check(
+                    L.gsb200_raster_fwd(
+                        I, N, D, ptr(means2d), ptr(conics), ptr(colors), ptr(opacities), ptr(backgrounds), ptr(m8), width,
+                        height, tile_size, tw, th, ptr(offsets), ptr(fl), S, ptr(records), ptr(render_colors),
+                        ptr(render_alphas), ptr(last_ids), st,
+                    ),
+                    "rasterize_to_pixels_3dgs",
+                )
         ctx.save_for_backward(backgrounds, m8, offsets, fl, records, render_alphas, last_ids)
         ctx.absgrad_holder = absgrad_holder  # filled in place by backward; deliberately not a saved tensor
         ctx.meta = (row_dims, I, N, R, D, width, height, tile_size, tw, th, S)
@@ -1020,7 +1066,7 @@ class _RasterizeToPixels(torch.autograd.Function):
         v_backgrounds = None
         if backgrounds is not None and ctx.needs_input_grad[4]:
             v_backgrounds = (v_render_colors * (1.0 - render_alphas)).sum(dim=(-3, -2))
-        return (v_means2d, v_conics, v_colors, v_opacities, v_backgrounds) + (None,) * 7
+        return (v_means2d, v_conics, v_colors, v_opacities, v_backgrounds) + (None,) * 8
 
 
 def rasterize_to_pixels(
@@ -1041,6 +1087,18 @@ def rasterize_to_pixels(
     """Front-to-back alpha compositing of depth-sorted Gaussians per 16x16 tile.
     Returns (render_colors [..., H, W, channels], render_alphas [..., H, W, 1]).  With ``absgrad`` the
     backward fills ``means2d.absgrad``."""
+    return rasterize_to_pixels_rows(
+        means2d, conics, colors, opacities, image_width, image_height, tile_size, isect_offsets, flatten_ids, backgrounds,
+        masks, packed, absgrad, None,
+    )
+
+
+def rasterize_to_pixels_rows(
+    means2d, conics, colors, opacities, image_width, image_height, tile_size, isect_offsets, flatten_ids, backgrounds=None,
+    masks=None, packed=False, absgrad=False, _row_records: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor]:
+    """rasterize_to_pixels with the optional ``RowSideOutputs.rows`` of the fused projection that produced the inputs
+    (rasterization() passes them; the forward's pack pass then only gathers)."""
     if packed != (means2d.dim() == 2):
         raise ValueError(f"packed={packed} but means2d has shape {tuple(means2d.shape)}")
     if tile_size != 16:
@@ -1061,7 +1119,7 @@ def rasterize_to_pixels(
     holder = torch.zeros_like(means2d) if absgrad else None
     render_colors, render_alphas = _RasterizeToPixels.apply(
         means2d, conics, colors, opacities, backgrounds, masks, int(image_width), int(image_height), int(tile_size),
-        isect_offsets, flatten_ids, holder,
+        isect_offsets, flatten_ids, holder, _row_records if pad == 0 else None,
     )
     if absgrad:
         means2d.absgrad = holder

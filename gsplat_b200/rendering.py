@@ -20,12 +20,14 @@ import torch
 from torch import Tensor
 
 from .ops import (
+    RowSideOutputs,
     fully_fused_projection,
     fused_project_sh,
     isect_offset_encode,
     isect_tiles,
     isect_tiles_sorted,
     rasterize_to_pixels,
+    rasterize_to_pixels_rows,
     spherical_harmonics,
     spherical_harmonics_rows,
 )
@@ -40,6 +42,10 @@ _ALL_MODES = _COLOR_MODES | _HIT_DISTANCE_MODES | _DEPTH_MODES
 
 # GSB200_ISECT_WIDE=1 keeps the 64-bit (image | tile | depth) keys through the S-sized sort (round-1 pipeline; A/B runs)
 _ISECT_WIDE = os.environ.get("GSB200_ISECT_WIDE", "0") == "1"
+
+
+# GSB200_ROW_RECORDS=0: the fused projection neither counts tiles nor writes compositing row records (A/B runs)
+_NO_ROW_RECORDS = os.environ.get("GSB200_ROW_RECORDS", "1") == "0"
 
 
 class _Lazy:
@@ -99,7 +105,7 @@ def _unsupported(name: str, why: str = "out of scope for the gsplat_b200 hot pat
 
 def _project_dense(
     means, covars, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree, eps2d, near_plane, far_plane,
-    radius_clip, antialiased, camera_model, has_color, nb, batch_dims, C, N,
+    radius_clip, antialiased, camera_model, has_color, nb, batch_dims, C, N, rows_out=None,
 ):
     """Dense [..., C, N] projection (+ SH): the fused single pass when it applies, else the per-op kernels."""
     fused = (
@@ -109,7 +115,7 @@ def _project_dense(
     if fused:
         radii, means2d, depths, conics, feat, compensations = fused_project_sh(
             means, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree, eps2d, near_plane,
-            far_plane, radius_clip, antialiased,
+            far_plane, radius_clip, antialiased, rows_out=rows_out,
         )
     else:
         radii, means2d, depths, conics, compensations = fully_fused_projection(
@@ -297,6 +303,7 @@ def rasterization(
     sharded = distributed and world_size > 1
     native_packed = packed
     camera_ids = gaussian_ids = batch_ids = None
+    rows_out = None
     if native_packed:
         batch_ids, camera_ids, gaussian_ids, indptr, radii, means2d, depths, conics, compensations = fully_fused_projection(
             means, covars, quats, scales, viewmats, Ks, width, height, eps2d=eps2d, near_plane=near_plane,
@@ -321,10 +328,16 @@ def rasterization(
                 feat = spherical_harmonics_rows(sh_degree, means, viewmats, colors, batch_ids, camera_ids, gaussian_ids)
                 feat = torch.clamp_min(feat + 0.5, 0.0)
     else:
+        # the fused projection can also count tiles and write the compositing row records, when what follows composites
+        # exactly its outputs: plain RGB, input opacities (no antialiasing compensation), rows not exchanged between ranks
+        if render_mode == "RGB" and not antialiased and not sharded and not _ISECT_WIDE and not _NO_ROW_RECORDS:
+            rows_out = RowSideOutputs(tile_size, math.ceil(width / float(tile_size)), math.ceil(height / float(tile_size)))
         radii, means2d, depths, conics, feat, compensations, opac = _project_dense(
             means, covars, quats, scales, opacities, colors, viewmats, Ks, width, height, sh_degree, eps2d, near_plane, far_plane,
-            radius_clip, antialiased, camera_model, has_color, nb, batch_dims, C, N,
+            radius_clip, antialiased, camera_model, has_color, nb, batch_dims, C, N, rows_out=rows_out,
         )
+        if rows_out is not None and rows_out.rows is None:
+            rows_out = None  # the per-op projection ran: nothing precomputed
 
     # ---- Seam B (distributed=True): all-to-all so that each rank holds ALL gaussians projected onto ITS cameras
     if sharded and packed:
@@ -381,7 +394,9 @@ def rasterization(
     else:
         # dense rows: the S-sized sort runs on 2- / 4-byte tile ids; meta["isect_ids"] (the reference's 64-bit ids) is
         # rebuilt from them on first access
-        hits = isect_tiles_sorted(means2d, radii, depths, tile_size, tile_width, tile_height, conics=conics, opacities=opac)
+        hits = isect_tiles_sorted(
+            means2d, radii, depths, tile_size, tile_width, tile_height, conics=conics, opacities=opac, precounted=rows_out,
+        )
         tiles_per_gauss, flatten_ids, isect_offsets = hits.tiles_per_gauss, hits.flatten_ids, hits.isect_offsets
         isect_ids = _Lazy(hits.isect_ids)
     isect_offsets = isect_offsets.reshape(batch_dims + (C, tile_height, tile_width))
@@ -411,9 +426,9 @@ def rasterization(
                 render_alphas = ra
         render_colors = torch.cat(outs, dim=-1)
     else:
-        render_colors, render_alphas = rasterize_to_pixels(
+        render_colors, render_alphas = rasterize_to_pixels_rows(
             means2d, conics, feat, opac, width, height, tile_size, isect_offsets, flatten_ids, backgrounds=backgrounds,
-            packed=packed, absgrad=absgrad,
+            packed=packed, absgrad=absgrad, _row_records=rows_out.rows if (rows_out is not None and n_ch == 3) else None,
         )
 
     if render_mode in _EXPECTED_MODES:  # ED / RGB+ED: normalise accumulated depth

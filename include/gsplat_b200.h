@@ -106,6 +106,21 @@ extern "C"
         float radius_clip, int calc_compensations, int32_t *radii, float *means2d, float *depths, float *conics,
         float *compensations, float *colors, void *stream
     );
+    /* gsb200_project_sh_fwd (without compensations) whose epilogue also hands the two following stages what they would
+     * otherwise recompute (round 2): tiles_per_gauss int32 [C,N] and totals int64 [3] exactly as
+     * gsb200_isect_count_totals computes them from this call's means2d / radii / conics and the INPUT opacities
+     * (AccuTile test, csrc/IntersectTile.cu:83-207), and row_records, 64 bytes per (camera, gaussian) row, 16-byte
+     * aligned: {mean2d + axis-aligned half extents | ellipse axis + oriented half extents | pre-scaled conic + opacity |
+     * r g b 0} -- the per-intersection record of the compositing kernels, so that gsb200_raster_fwd_rows only gathers.
+     * Only rows with radii > 0 are written. */
+    int gsb200_project_sh_fwd_rows(
+        int64_t C, int64_t N, int64_t K, int degrees_to_use, const float *means, const float *quats,
+        const float *scales, const float *opacities, const float *sh_coeffs, const float *viewmats, const float *Ks,
+        uint32_t image_width, uint32_t image_height, float eps2d, float near_plane, float far_plane,
+        float radius_clip, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, int32_t *radii,
+        float *means2d, float *depths, float *conics, float *colors, void *row_records, int32_t *tiles_per_gauss,
+        int64_t *totals, void *stream
+    );
     /* Backward of the fused pass.  v_colors is the gradient w.r.t. the post-activation colours
      * (the relu mask is re-derived).  All outputs fully written; deterministic.  seen_bits (optional,
      * ceil(N / 32) words): bit n%32 of word n/32 = gaussian n is visible in some camera of this call, i.e. its
@@ -284,6 +299,14 @@ extern "C"
         uint32_t image_height, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, const int32_t *offsets,
         const int32_t *flatten_ids, int64_t n_isects, void *records, float *render_colors, float *render_alphas,
         int32_t *last_ids, void *stream
+    );
+    /* gsb200_raster_fwd for D <= 4 from the row records of gsb200_project_sh_fwd_rows (the gaussians' means2d / conics /
+     * colours / opacities are read from there); same outputs, same `records` for gsb200_raster_bwd. */
+    int gsb200_raster_fwd_rows(
+        int64_t I, int64_t N, int D, const void *row_records, const float *backgrounds, const uint8_t *masks,
+        uint32_t image_width, uint32_t image_height, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+        const int32_t *offsets, const int32_t *flatten_ids, int64_t n_isects, void *records, float *render_colors,
+        float *render_alphas, int32_t *last_ids, void *stream
     );
     /* Gradient outputs are ACCUMULATED into (caller zero-initialises): each is addressed as
      * ptr[g * stride + k], g in [0, I*N), so they may be views into one packed record per gaussian.

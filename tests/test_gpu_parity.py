@@ -373,6 +373,45 @@ def test_isect_narrow_keys_match_wide_pipeline(gs, big_gaussians):
     assert z.flatten_ids.numel() == 0 and z.isect_ids().numel() == 0 and (z.isect_offsets == 0).all() and (z.tiles_per_gauss == 0).all()
 
 
+def test_fused_projection_row_side_outputs(gs):
+    """The fused projection's side outputs (per-row tile counts + totals, 64-byte compositing row records) must reproduce
+    what the stand-alone stages compute: counts / totals bit for bit, and a forward that is BIT-identical to the one that
+    packs its records from means2d / conics / colours / opacities (the extents only steer a conservative culling)."""
+    from gsplat_b200.ops import RowSideOutputs, fused_project_sh, isect_tiles_sorted, rasterize_to_pixels_rows
+
+    sc = scene.make_scene(n_max=40000, sh_degree=3)
+    W, H, C = 640, 360, 2
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    Ks = scene.rescale_K(sc["Ks"], sc["width"], sc["height"], W, H)[:C]
+    P = {k: _t(sc[k]) for k in ("means", "quats", "scales", "opacities", "sh")}
+    vm, K = _t(sc["viewmats"][:C]), _t(Ks)
+    plain = fused_project_sh(P["means"], P["quats"], P["scales"], P["opacities"], P["sh"], vm, K, W, H, 3)
+    side = RowSideOutputs(16, tw, th)
+    rows = fused_project_sh(P["means"], P["quats"], P["scales"], P["opacities"], P["sh"], vm, K, W, H, 3, rows_out=side)
+    for a, b in zip(plain[:5], rows[:5]):
+        assert torch.equal(a, b)
+    radii, m2, dep, con, col = rows[:5]
+    op = torch.broadcast_to(P["opacities"][None], dep.shape).contiguous()
+    ref = gs.isect_tiles(m2, radii, dep, 16, tw, th, conics=con, opacities=op)
+    assert torch.equal(side.tiles_per_gauss, ref[0])
+    tot = side.totals.tolist()
+    assert tot == [ref[1].numel(), int((ref[0] > 0).sum()), int(ref[0].max())] and tot[0] > 30000
+    hits = isect_tiles_sorted(m2, radii, dep, 16, tw, th, conics=con, opacities=op, precounted=side)
+    assert torch.equal(hits.flatten_ids, ref[2]) and torch.equal(hits.isect_ids(), ref[1])
+    bg = torch.rand(C, 3, device=DEV)
+    outs = []
+    for rr in (None, side.rows):
+        m2g, cong, colg, opg = (x.clone().requires_grad_(True) for x in (m2, con, col, op))
+        rc, ra = rasterize_to_pixels_rows(m2g, cong, colg, opg, W, H, 16, hits.isect_offsets.view(C, th, tw), hits.flatten_ids, backgrounds=bg, _row_records=rr)
+        w = torch.linspace(0.5, 1.5, rc.numel(), device=DEV).view_as(rc)
+        ((rc * w).sum() + ra.sum()).backward()
+        outs.append((rc.detach(), ra.detach(), m2g.grad, cong.grad, colg.grad, opg.grad))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    for a, b, name in zip(outs[0][2:], outs[1][2:], ("v_means2d", "v_conics", "v_colors", "v_opacities")):
+        rel = float((a - b).norm() / a.norm())
+        assert rel < 1e-5, (name, rel)  # same pairs, same arithmetic; only the order of the atomic adds differs
+
+
 def test_isect_sorted_equals_stable_sort_of_unsorted(gs):
     """The two-level sort (rows by depth, then intersections by (image, tile) bits only) must give exactly what
     one stable sort of the reference's unsorted emission gives (csrc/Intersect.cpp:283-326)."""
