@@ -1123,18 +1123,41 @@ struct IsectKey<int64_t>
     __device__ __forceinline__ int64_t operator()(int64_t tile) const { return hi_db | (tile << 32); }
 };
 
+// Capacity-bounded emission (gsb200_isect_sorted): the launch covers `total` = capacity row slots and writes into
+// capacity-sized outputs, while the real counts sit in device memory (totals[0] intersections, totals[1] rows with
+// tiles).  Returns the number of real row slots; the slots between the real intersections and the capacity get padding
+// pairs (largest key: the stable sort leaves them behind every real pair; row 0: any valid row).
+template<class KeyT>
+__device__ __forceinline__ int64_t emit_bounded_rows(
+    int64_t j, int64_t n_threads, int64_t total, const int64_t *__restrict__ totals, int64_t cap_isects,
+    KeyT *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids
+)
+{
+    const int64_t n_real = totals[0] < cap_isects ? totals[0] : cap_isects;
+    for(int64_t s = n_real + j; s < cap_isects; s += n_threads)
+    {
+        isect_ids[s]   = (KeyT)~(KeyT)0;
+        flatten_ids[s] = 0;
+    }
+    return totals[1] < total ? totals[1] : total;
+}
+
 template<class KeyT>
 __global__ void __launch_bounds__(kThreads) isect_emit_kernel(
     int64_t total, int64_t N, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
     const float *__restrict__ depths, const float *__restrict__ conics, const float *__restrict__ opacities,
     const int64_t *__restrict__ cum_tiles, const int64_t *__restrict__ image_ids, const int32_t *__restrict__ order,
     uint32_t tile_size, uint32_t tw, uint32_t th, uint32_t tile_n_bits, KeyT *__restrict__ isect_ids,
-    int32_t *__restrict__ flatten_ids
+    int32_t *__restrict__ flatten_ids, const int64_t *__restrict__ totals = nullptr, int64_t cap_isects = 0
 )
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(totals != nullptr)
+        total = emit_bounded_rows<KeyT>(j, (int64_t)gridDim.x * blockDim.x, total, totals, cap_isects, isect_ids, flatten_ids);
     if(j >= total)
         return;
+    if(totals != nullptr && cum_tiles[j] > cap_isects)
+        return; // beyond the speculative capacity: the host sees totals[0] > capacity and redoes the stage
     const int64_t i = order ? (int64_t)order[j] : j;
     const int2 r    = reinterpret_cast<const int2 *>(radii)[i];
     if(r.x <= 0 || r.y <= 0)
@@ -1267,12 +1290,14 @@ __global__ void __launch_bounds__(kThreads) isect_emit_coop_kernel(
     const float *__restrict__ depths, const float *__restrict__ conics, const float *__restrict__ opacities,
     const int64_t *__restrict__ cum_tiles, const int64_t *__restrict__ image_ids, const int32_t *__restrict__ order,
     uint32_t tile_size, uint32_t tw, uint32_t th, uint32_t tile_n_bits, KeyT *__restrict__ isect_ids,
-    int32_t *__restrict__ flatten_ids
+    int32_t *__restrict__ flatten_ids, const int64_t *__restrict__ totals = nullptr, int64_t cap_isects = 0
 )
 {
     const int64_t j     = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
-    const bool active   = j < total;
+    if(totals != nullptr)
+        total = emit_bounded_rows<KeyT>(j, (int64_t)gridDim.x * blockDim.x, total, totals, cap_isects, isect_ids, flatten_ids);
+    const bool active   = j < total && !(totals != nullptr && cum_tiles[j] > cap_isects);
     const int64_t i     = active ? (order ? (int64_t)order[j] : j) : 0;
     int2 r              = make_int2(0, 0);
     float2 m            = make_float2(0.f, 0.f);
@@ -1836,7 +1861,8 @@ template<class KeyT>
 static int emit_ordered(
     int64_t I, int64_t N, int64_t n_order, int64_t max_tiles_hint, const float *means2d, const int32_t *radii, const float *depths,
     const float *conics, const float *opacities, const int64_t *cum_tiles, const int64_t *image_ids, const int32_t *order,
-    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, KeyT *keys, int32_t *flatten_ids, void *stream
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, KeyT *keys, int32_t *flatten_ids, void *stream,
+    const int64_t *totals = nullptr, int64_t cap_isects = 0
 )
 {
     if(I < 0 || N < 0 || n_order < 0 || tile_size == 0)
@@ -1856,23 +1882,45 @@ static int emit_ordered(
     if(max_tiles_hint > 0 && max_tiles_hint <= 96)
         isect_emit_kernel<KeyT><<<grid_for(n_order, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
             n_order, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
-            tile_bits, keys, flatten_ids
+            tile_bits, keys, flatten_ids, totals, cap_isects
         );
     else
         isect_emit_coop_kernel<KeyT><<<grid_for(n_order, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
             n_order, N, means2d, radii, depths, conics, opacities, cum_tiles, image_ids, order, tile_size, tile_width, tile_height,
-            tile_bits, keys, flatten_ids
+            tile_bits, keys, flatten_ids, totals, cap_isects
         );
     return check_launch();
+}
+
+// stage of gsb200_isect_sorted (sort.cu): emission into capacity-sized outputs, real counts in `totals` (device)
+int emit_tilekeys_bounded(
+    int64_t I, int64_t N, int64_t cap_vis, int64_t max_tiles_hint, const float *means2d, const int32_t *radii, const float *depths,
+    const float *conics, const float *opacities, const int64_t *cum_tiles, const int32_t *order, uint32_t tile_size,
+    uint32_t tile_width, uint32_t tile_height, int key_bytes, void *keys, int32_t *flatten_ids, const int64_t *totals,
+    int64_t cap_isects, cudaStream_t st
+)
+{
+    if(key_bytes == 2)
+        return emit_ordered<uint16_t>(
+            I, N, cap_vis, max_tiles_hint, means2d, radii, depths, conics, opacities, cum_tiles, nullptr, order, tile_size, tile_width,
+            tile_height, static_cast<uint16_t *>(keys), flatten_ids, st, totals, cap_isects
+        );
+    return emit_ordered<uint32_t>(
+        I, N, cap_vis, max_tiles_hint, means2d, radii, depths, conics, opacities, cum_tiles, nullptr, order, tile_size, tile_width,
+        tile_height, static_cast<uint32_t *>(keys), flatten_ids, st, totals, cap_isects
+    );
 }
 
 // offsets[(image, tile)] from sorted dense tile ids (narrow keys): same contract as isect_offsets_kernel
 template<class KeyT>
 __global__ void __launch_bounds__(kThreads) isect_offsets_tilekeys_kernel(
-    int64_t n_isects, const KeyT *__restrict__ keys, int64_t total_tiles, int32_t *__restrict__ offsets
+    int64_t n_isects, const KeyT *__restrict__ keys, int64_t total_tiles, int32_t *__restrict__ offsets,
+    const int64_t *__restrict__ totals = nullptr
 )
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(totals != nullptr && totals[0] < n_isects)
+        n_isects = totals[0]; // capacity-sized launch: the pairs past the real count are padding
     if(s >= n_isects)
         return;
     const int64_t id   = (int64_t)keys[s];
@@ -1882,6 +1930,25 @@ __global__ void __launch_bounds__(kThreads) isect_offsets_tilekeys_kernel(
     if(s == n_isects - 1)
         for(int64_t k = id + 1; k < total_tiles; ++k)
             offsets[k] = (int32_t)n_isects;
+}
+
+int offsets_tilekeys_bounded(
+    int64_t cap_isects, int key_bytes, const void *keys, int64_t total_tiles, int32_t *offsets, const int64_t *totals, cudaStream_t st
+)
+{
+    // no thread writes anything when the real count is 0: start from zeros
+    GSB_CUDA_TRY(cudaMemsetAsync(offsets, 0, sizeof(int32_t) * (size_t)total_tiles, st));
+    if(cap_isects == 0)
+        return GSB200_OK;
+    if(key_bytes == 2)
+        isect_offsets_tilekeys_kernel<uint16_t><<<grid_for(cap_isects, kThreads), kThreads, 0, st>>>(
+            cap_isects, static_cast<const uint16_t *>(keys), total_tiles, offsets, totals
+        );
+    else
+        isect_offsets_tilekeys_kernel<uint32_t><<<grid_for(cap_isects, kThreads), kThreads, 0, st>>>(
+            cap_isects, static_cast<const uint32_t *>(keys), total_tiles, offsets, totals
+        );
+    return check_launch();
 }
 
 // the reference's 64-bit intersection ids, rebuilt from the sorted tile ids and the rows' depths

@@ -351,3 +351,166 @@ extern "C" int gsb200_isect_order_visible(
     GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(ws + L.cub, cub_bytes, it, cum_tiles, n_vis, st));
     return GSB200_OK;
 }
+
+// ---- the whole sorted dense intersection stage in one call, sized by CAPACITIES (round 2).
+// rasterization() used to read the totals of the count pass on the host before it could size and launch anything else:
+// the GPU idled for the round trip and for the host's launch latency behind it (40 us per step at BASELINE configs[2],
+// 100 us when a PCIe upload was in flight).  Here every launch is sized by host-side capacities (cap_vis rows with
+// tiles, cap_isects intersections) while the REAL counts stay in device memory (`totals`, from gsb200_isect_count_totals
+// or gsb200_project_sh_fwd_rows): slots beyond the real counts are padding that sorts last, and nothing is ever written
+// past a capacity.  The caller launches this with capacities predicted from earlier calls, reads the totals afterwards
+// (by then this work is queued behind them), takes the first totals[0] entries if both counts fit, and otherwise calls
+// again with exact capacities.  With capacities equal to the totals the padding is empty and this is the plain pipeline.
+namespace gsb
+{
+struct CountOfBounded
+{
+    const int32_t *tiles, *order;
+    const int64_t *totals;
+    int64_t cap;
+    __host__ __device__ int64_t operator()(const int32_t &j) const
+    {
+        const int64_t n = totals[1] < cap ? totals[1] : cap;
+        return (int64_t)j < n ? (int64_t)tiles[order[j]] : 0;
+    }
+};
+
+__global__ void __launch_bounds__(256) depth_key_rows_bounded_kernel(
+    int64_t cap_vis, int64_t N, const int32_t *__restrict__ rows, const float *__restrict__ depths, bool single_image,
+    const int64_t *__restrict__ totals, void *__restrict__ keys
+)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if(j >= cap_vis)
+        return;
+    const bool real  = j < totals[1];
+    const int64_t i  = real ? rows[j] : 0;
+    const uint32_t d = real ? __float_as_uint(depths[i]) : 0xffffffffu;
+    if(single_image)
+        static_cast<uint32_t *>(keys)[j] = d;
+    else
+        static_cast<uint64_t *>(keys)[j] = real ? (((uint64_t)(i / N) << 32) | (uint64_t)d) : ~0ull;
+}
+
+struct SortedLayout
+{
+    size_t rows_in, keys_in, keys_out, order, cum, n_sel, tkeys, tvals, cub, total;
+};
+static SortedLayout sorted_layout(int64_t total_rows, int64_t cap_vis, int64_t cap_isects, int key_bytes, int depth_end_bit, int tile_end_bit)
+{
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    SortedLayout L;
+    size_t a = 0, b = 0, c = 0, d = 0;
+    cub::DeviceSelect::If((void *)nullptr, a, cub::CountingInputIterator<int32_t>(0), (int32_t *)nullptr, (int32_t *)nullptr, total_rows, HasTiles{nullptr});
+    cub::DeviceRadixSort::SortPairs(
+        (void *)nullptr, b, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const int32_t *)nullptr, (int32_t *)nullptr, cap_vis, 0, depth_end_bit
+    );
+    cub::TransformInputIterator<int64_t, CountOfBounded, cub::CountingInputIterator<int32_t>> it(
+        cub::CountingInputIterator<int32_t>(0), CountOfBounded{nullptr, nullptr, nullptr, 0}
+    );
+    cub::DeviceScan::InclusiveSum((void *)nullptr, c, it, (int64_t *)nullptr, cap_vis);
+    if(key_bytes == 2)
+        cub::DeviceRadixSort::SortPairs(
+            (void *)nullptr, d, (const uint16_t *)nullptr, (uint16_t *)nullptr, (const int32_t *)nullptr, (int32_t *)nullptr, cap_isects, 0, tile_end_bit
+        );
+    else
+        cub::DeviceRadixSort::SortPairs(
+            (void *)nullptr, d, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int32_t *)nullptr, (int32_t *)nullptr, cap_isects, 0, tile_end_bit
+        );
+    size_t cub_bytes = a > b ? a : b;
+    cub_bytes        = cub_bytes > c ? cub_bytes : c;
+    cub_bytes        = cub_bytes > d ? cub_bytes : d;
+    L.rows_in  = 0; // the compaction writes every row that has tiles, however many: sized for all rows
+    L.keys_in  = L.rows_in + al(sizeof(int32_t) * (size_t)total_rows);
+    L.keys_out = L.keys_in + al(sizeof(uint64_t) * (size_t)cap_vis);
+    L.order    = L.keys_out + al(sizeof(uint64_t) * (size_t)cap_vis);
+    L.cum      = L.order + al(sizeof(int32_t) * (size_t)cap_vis);
+    L.n_sel    = L.cum + al(sizeof(int64_t) * (size_t)cap_vis);
+    L.tkeys    = L.n_sel + 256;
+    L.tvals    = L.tkeys + al((size_t)key_bytes * (size_t)cap_isects);
+    L.cub      = L.tvals + al(sizeof(int32_t) * (size_t)cap_isects);
+    L.total    = L.cub + al(cub_bytes) + 256;
+    return L;
+}
+} // namespace gsb
+
+extern "C" size_t gsb200_isect_sorted_workspace_bytes(
+    int64_t I, int64_t N, int64_t cap_vis, int64_t cap_isects, int key_bytes, uint32_t tile_width, uint32_t tile_height
+)
+{
+    if(I <= 0 || N <= 0 || cap_vis <= 0 || cap_isects <= 0 || (key_bytes != 2 && key_bytes != 4))
+        return 0;
+    const int tile_end = (int)gsb::bits_for_count(I * (int64_t)tile_width * tile_height);
+    return gsb::sorted_layout(I * N, cap_vis, cap_isects, key_bytes, 32 + (int)gsb::bits_for_count(I), tile_end > 0 ? tile_end : 1).total;
+}
+
+extern "C" int gsb200_isect_sorted(
+    int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *depths, const float *conics,
+    const float *opacities, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, const int32_t *tiles_per_gauss,
+    const int64_t *totals, int64_t cap_vis, int64_t cap_isects, int64_t max_tiles_hint, int key_bytes, void *tile_keys,
+    int32_t *flatten_ids, int32_t *offsets, void *workspace, size_t workspace_bytes, void *stream
+)
+{
+    if(I <= 0 || N <= 0 || cap_vis <= 0 || cap_isects <= 0 || tile_size == 0 || (key_bytes != 2 && key_bytes != 4))
+        return GSB200_E_INVALID;
+    const int64_t total = I * N, total_tiles = I * (int64_t)tile_width * tile_height;
+    if(!means2d || !radii || !depths || !tiles_per_gauss || !totals || !tile_keys || !flatten_ids || !offsets || !workspace
+       || total > 0x7fffffffLL || cap_vis > total || cap_isects > 0x7fffffffLL)
+        return GSB200_E_INVALID;
+    if((int)gsb::bits_for_count(total_tiles) > 8 * key_bytes)
+        return GSB200_E_KEYBITS;
+    const bool single  = I == 1;
+    const int depth_end = single ? 32 : 32 + (int)gsb::bits_for_count(I);
+    int tile_end        = (int)gsb::bits_for_count(total_tiles);
+    tile_end            = tile_end > 0 ? tile_end : 1;
+    const auto L        = gsb::sorted_layout(total, cap_vis, cap_isects, key_bytes, 32 + (int)gsb::bits_for_count(I), tile_end);
+    if(L.total > workspace_bytes)
+        return GSB200_E_WORKSPACE;
+    char *ws         = static_cast<char *>(workspace);
+    int32_t *rows_in = reinterpret_cast<int32_t *>(ws + L.rows_in), *order = reinterpret_cast<int32_t *>(ws + L.order);
+    void *k_in = ws + L.keys_in, *k_out = ws + L.keys_out;
+    int64_t *cum     = reinterpret_cast<int64_t *>(ws + L.cum);
+    int32_t *n_sel   = reinterpret_cast<int32_t *>(ws + L.n_sel);
+    void *tkeys      = ws + L.tkeys;
+    int32_t *tvals   = reinterpret_cast<int32_t *>(ws + L.tvals);
+    cudaStream_t st  = (cudaStream_t)stream;
+    const size_t cub_cap = L.total - L.cub;
+    size_t cub_bytes     = cub_cap;
+    // 1. rows with tiles, ascending
+    GSB_CUDA_TRY(cub::DeviceSelect::If(
+        ws + L.cub, cub_bytes, cub::CountingInputIterator<int32_t>(0), rows_in, n_sel, total, gsb::HasTiles{tiles_per_gauss}, st
+    ));
+    // 2. their (image, depth) keys -- padding slots get the largest key -- and a stable sort of the cap_vis slots
+    gsb::depth_key_rows_bounded_kernel<<<(unsigned)((cap_vis + 255) / 256), 256, 0, st>>>(cap_vis, N, rows_in, depths, single, totals, k_in);
+    if(int rc = gsb::check_launch())
+        return rc;
+    cub_bytes = cub_cap;
+    if(single)
+        GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(
+            ws + L.cub, cub_bytes, static_cast<const uint32_t *>(k_in), static_cast<uint32_t *>(k_out), rows_in, order, cap_vis, 0, 32, st
+        ));
+    else
+        GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(
+            ws + L.cub, cub_bytes, static_cast<const uint64_t *>(k_in), static_cast<uint64_t *>(k_out), rows_in, order, cap_vis, 0, depth_end, st
+        ));
+    // 3. inclusive scan of the tile counts in that order (0 for padding slots)
+    cub::TransformInputIterator<int64_t, gsb::CountOfBounded, cub::CountingInputIterator<int32_t>> it(
+        cub::CountingInputIterator<int32_t>(0), gsb::CountOfBounded{tiles_per_gauss, order, totals, cap_vis}
+    );
+    cub_bytes = cub_cap;
+    GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(ws + L.cub, cub_bytes, it, cum, cap_vis, st));
+    // 4. emission in depth order, (dense tile id, row) pairs; 5. stable sort on the tile id; 6. offsets
+    if(int rc = gsb::emit_tilekeys_bounded(
+           I, N, cap_vis, max_tiles_hint, means2d, radii, depths, conics, opacities, cum, order, tile_size, tile_width, tile_height,
+           key_bytes, tkeys, tvals, totals, cap_isects, st
+       ))
+        return rc;
+    if(key_bytes == 2)
+    {
+        if(int rc = gsb::sort_tile_pairs<uint16_t>(cap_isects, tile_end, tkeys, tvals, tile_keys, flatten_ids, ws + L.cub, cub_cap, st))
+            return rc;
+    }
+    else if(int rc = gsb::sort_tile_pairs<uint32_t>(cap_isects, tile_end, tkeys, tvals, tile_keys, flatten_ids, ws + L.cub, cub_cap, st))
+        return rc;
+    return gsb::offsets_tilekeys_bounded(cap_isects, key_bytes, tile_keys, total_tiles, offsets, totals, st);
+}

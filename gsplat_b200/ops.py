@@ -822,8 +822,58 @@ def isect_tiles(
     return tiles_per_gauss, isect_ids, flatten_ids
 
 
-_MEASURE_NO_SYNC = __import__("os").environ.get("GSB200_MEASURE_NO_SYNC", "0") == "1"
-_last_totals = {}
+# GSB200_ISECT_SPECULATE=0: always read the totals before sizing the intersection stage (A/B runs)
+_SPECULATE = __import__("os").environ.get("GSB200_ISECT_SPECULATE", "1") != "0"
+
+
+class _IsectPredictor:
+    """Capacities for gsb200_isect_sorted from the totals of the last calls on the same (device, image count, tile grid),
+    and the asynchronous host read of the current totals (side stream -> pinned memory)."""
+
+    def __init__(self, dev: torch.device):
+        self.hist = []  # (n_isects, n_vis, max_tiles) of the last 8 calls
+        self.hits = self.misses = 0
+        self.pinned = torch.empty(3, dtype=torch.int64).pin_memory()
+        self.side = torch.cuda.Stream(device=dev)
+        self.ready, self.done = torch.cuda.Event(), torch.cuda.Event()
+        self.dev = dev
+
+    def capacities(self, total_rows: int):
+        if not _SPECULATE or not self.hist:
+            return None
+        n_isects = max(h[0] for h in self.hist)
+        n_vis = max(h[1] for h in self.hist)
+        if n_isects == 0 or n_vis == 0:
+            return None
+        cap_vis = min(total_rows, n_vis + n_vis // 32 + 512)
+        cap_isects = min(0x7FFFFFFF, n_isects + n_isects // 32 + 2048)
+        return cap_vis, cap_isects, max(h[2] for h in self.hist)
+
+    def observe(self, n_isects: int, n_vis: int, max_tiles: int):
+        self.hist.append((n_isects, n_vis, max_tiles))
+        del self.hist[:-8]
+
+    def stage(self, totals: Tensor):
+        self.ready.record(torch.cuda.current_stream(self.dev))
+        self.side.wait_event(self.ready)
+        with torch.cuda.stream(self.side):
+            self.pinned.copy_(totals, non_blocking=True)
+            self.done.record(self.side)
+
+    def read(self):
+        self.done.synchronize()  # `totals` stays referenced by the caller until here
+        return tuple(int(v) for v in self.pinned.tolist())
+
+
+_predictors = {}
+
+
+def _isect_predictor(dev: torch.device, I: int, tile_width: int, tile_height: int) -> _IsectPredictor:
+    key = (dev.index, I, tile_width, tile_height, torch.cuda.current_stream(dev).cuda_stream)
+    p = _predictors.get(key)
+    if p is None:
+        p = _predictors[key] = _IsectPredictor(dev)
+    return p
 
 
 class SortedIntersections:
@@ -905,6 +955,7 @@ def isect_tiles_sorted(
     if total == 0:
         return empty()
     totals = precounted.totals if have_counts else torch.empty(3, device=dev, dtype=torch.int64)
+    pred = _isect_predictor(dev, I, tile_width, tile_height)
     with _Ctx(dev) as st:
         if not have_counts:
             check(
@@ -914,46 +965,45 @@ def isect_tiles_sorted(
                 ),
                 "intersect_tile (count)",
             )
-        if _MEASURE_NO_SYNC and (I, N, tile_width, tile_height) in _last_totals:
-            # measurement knob only (GSB200_MEASURE_NO_SYNC=1, static scene): reuse the previous call's totals to see what
-            # the host read below costs in a steady-state step; never set outside bench A/B runs
-            n_isects, n_vis, max_tiles = _last_totals[(I, N, tile_width, tile_height)]
+
+        def run(cap_vis: int, cap_isects: int, max_tiles: int):
+            # compaction, depth order, scan, emission, tile sort, offsets: one call, every launch sized by the capacities
+            keys_out = torch.empty(cap_isects, device=dev, dtype=key_dtype)
+            vals_out = torch.empty(cap_isects, device=dev, dtype=torch.int32)
+            ws = _scratch_buffer(dev, "isect", L.gsb200_isect_sorted_workspace_bytes(I, N, cap_vis, cap_isects, key_bytes, tile_width, tile_height))
+            check(
+                L.gsb200_isect_sorted(
+                    I, N, ptr(means2d), ptr(radii), ptr(depths), ptr(conics) if accu else None, ptr(opacities) if accu else None,
+                    tile_size, tile_width, tile_height, ptr(tiles_per_gauss), ptr(totals), cap_vis, cap_isects, max_tiles, key_bytes,
+                    ptr(keys_out), ptr(vals_out), ptr(offsets), ptr(ws), ws.numel(), st,
+                ),
+                "intersect_tile (sorted)",
+            )
+            return keys_out, vals_out
+
+        caps = pred.capacities(total)
+        if caps is not None:
+            # Launch on PREDICTED capacities, then read the totals: the host read (the reference's one sync of the forward,
+            # csrc/Intersect.cpp:259) overlaps the queued stage instead of idling the GPU.  A miss (a count above its
+            # capacity) costs one exact re-run; nothing is ever written past a capacity.
+            pred.stage(totals)
+            keys_out, vals_out = run(*caps)
+            n_isects, n_vis, max_tiles = pred.read()
+            pred.observe(n_isects, n_vis, max_tiles)
+            if n_isects == 0:
+                return empty()
+            if n_vis > caps[0] or n_isects > caps[1]:
+                pred.misses += 1
+                keys_out, vals_out = run(n_vis, n_isects, max_tiles)
+            else:
+                pred.hits += 1
+                keys_out, vals_out = keys_out[:n_isects], vals_out[:n_isects]
         else:
-            n_isects, n_vis, max_tiles = (int(v) for v in totals.tolist())  # the one host sync of the forward (reference: csrc/Intersect.cpp:259)
-            if _MEASURE_NO_SYNC:
-                _last_totals[(I, N, tile_width, tile_height)] = (n_isects, n_vis, max_tiles)
-        if n_isects == 0:
-            return empty()
-        keys = torch.empty(n_isects, device=dev, dtype=key_dtype)
-        flatten_ids = torch.empty(n_isects, device=dev, dtype=torch.int32)
-        order = torch.empty(n_vis, device=dev, dtype=torch.int32)
-        cum = torch.empty(n_vis, device=dev, dtype=torch.int64)
-        ws = _scratch_buffer(dev, "vorder", L.gsb200_isect_order_visible_workspace_bytes(I, total, n_vis))
-        check(
-            L.gsb200_isect_order_visible(I, N, n_vis, ptr(tiles_per_gauss), ptr(depths), None, ptr(order), ptr(cum), ptr(ws), ws.numel(), st),
-            "intersect_tile (order)",
-        )
-        check(
-            L.gsb200_isect_emit_tilekeys(
-                I, N, n_vis, max_tiles, ptr(means2d), ptr(radii), ptr(depths), ptr(conics) if accu else None,
-                ptr(opacities) if accu else None, ptr(cum), None, ptr(order), tile_size, tile_width, tile_height, key_bytes,
-                ptr(keys), ptr(flatten_ids), st,
-            ),
-            "intersect_tile (emit)",
-        )
-        keys_out, vals_out = torch.empty_like(keys), torch.empty_like(flatten_ids)
-        end_bit = max(key_bits, 1)
-        ws = _scratch_buffer(dev, "sort", L.gsb200_sort_tile_pairs_workspace_bytes(n_isects, key_bytes, end_bit))
-        check(
-            L.gsb200_sort_tile_pairs(
-                n_isects, key_bytes, end_bit, ptr(keys), ptr(flatten_ids), ptr(keys_out), ptr(vals_out), ptr(ws), ws.numel(), st,
-            ),
-            "intersect_tile (sort)",
-        )
-        check(
-            L.gsb200_isect_offsets_tilekeys(n_isects, key_bytes, ptr(keys_out), I, tile_width, tile_height, ptr(offsets), st),
-            "intersect_offset",
-        )
+            n_isects, n_vis, max_tiles = (int(v) for v in totals.tolist())  # first call of a shape: exact sizes
+            pred.observe(n_isects, n_vis, max_tiles)
+            if n_isects == 0:
+                return empty()
+            keys_out, vals_out = run(n_vis, n_isects, max_tiles)
     return SortedIntersections(tiles_per_gauss, vals_out, offsets, keys_out, key_bytes, depths, geom)
 
 

@@ -263,6 +263,26 @@ extern "C"
         int64_t n_isects, int key_bytes, const void *tile_keys, const int32_t *flatten_ids, const float *depths, int64_t I,
         uint32_t tile_width, uint32_t tile_height, int64_t *isect_ids, void *stream
     );
+    /* The sorted dense intersection stage in ONE call, sized by capacities (round 2): rows-with-tiles compaction, depth
+     * order, scan, emission of (dense tile id, row) pairs, stable sort on the tile id, offsets.  Inputs: the per-row tile
+     * counts and `totals` (int64 [3], DEVICE memory) of gsb200_isect_count_totals / gsb200_project_sh_fwd_rows.  Every
+     * launch is sized by cap_vis (<= I * N) and cap_isects; the real counts are read on the device: entries past
+     * totals[0] in tile_keys / flatten_ids ([cap_isects] each) are padding, nothing is written past a capacity, and
+     * offsets int32 [I, th, tw] is exact whenever totals[1] <= cap_vis and totals[0] <= cap_isects.  A caller may
+     * therefore launch with PREDICTED capacities before it has read the totals (the host read then overlaps this work
+     * instead of idling the GPU: the sync being hidden is the reference's csrc/Intersect.cpp:258-259), use the first
+     * totals[0] entries if both counts fit, and otherwise call again with capacities = totals.  key_bytes: 2 when
+     * I * th * tw <= 65536, else 4. */
+    size_t gsb200_isect_sorted_workspace_bytes(
+        int64_t I, int64_t N, int64_t cap_vis, int64_t cap_isects, int key_bytes, uint32_t tile_width, uint32_t tile_height
+    );
+    int gsb200_isect_sorted(
+        int64_t I, int64_t N, const float *means2d, const int32_t *radii, const float *depths, const float *conics,
+        const float *opacities, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+        const int32_t *tiles_per_gauss, const int64_t *totals, int64_t cap_vis, int64_t cap_isects, int64_t max_tiles_hint,
+        int key_bytes, void *tile_keys, int32_t *flatten_ids, int32_t *offsets, void *workspace, size_t workspace_bytes,
+        void *stream
+    );
     /* Stable radix sort of (isect_ids, flatten_ids) on key bits [begin_bit, end_bit)
      * (cub::DeviceRadixSort::SortPairs, csrc/IntersectTile.cu:1078-1121); begin_bit = 32 after pass 0. */
     size_t gsb200_sort_workspace_bytes(int64_t n_isects, int begin_bit, int end_bit);

@@ -373,6 +373,37 @@ def test_isect_narrow_keys_match_wide_pipeline(gs, big_gaussians):
     assert z.flatten_ids.numel() == 0 and z.isect_ids().numel() == 0 and (z.isect_offsets == 0).all() and (z.tiles_per_gauss == 0).all()
 
 
+def test_isect_speculative_capacities(gs):
+    """rasterization() sizes the intersection stage by capacities predicted from earlier calls and reads the real totals
+    afterwards: a hit (counts fit: padded slots must not leak into the result), a miss (counts grew: exact re-run) and a
+    large over-estimate (counts shrank) must all give exactly the lists of the exact pipeline."""
+    from gsplat_b200 import ops
+
+    sc = scene.make_scene(n_max=30000)
+    W, H = 800, 448  # a tile grid no other test uses: this test owns its predictor
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    Ks = scene.rescale_K(sc["Ks"], sc["width"], sc["height"], W, H)
+    pred = ops._isect_predictor(torch.device(DEV), 2, tw, th)
+    pred.hist.clear()
+    pred.hits = pred.misses = 0
+    seen = []
+    for scale in (1.0, 1.0, 3.0, 0.4, 0.4, 1.0):
+        sc2 = dict(sc, scales=sc["scales"] * np.float32(scale))
+        radii, m2, dep, con, _ = _project_scene(sc2, W, H, Ks, C=2)
+        op = np.ascontiguousarray(np.broadcast_to(sc["opacities"][None], dep.shape))
+        a = (_t(m2), _t(radii), _t(dep))
+        kw = dict(conics=_t(con), opacities=_t(op))
+        ref = gs.isect_tiles(*a, 16, tw, th, **kw)
+        hits = ops.isect_tiles_sorted(*a, 16, tw, th, **kw)
+        assert torch.equal(hits.tiles_per_gauss, ref[0]) and torch.equal(hits.flatten_ids, ref[2])
+        assert torch.equal(hits.isect_ids(), ref[1])
+        assert torch.equal(hits.isect_offsets, gs.isect_offset_encode(ref[1], 2, tw, th))
+        seen.append((ref[1].numel(), pred.hits, pred.misses))
+    # call 1 exact, call 2 hit, call 3 (3x scales) miss, call 4 (0.4x) hit with a large over-estimate, ...
+    assert [s[1:] for s in seen] == [(0, 0), (1, 0), (1, 1), (2, 1), (3, 1), (4, 1)], seen
+    assert seen[2][0] > 1.5 * seen[0][0] and seen[0][0] > seen[3][0] > 0, seen
+
+
 def test_fused_projection_row_side_outputs(gs):
     """The fused projection's side outputs (per-row tile counts + totals, 64-byte compositing row records) must reproduce
     what the stand-alone stages compute: counts / totals bit for bit, and a forward that is BIT-identical to the one that
