@@ -519,12 +519,15 @@ def main():
             loss_host.copy_(loss.detach(), non_blocking=True)
         return meta
 
+    host_issue_ms = {}
+
     def timed(e2e: bool, steps: int) -> float:
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t_host = time.perf_counter()
         if e2e:
             for c in consumed:
                 c.record()
@@ -537,6 +540,7 @@ def main():
             for _ in range(steps):
                 step(False)
         e1.record()
+        host_issue_ms[e2e] = (time.perf_counter() - t_host) * 1e3 / steps  # host time to ISSUE a step (diagnostic)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -767,11 +771,13 @@ def main():
         line = {
             "metric": METRIC, "value": n_gpus * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+            "host_issue_ms_per_step": host_issue_ms.get(False),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(n_gpus), **({"allreduce": allreduce_kind} if n_gpus > 1 else {})),
             "e2e": {
                 "value": n_gpus * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "host_issue_ms_per_step": host_issue_ms.get(True),
                 "input": ("target image shipped as uint8 HWC from pinned memory and converted to float on the device inside "
                           "the timed region" if e2e_u8 else "target image shipped as float32 HWC from pinned memory"),
             },

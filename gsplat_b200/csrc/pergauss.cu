@@ -1923,8 +1923,11 @@ __global__ void __launch_bounds__(kThreads) isect_offsets_tilekeys_kernel(
         n_isects = totals[0]; // capacity-sized launch: the pairs past the real count are padding
     if(s >= n_isects)
         return;
-    const int64_t id   = (int64_t)keys[s];
+    // Real keys are < total_tiles.  After a capacity miss (gsb200_isect_sorted with a count above its capacity) some
+    // slots hold uninitialised pairs: the result is discarded by the caller, but no write may leave the array.
+    int64_t id         = (int64_t)keys[s];
     const int64_t prev = s > 0 ? (int64_t)keys[s - 1] : -1;
+    id                 = id < total_tiles ? id : total_tiles - 1;
     for(int64_t k = prev + 1; k <= id; ++k)
         offsets[k] = (int32_t)s;
     if(s == n_isects - 1)
