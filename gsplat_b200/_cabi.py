@@ -28,6 +28,7 @@ c_i64, c_u32, c_int, c_f32, c_vp, c_sz = (
 # name -> (restype, argtypes) ; mirrors include/gsplat_b200.h one to one
 _SIGNATURES = {
     "gsb200_version": (ctypes.c_char_p, []),
+    "gsb200_source_hash": (ctypes.c_char_p, []),
     "gsb200_error_string": (ctypes.c_char_p, [c_int]),
     "gsb200_last_cuda_error": (ctypes.c_char_p, []),
     "gsb200_bits_for_count": (c_u32, [c_i64]),

@@ -37,6 +37,21 @@ def _nvcc() -> str:
     return "nvcc"
 
 
+def source_hash() -> str:
+    """sha256 over the CUDA sources and headers the library is built from (sorted by name): compiled into the library
+    (gsb200_source_hash()) so that a shipped binary can be matched against the tree it sits in."""
+    import hashlib
+
+    h = hashlib.sha256()
+    names = sorted(UNITS) + sorted(os.path.basename(x) for x in HEADERS)
+    for name in names:
+        path = os.path.join(CSRC, name) if name != "gsplat_b200.h" else os.path.join(CSRC, "..", "..", "include", name)
+        h.update(name.encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale(target: str, deps) -> bool:
     if not os.path.exists(target):
         return True
@@ -56,6 +71,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
             jobs.append([nvcc, *ARCH, *COMMON, *extra, "-c", src, "-o", obj])
+    # the hash of ALL sources, in its own tiny unit so that it is refreshed whenever anything is rebuilt
+    stamp_src, stamp_obj = os.path.join(OBJ, "source_hash.cu"), os.path.join(OBJ, "source_hash.o")
+    digest = source_hash()
+    text = f'extern "C" const char *gsb200_source_hash(void) {{ return "{digest}"; }}\n'
+    if not os.path.exists(stamp_src) or open(stamp_src).read() != text:
+        with open(stamp_src, "w") as f:
+            f.write(text)
+    objs.append(stamp_obj)
+    if force or _stale(stamp_obj, [stamp_src]):
+        jobs.append([nvcc, *ARCH, "-O1", "-Xcompiler", "-fPIC", "-c", stamp_src, "-o", stamp_obj])
 
     def run(cmd):
         if verbose:

@@ -36,6 +36,9 @@ extern "C"
 #define GSB200_E_KEYBITS -5     /* (image, tile) id needs more than 32 key bits (csrc/Intersect.cpp:219-228) */
 
     const char *gsb200_version(void);
+    /* sha256 (hex) over the CUDA sources and headers this binary was built from (gsplat_b200/build.py: source_hash()):
+     * the built library is shipped next to its sources, this is how the two are matched. */
+    const char *gsb200_source_hash(void);
     const char *gsb200_error_string(int code);
     /* cudaGetErrorString of the last CUDA failure seen by this library on the calling thread. */
     const char *gsb200_last_cuda_error(void);

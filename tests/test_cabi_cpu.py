@@ -62,6 +62,15 @@ def test_host_only_entry_points():
 
     L = _cabi.lib()
     assert b"sm_100a" in L.gsb200_version()
+
+
+def test_shipped_binary_matches_the_sources():
+    """The built library travels with the tree as a binary (git-ignored): it carries the sha256 of the sources it was
+    compiled from, which must be the hash of the sources in this tree."""
+    from gsplat_b200 import _cabi, build
+
+    L = _cabi.lib()
+    assert L.gsb200_source_hash().decode() == build.source_hash()
     # bits_for_count known answers: /root/reference/tests/cpp/test_mathutils.cpp:53-63
     for count, bits in [(0, 0), (1, 0), (2, 1), (3, 2), (4, 2), (5, 3), (7, 3), (8, 3), (9, 4), (8160, 13)]:
         assert _cabi.bits_for_count(count) == bits
