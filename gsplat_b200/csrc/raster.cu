@@ -20,6 +20,7 @@
 #include <algorithm>
 
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 #include "rowrec.cuh"
@@ -147,21 +148,36 @@ __global__ void __launch_bounds__(256) pack_records_kernel(
 
 // pack from 64-byte row records {cull | axis | geom | color} written by the fused projection (CDIM <= 4): a pure gather,
 // four lanes per intersection, each moving one float4 -- 64 contiguous bytes read per intersection, 128 contiguous bytes
-// written per stream and warp.
+// written per stream and warp.  The id -> row -> store chain is two dependent loads long, so every thread carries
+// kPackUnroll independent chains (with one it was latency-bound: 50 us for 236 MB at S = 1.84 M).
+constexpr int kPackUnroll = 4;
 __global__ void __launch_bounds__(256) pack_rows_kernel(
     const int64_t S, const int32_t *__restrict__ flatten_ids, const float4 *__restrict__ rows, float4 *__restrict__ cull,
     float4 *__restrict__ axis, float4 *__restrict__ geom, float4 *__restrict__ color
 )
 {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t s = t >> 2;
-    if(s >= S)
-        return;
-    const int part  = (int)(t & 3);
-    const int64_t g = flatten_ids[s];
-    const float4 v  = ldg_nc_f4(rows + g * 4 + part);
-    float4 *dst     = part == 0 ? cull : (part == 1 ? axis : (part == 2 ? geom : color));
-    dst[s]          = v;
+    // a block covers kPackUnroll * 64 consecutive intersections; chain u of a thread handles intersection base + u * 64
+    const int part     = (int)(threadIdx.x & 3);
+    const int64_t base = (int64_t)blockIdx.x * (kPackUnroll * 64) + (threadIdx.x >> 2);
+    float4 *dst        = part == 0 ? cull : (part == 1 ? axis : (part == 2 ? geom : color));
+    int32_t g[kPackUnroll];
+#pragma unroll
+    for(int u = 0; u < kPackUnroll; ++u)
+    {
+        const int64_t s = base + u * 64;
+        g[u]            = s < S ? __ldg(flatten_ids + s) : 0;
+    }
+    float4 v[kPackUnroll];
+#pragma unroll
+    for(int u = 0; u < kPackUnroll; ++u)
+        v[u] = ldg_nc_f4(rows + (int64_t)g[u] * 4 + part);
+#pragma unroll
+    for(int u = 0; u < kPackUnroll; ++u)
+    {
+        const int64_t s = base + u * 64;
+        if(s < S)
+            dst[s] = v[u];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1139,6 +1155,34 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
 // ---------------------------------------------------------------------------------------------
 // record streams + tile dispatch order of one view batch (the first stage of the forward; also callable on its own,
 // gsb200_raster_pack, for bindings that rebuild the records in their backward instead of keeping them alive)
+// The tile dispatch order (one CTA, ~9 us) depends only on the offsets: it runs on a side stream next to the pack pass
+// (fork / join by events, one set per device, created on first use).
+struct SideLane
+{
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static std::mutex g_side_mu; // held from fork to join: the event pair of a device is shared by all callers
+static SideLane *side_lane()
+{
+    static SideLane lanes[64];
+    int dev = 0;
+    if(cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+        return nullptr;
+    SideLane &l = lanes[dev];
+    if(l.stream == nullptr)
+    {
+        if(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess
+           || cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess
+           || cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess)
+        {
+            l.stream = nullptr;
+            return nullptr;
+        }
+    }
+    return &l;
+}
+
 template<int CDIM>
 static int launch_pack(
     const float *means2d, const float *conics, const float *colors, const float *opacities, const int32_t *offsets,
@@ -1146,10 +1190,24 @@ static int launch_pack(
 )
 {
     RecordStreams r = carve_records(records, S, RecLayout<CDIM>::kColorVec4);
+    const bool want_order = S > 0 && n_tiles >= 2 * 148; // enough tiles for dispatch order to matter
+    std::unique_lock<std::mutex> side_lock(g_side_mu, std::defer_lock);
+    if(want_order)
+        side_lock.lock();
+    SideLane *lane = want_order ? side_lane() : nullptr;
+    if(lane != nullptr)
+    {
+        GSB_CUDA_TRY(cudaEventRecord(lane->fork, st));
+        GSB_CUDA_TRY(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
+        tile_order_kernel<<<1, 1024, 0, lane->stream>>>(offsets, (int32_t)n_tiles, (int32_t)S, r.order);
+        if(int rc = check_launch())
+            return rc;
+        GSB_CUDA_TRY(cudaEventRecord(lane->join, lane->stream));
+    }
     if(S > 0)
     {
         if(rows != nullptr && CDIM <= 4) // 64-byte row records from the fused projection: gather only
-            pack_rows_kernel<<<grid_for(S * 4, 256), 256, 0, st>>>(S, flatten_ids, rows, r.cull, r.axis, r.geom, r.color);
+            pack_rows_kernel<<<grid_for(S, kPackUnroll * 64), 256, 0, st>>>(S, flatten_ids, rows, r.cull, r.axis, r.geom, r.color);
         else
             pack_records_kernel<CDIM><<<grid_for(S, 256), 256, 0, st>>>(
                 S, flatten_ids, means2d, conics, colors, opacities, r.cull, r.axis, r.geom, r.color
@@ -1157,8 +1215,10 @@ static int launch_pack(
         if(int rc = check_launch())
             return rc;
     }
-    if(S > 0 && n_tiles >= 2 * 148)
-    { // enough tiles for dispatch order to matter
+    if(lane != nullptr)
+        GSB_CUDA_TRY(cudaStreamWaitEvent(st, lane->join, 0));
+    else if(want_order)
+    {
         tile_order_kernel<<<1, 1024, 0, st>>>(offsets, (int32_t)n_tiles, (int32_t)S, r.order);
         if(int rc = check_launch())
             return rc;

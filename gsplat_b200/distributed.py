@@ -19,6 +19,8 @@ import os
 from typing import Callable, Dict, Iterable, List, Optional, Sequence
 
 import torch
+
+from ._cabi import stream as _raw_stream
 import torch.distributed as dist
 from torch import Tensor
 
@@ -232,7 +234,7 @@ class NvlsGradArena:
             elif p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad)  # produced elsewhere (e.g. opacities): staged
             p.grad = v
-        st = torch.cuda.current_stream().cuda_stream
+        st = _raw_stream()
         pads, pad_bytes = int(self.hdl.signal_pad_ptrs_dev), int(self.hdl.signal_pad_size)
         self.last_kind = ("rows-" if sparse else "") + self.algo
         if sparse:

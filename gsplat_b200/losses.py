@@ -9,6 +9,8 @@ from __future__ import annotations
 import ctypes
 
 import torch
+
+from ._cabi import stream as _raw_stream
 from torch import Tensor
 
 from ._cabi import check, lib, ptr, require_cuda
@@ -34,7 +36,7 @@ class _L1Loss(torch.autograd.Function):
         loss = torch.empty((), device=dev, dtype=torch.float32)
         ws = torch.empty(L.gsb200_l1_loss_workspace_bytes(), device=dev, dtype=torch.uint8)
         with torch.cuda.device(dev):
-            st = torch.cuda.current_stream().cuda_stream
+            st = _raw_stream()
             check(L.gsb200_l1_loss_fwd(a.numel(), ptr(a), ptr(b), ptr(loss), ptr(ws), st), "l1_loss")
         ctx.save_for_backward(a, b)
         return loss
@@ -45,7 +47,7 @@ class _L1Loss(torch.autograd.Function):
         v_loss = v_loss.to(dtype=torch.float32).contiguous()
         v_a = torch.empty_like(a)
         with torch.cuda.device(a.device):
-            st = torch.cuda.current_stream().cuda_stream
+            st = _raw_stream()
             check(lib().gsb200_l1_loss_bwd(a.numel(), ptr(a), ptr(b), ptr(v_loss), ptr(v_a), st), "l1_loss_bwd")
         return (v_a if ctx.needs_input_grad[0] else None), (-v_a if ctx.needs_input_grad[1] else None)
 
@@ -68,7 +70,7 @@ class _SsimLoss(torch.autograd.Function):
         xs = (ctypes.c_int64 * 4)(*img1.stride())
         ys = (ctypes.c_int64 * 4)(*img2.stride())
         with torch.cuda.device(dev):
-            st = torch.cuda.current_stream().cuda_stream
+            st = _raw_stream()
             check(L.gsb200_ssim_fwd(B, C, H, W, ptr(img1), xs, ptr(img2), ys, ptr(maps), ptr(ws), ptr(loss), st), "ssim_loss")
         ctx.save_for_backward(img1, img2, maps)
         return loss
@@ -85,7 +87,7 @@ class _SsimLoss(torch.autograd.Function):
         ys = (ctypes.c_int64 * 4)(*img2.stride())
         vs = (ctypes.c_int64 * 4)(*v_x.stride())
         with torch.cuda.device(img1.device):
-            st = torch.cuda.current_stream().cuda_stream
+            st = _raw_stream()
             check(
                 lib().gsb200_ssim_bwd(B, C, H, W, ptr(img1), xs, ptr(img2), ys, ptr(maps), ptr(v_loss), ptr(v_x), vs, st),
                 "ssim_loss_bwd",

@@ -64,16 +64,22 @@ def _rows(t: Optional[Tensor], width: int, name: str) -> Tuple[Optional[Tensor],
 class _Ctx:
     """device guard + stream fetch for one operator call"""
 
+    __slots__ = ("dev", "_g")
+
     def __init__(self, dev: torch.device):
         self.dev = dev
 
     def __enter__(self):
-        self._g = torch.cuda.device(self.dev)
-        self._g.__enter__()
-        return stream()
+        idx = self.dev.index
+        if idx is None or torch._C._cuda_getDevice() != idx:  # not the current device: switch for the launches
+            self._g = torch.cuda.device(self.dev)
+            self._g.__enter__()
+            return stream()
+        self._g = None
+        return stream(idx)
 
     def __exit__(self, *a):
-        return self._g.__exit__(*a)
+        return self._g.__exit__(*a) if self._g is not None else None
 
 
 def _camera_model_id(camera_model: str) -> int:
@@ -671,7 +677,7 @@ _scratch = {}
 
 def _scratch_buffer(dev: torch.device, tag: str, nbytes: int) -> Tensor:
     """Grow-only per-device scratch (CUB temp storage).  Stream-ordered use only."""
-    key = (dev, tag, torch.cuda.current_stream(dev).cuda_stream)
+    key = (dev, tag, stream(dev.index))
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 16), device=dev, dtype=torch.uint8)
@@ -869,7 +875,7 @@ _predictors = {}
 
 
 def _isect_predictor(dev: torch.device, I: int, tile_width: int, tile_height: int) -> _IsectPredictor:
-    key = (dev.index, I, tile_width, tile_height, torch.cuda.current_stream(dev).cuda_stream)
+    key = (dev.index, I, tile_width, tile_height, stream(dev.index))
     p = _predictors.get(key)
     if p is None:
         p = _predictors[key] = _IsectPredictor(dev)

@@ -16,6 +16,8 @@ from __future__ import annotations
 
 import torch
 
+from ._cabi import stream as _raw_stream
+
 from ._cabi import check, lib, ptr
 
 _libs = []
@@ -28,7 +30,7 @@ def _geom(isect_offsets, flatten_ids, colors):
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return _raw_stream()
 
 
 def rasterize_to_pixels_3dgs(means2d, conics, colors, opacities, backgrounds, masks, image_width, image_height, tile_size,
