@@ -9,12 +9,13 @@ Workload (config.workload): BASELINE.json configs[2] -- 1 006 065 Gaussians (the
 A "step" is one pass of the hot path: rasterization() forward (fused projection + SH, tile intersection,
 radix sort, offsets, compositing) + L1 loss against a target image + backward to all five parameter
 tensors; at N > 1 every rank renders its own view of the replicated scene and the Gaussian gradients are
-all-reduced over NCCL (view-axis data parallelism, weak scaling).  The optimizer is outside the path.
+all-reduced over NVLink by the library's own row-sparse kernel (NCCL where there is no symmetric memory; view-axis
+data parallelism, weak scaling).  The optimizer is outside the path.
 
 Printed line (rank 0): metric = rendered views/s (fwd+bwd), ms_per_step = train-step ms,
 value = device-resident timing, e2e = same step with the per-step host->device copy of the camera and
-the target image from pinned memory (double-buffered on a copy stream) and the device->host read of the
-loss inside the timed region.
+the target image (uint8 HWC, converted on the device inside the timed region) from pinned memory, double-buffered on
+a copy stream, and the device->host read of the loss inside the timed region.
 roofline = dominant kernel (compositing backward) algorithmic bytes / CUDA-event time vs the measured
 HBM peak; cpu_baseline = the CPU oracle port timed on this box's host cores.
 """
@@ -743,13 +744,13 @@ def main():
         "required, pair throughput below is the meaningful figure",
         "raster_fwd": {"ms": ms_rfwd, "achieved": bytes_fwd / (ms_rfwd * 1e-3) / 1e9, "algorithmic_bytes": bytes_fwd},
         # compute-side figure: candidate (pixel, gaussian) pairs = 256 per (tile, gaussian)
-        # intersection; the kernels are instruction-issue bound (profiles/r02_v1_ncu.md: 77 % / 85 % issue-active)
+        # intersection; the kernels are instruction-issue bound (profiles/r02_v7_ncu.md: 77 % / 93 % issue-active)
         "pairs": {
             "candidate_pairs": 256 * S,
             "bwd_gpairs_per_s": 256 * S / (ms_rbwd * 1e-3) / 1e9,
             "fwd_gpairs_per_s": 256 * S / (ms_rfwd * 1e-3) / 1e9,
             "issue_peak_ginst_per_s": 148 * 4 * 1.965,
-            "issue_evidence": "profiles/r02_v1_ncu.md (smsp__issue_active, smsp__inst_executed: 413 M backward, 238 M forward)",
+            "issue_evidence": "profiles/r02_v7_ncu.md (smsp__issue_active 77 % / 93 %, smsp__inst_executed: 418 M backward, 251 M forward)",
         },
     }
 
@@ -781,11 +782,11 @@ def main():
                 "input": ("target image shipped as uint8 HWC from pinned memory and converted to float on the device inside "
                           "the timed region" if e2e_u8 else "target image shipped as float32 HWC from pinned memory"),
             },
-            # our own kernels per step (profiles/r02_v1_launches.csv): project_sh_fwd, isect_count_totals, depth_key_rows,
-            # isect_emit_coop, isect_offsets, pack_records, tile_order, raster_fwd, l1 partial/final/bwd, raster_bwd2,
-            # project_sh_bwd (= 13; the cub select / scan / radix-sort launches made by the library are not counted);
-            # timed region = `steps` device-resident + `steps` e2e steps
-            "gpu_launches": args.steps * 2 * (13 + (1 if arena is not None else 0)),
+            # our own kernels per step (profiles/r02_v7_launches.csv): project_sh_fwd (+ tile counts + row records),
+            # depth_key_rows_bounded, isect_emit_coop, isect_offsets_tilekeys, pack_rows, tile_order, raster_fwd,
+            # l1 partial/final/bwd, raster_bwd2, project_sh_bwd (= 12; the cub select / scan / radix-sort launches made by
+            # the library are not counted); timed region = `steps` device-resident + `steps` e2e steps
+            "gpu_launches": args.steps * 2 * (12 + (1 if arena is not None else 0)),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "ref_cuda_stock": ref_stock,
             "ref_cuda": ref_cuda, "big_s": big_s, "trainer": trainer, "dp": dp_info,
         }

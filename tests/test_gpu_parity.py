@@ -923,7 +923,9 @@ def test_distributed_two_ranks_sharded():
 def test_nvls_allreduce_two_ranks():
     """Own all-reduce kernels (multimem + peer-to-peer) vs NCCL, bit-exact at 2 ranks (skipped on a 1-GPU box)."""
     out = _torchrun2("dist_nvls_check.py", 29590)
-    assert out.count("nvls check ok") == 7
+    # dense multicast / peer kernels at two grid sizes, the two row-sparse variants, the end-to-end fused backward
+    assert "AssertionError" not in out and out.count("nvls check ok") >= 9, out[-2000:]
+    assert "rows-p2p moved" in out and "rows-nvls moved" in out and "end-to-end gradients in the arena" in out
 
 
 def test_selective_adam(gs):
