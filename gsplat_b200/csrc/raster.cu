@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd_kernel(
         if(bg)
             bg_dot += bg[k] * v_render_c[k];
     }
-    const float v_render_a       = inside ? v_render_alphas[pix] : 0.f;
+    const float v_render_a       = (inside && v_render_alphas != nullptr) ? v_render_alphas[pix] : 0.f; // null: no gradient on alpha
     const int32_t bin_final      = inside ? last_ids[pix] : -1;
     const int32_t warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
 
@@ -866,7 +866,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) raster_bwd2_kernel(
         if(bg && k < CDIM)
             bg_dot += bg[k] * v_render_c[k];
     }
-    const float v_render_a       = inside ? v_render_alphas[pix] : 0.f;
+    const float v_render_a       = (inside && v_render_alphas != nullptr) ? v_render_alphas[pix] : 0.f; // null: no gradient on alpha
     const int32_t bin_final      = inside ? last_ids[pix] : -1;
     const int32_t warp_bin_final = __reduce_max_sync(0xffffffffu, bin_final);
 
@@ -1523,7 +1523,7 @@ extern "C" int gsb200_raster_bwd(
         return GSB200_E_UNSUPPORTED;
     if(n_isects == 0 || I == 0)
         return GSB200_OK;
-    if(!offsets || !flatten_ids || !records || !render_alphas || !last_ids || !v_render_colors || !v_render_alphas
+    if(!offsets || !flatten_ids || !records || !render_alphas || !last_ids || !v_render_colors
        || !v_means2d || !v_conics || !v_colors || !v_opacities)
         return GSB200_E_INVALID;
     {   // the kernels address gradient rows with 32-bit element offsets

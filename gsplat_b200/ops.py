@@ -597,6 +597,7 @@ class _ProjectSH(torch.autograd.Function):
         ctx.save_for_backward(means, quats, scales, sh_coeffs, viewmats, Ks, radii, conics, comps, colors)
         ctx.meta = (width, height, eps2d, sh_degree)
         ctx.mark_non_differentiable(radii)
+        ctx.set_materialize_grads(False)  # no zero tensors for radii / depths / compensations nobody differentiated
         return radii, means2d, depths, conics, colors, comps
 
     @staticmethod
@@ -1089,6 +1090,7 @@ class _RasterizeToPixels(torch.autograd.Function):
                     "rasterize_to_pixels_3dgs",
                 )
         ctx.save_for_backward(backgrounds, m8, offsets, fl, records, render_alphas, last_ids)
+        ctx.set_materialize_grads(False)
         ctx.absgrad_holder = absgrad_holder  # filled in place by backward; deliberately not a saved tensor
         ctx.meta = (row_dims, I, N, R, D, width, height, tile_size, tw, th, S)
         return render_colors, render_alphas
@@ -1099,8 +1101,12 @@ class _RasterizeToPixels(torch.autograd.Function):
         absgrad_holder = ctx.absgrad_holder
         row_dims, I, N, R, D, width, height, tile_size, tw, th, S = ctx.meta
         dev = render_alphas.device
+        # set_materialize_grads(False): an output the loss does not use arrives as None instead of a zero-filled tensor
+        # (render_alphas in a plain photometric loss: 8 MB of zeros per 1080p step); the kernel takes a null pointer for it
+        if v_render_colors is None:
+            v_render_colors = torch.zeros(render_alphas.shape[:-1] + (D,), device=dev, dtype=torch.float32)
         v_render_colors = v_render_colors.contiguous()
-        v_render_alphas = v_render_alphas.contiguous()
+        v_render_alphas = v_render_alphas.contiguous() if v_render_alphas is not None else None
         absgrad = absgrad_holder is not None
         P = _grad_record_width(D, absgrad)
         # one packed gradient record per gaussian: [v_xy 2 | v_conic 3 | v_opacity 1 | v_rgb D | (abs 2) | pad]

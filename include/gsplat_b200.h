@@ -333,7 +333,7 @@ extern "C"
     );
     /* Gradient outputs are ACCUMULATED into (caller zero-initialises): each is addressed as
      * ptr[g * stride + k], g in [0, I*N), so they may be views into one packed record per gaussian.
-     * v_means2d_abs may be NULL (absgrad off). */
+     * v_means2d_abs may be NULL (absgrad off); v_render_alphas may be NULL (no gradient flows into render_alphas). */
     int gsb200_raster_bwd(
         int64_t I, int64_t N, int D, const float *backgrounds, const uint8_t *masks, uint32_t image_width,
         uint32_t image_height, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, const int32_t *offsets,
