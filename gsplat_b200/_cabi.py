@@ -109,6 +109,7 @@ _SIGNATURES = {
         c_int,
         [c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_u32, c_u32, c_u32, c_u32, c_u32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp],
     ),
+    "gsb200_publish_totals": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "gsb200_isect_sorted_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_i64, c_int, c_u32, c_u32]),
     "gsb200_isect_sorted": (
         c_int,

@@ -514,3 +514,29 @@ extern "C" int gsb200_isect_sorted(
         return rc;
     return gsb::offsets_tilekeys_bounded(cap_isects, key_bytes, tile_keys, total_tiles, offsets, totals, st);
 }
+
+// ---- the totals, published straight into pinned host memory.  A cudaMemcpyAsync of 24 bytes takes a copy engine and,
+// on a box whose PCIe link is busy with an image upload, arrives late; a handful of system-scope stores from a kernel do
+// not.  host_mapped: int64 [4] in pinned (mapped) host memory; the host polls host_mapped[3] for `seq`.
+namespace gsb
+{
+__global__ void publish_totals_kernel(const int64_t *__restrict__ totals, volatile int64_t *host, int64_t seq)
+{
+    if(threadIdx.x < 3)
+        host[threadIdx.x] = totals[threadIdx.x];
+    __threadfence_system();
+    __syncwarp();
+    if(threadIdx.x == 0)
+        host[3] = seq;
+}
+} // namespace gsb
+
+extern "C" int gsb200_publish_totals(const int64_t *totals, int64_t *host_mapped, int64_t seq, void *stream)
+{
+    if(!totals || !host_mapped)
+        return GSB200_E_INVALID;
+    void *dptr = nullptr;
+    GSB_CUDA_TRY(cudaHostGetDevicePointer(&dptr, host_mapped, 0));
+    gsb::publish_totals_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(totals, static_cast<volatile int64_t *>(dptr), seq);
+    return gsb::check_launch();
+}

@@ -840,9 +840,10 @@ class _IsectPredictor:
     def __init__(self, dev: torch.device):
         self.hist = []  # (n_isects, n_vis, max_tiles) of the last 8 calls
         self.hits = self.misses = 0
-        self.pinned = torch.empty(3, dtype=torch.int64).pin_memory()
-        self.side = torch.cuda.Stream(device=dev)
-        self.ready, self.done = torch.cuda.Event(), torch.cuda.Event()
+        self.pinned = torch.zeros(4, dtype=torch.int64).pin_memory()  # totals[3] + sequence word, written by the GPU
+        self.words = self.pinned.numpy()  # same memory: what the host polls
+        self.seq = 0
+        self.zero_copy, self.copied, self.copy_done = True, None, None
         self.dev = dev
 
     def capacities(self, total_rows: int):
@@ -860,16 +861,35 @@ class _IsectPredictor:
         self.hist.append((n_isects, n_vis, max_tiles))
         del self.hist[:-8]
 
-    def stage(self, totals: Tensor):
-        self.ready.record(torch.cuda.current_stream(self.dev))
-        self.side.wait_event(self.ready)
-        with torch.cuda.stream(self.side):
-            self.pinned.copy_(totals, non_blocking=True)
-            self.done.record(self.side)
+    def stage(self, totals: Tensor, st: int):
+        """Queues, right behind the kernel that produced them, a one-warp kernel that stores the totals and then a
+        sequence number into pinned host memory (no copy engine, no event)."""
+        self.seq += 1
+        self.copied = None
+        if self.zero_copy:
+            rc = lib().gsb200_publish_totals(ptr(totals), self.pinned.data_ptr(), self.seq, st)
+            if rc == 0:
+                return
+            self.zero_copy = False  # pinned memory not device-mapped on this system: plain asynchronous copy from now on
+        self.copied = torch.empty(3, dtype=torch.int64).pin_memory()
+        self.copied.copy_(totals, non_blocking=True)
+        self.copy_done = torch.cuda.Event()
+        self.copy_done.record(torch.cuda.current_stream(self.dev))
 
     def read(self):
-        self.done.synchronize()  # `totals` stays referenced by the caller until here
-        return tuple(int(v) for v in self.pinned.tolist())
+        """Polls the sequence word; the stores before it are ordered by the kernel's system-scope fence."""
+        if self.copied is not None:
+            self.copy_done.synchronize()
+            return tuple(int(v) for v in self.copied.tolist())
+        words, seq = self.words, self.seq
+        spins = 0
+        while int(words[3]) != seq:
+            spins += 1
+            if spins % 4_000_000 == 0:  # seconds without progress: surface a device-side failure instead of hanging
+                torch.cuda.synchronize(self.dev)
+                if int(words[3]) != seq:
+                    raise RuntimeError("intersect_tile: the totals never arrived from the device")
+        return int(words[0]), int(words[1]), int(words[2])
 
 
 _predictors = {}
@@ -993,7 +1013,7 @@ def isect_tiles_sorted(
             # Launch on PREDICTED capacities, then read the totals: the host read (the reference's one sync of the forward,
             # csrc/Intersect.cpp:259) overlaps the queued stage instead of idling the GPU.  A miss (a count above its
             # capacity) costs one exact re-run; nothing is ever written past a capacity.
-            pred.stage(totals)
+            pred.stage(totals, st)
             keys_out, vals_out = run(*caps)
             n_isects, n_vis, max_tiles = pred.read()
             pred.observe(n_isects, n_vis, max_tiles)

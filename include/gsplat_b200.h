@@ -286,6 +286,10 @@ extern "C"
         int key_bytes, void *tile_keys, int32_t *flatten_ids, int32_t *offsets, void *workspace, size_t workspace_bytes,
         void *stream
     );
+    /* Publishes totals (int64 [3], device) into host_mapped (int64 [4], pinned / mapped host memory) with system-scope
+     * stores from a one-warp kernel, then writes seq into host_mapped[3]: the host polls that word instead of waiting for
+     * a copy (which takes a copy engine and queues behind PCIe uploads). */
+    int gsb200_publish_totals(const int64_t *totals, int64_t *host_mapped, int64_t seq, void *stream);
     /* Stable radix sort of (isect_ids, flatten_ids) on key bits [begin_bit, end_bit)
      * (cub::DeviceRadixSort::SortPairs, csrc/IntersectTile.cu:1078-1121); begin_bit = 32 after pass 0. */
     size_t gsb200_sort_workspace_bytes(int64_t n_isects, int begin_bit, int end_bit);
