@@ -782,11 +782,11 @@ def main():
                 "input": ("target image shipped as uint8 HWC from pinned memory and converted to float on the device inside "
                           "the timed region" if e2e_u8 else "target image shipped as float32 HWC from pinned memory"),
             },
-            # our own kernels per step (profiles/r02_v7_launches.csv): project_sh_fwd (+ tile counts + row records),
-            # depth_key_rows_bounded, isect_emit_coop, isect_offsets_tilekeys, pack_rows, tile_order, raster_fwd,
-            # l1 partial/final/bwd, raster_bwd2, project_sh_bwd (= 12; the cub select / scan / radix-sort launches made by
-            # the library are not counted); timed region = `steps` device-resident + `steps` e2e steps
-            "gpu_launches": args.steps * 2 * (12 + (1 if arena is not None else 0)),
+            # our own kernels per step (profiles/r02_v9_launches.csv): project_sh_fwd (+ tile counts + row records),
+            # publish_totals, depth_key_rows_bounded, isect_emit_coop, isect_offsets_tilekeys, pack_rows, tile_order,
+            # raster_fwd, l1 partial/final/bwd, raster_bwd2, project_sh_bwd (= 13; the cub select / scan / radix-sort launches
+            # made by the library are not counted); timed region = `steps` device-resident + `steps` e2e steps
+            "gpu_launches": args.steps * 2 * (13 + (1 if arena is not None else 0)),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "ref_cuda_stock": ref_stock,
             "ref_cuda": ref_cuda, "big_s": big_s, "trainer": trainer, "dp": dp_info,
         }
