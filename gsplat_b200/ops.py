@@ -835,7 +835,7 @@ _SPECULATE = __import__("os").environ.get("GSB200_ISECT_SPECULATE", "1") != "0"
 
 class _IsectPredictor:
     """Capacities for gsb200_isect_sorted from the totals of the last calls on the same (device, image count, tile grid),
-    and the asynchronous host read of the current totals (side stream -> pinned memory)."""
+    and the asynchronous host read of the current totals (a kernel stores them into pinned memory, the host polls)."""
 
     def __init__(self, dev: torch.device):
         self.hist = []  # (n_isects, n_vis, max_tiles) of the last 8 calls
