@@ -536,7 +536,11 @@ extern "C" int gsb200_publish_totals(const int64_t *totals, int64_t *host_mapped
     if(!totals || !host_mapped)
         return GSB200_E_INVALID;
     void *dptr = nullptr;
-    GSB_CUDA_TRY(cudaHostGetDevicePointer(&dptr, host_mapped, 0));
+    if(cudaHostGetDevicePointer(&dptr, host_mapped, 0) != cudaSuccess || dptr == nullptr)
+    {
+        (void)cudaGetLastError(); // not mapped for this device: clear the error, the caller falls back to a copy
+        return GSB200_E_UNSUPPORTED;
+    }
     gsb::publish_totals_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(totals, static_cast<volatile int64_t *>(dptr), seq);
     return gsb::check_launch();
 }
