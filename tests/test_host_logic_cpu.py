@@ -51,3 +51,39 @@ def test_isect_capacity_prediction():
     q = _predictor()
     q.observe(0, 0, 0)
     assert q.capacities(1000) is None
+
+
+def test_capacity_padding_model():
+    """numpy model of the capacity-sized intersection stage (sort.cu: gsb200_isect_sorted): padding pairs carry the largest
+    key and sit behind the real pairs, the stable sort only looks at the low `end_bit` bits, and the offsets kernel reads the
+    first totals[0] sorted keys -- the result must equal the exact pipeline's, also when the number of (image, tile) cells is a
+    power of two (the padding key then aliases the last real cell) and when a miss leaves garbage keys in the list."""
+    import numpy as np
+
+    def offsets_of(sorted_keys, n_real, total_tiles):
+        off = np.zeros(total_tiles, np.int64)
+        for s in range(n_real):  # isect_offsets_tilekeys_kernel, one iteration per thread
+            ident = min(int(sorted_keys[s]), total_tiles - 1)
+            prev = int(sorted_keys[s - 1]) if s > 0 else -1
+            off[prev + 1 : ident + 1] = s
+            if s == n_real - 1:
+                off[ident + 1 :] = n_real
+        return off
+
+    rng = np.random.RandomState(3)
+    for total_tiles in (4096, 2800, 1):
+        end_bit = max(1, int(total_tiles - 1).bit_length())
+        n_real, cap = 5000, 5600
+        keys = rng.randint(0, total_tiles, n_real).astype(np.uint16)
+        rows = np.arange(n_real, dtype=np.int32)  # emission order = depth order
+        padded = np.concatenate([keys, np.full(cap - n_real, 0xFFFF, np.uint16)])
+        prow = np.concatenate([rows, np.zeros(cap - n_real, np.int32)])
+        order = np.argsort(padded & ((1 << end_bit) - 1), kind="stable")  # LSD radix sort on bits [0, end_bit)
+        exact = np.argsort(keys, kind="stable")
+        assert np.array_equal(prow[order][:n_real], rows[exact]) and np.array_equal(padded[order][:n_real], keys[exact])
+        want = np.searchsorted(keys[exact], np.arange(total_tiles), side="left")
+        assert np.array_equal(offsets_of(padded[order], n_real, total_tiles), want)
+    # after a miss some slots hold uninitialised keys: every write must still land inside the array
+    garbage = rng.randint(0, 65536, 300).astype(np.uint16)
+    off = offsets_of(garbage, 300, 2800)
+    assert off.shape == (2800,) and off.min() >= 0 and off.max() <= 300
